@@ -1,0 +1,284 @@
+"""Generate tests/golden/*.npz from the UNMODIFIED reference (build container only).
+
+    python tests/golden/make_golden.py
+
+Imports /root/reference read-only through oracle/ref_shim.py (torch_scatter / ase stubs),
+runs the reference modules on small seeded inputs and freezes inputs, weights
+(state_dict), outputs and autograd gradients.  The reference has no golden vectors of
+its own; these fixtures are what pins the oracle -- and through it
+the CUDA path -- to the reference's behaviour.  The fixtures travel to the GPU box; the
+reference does not.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.abspath(os.path.join(HERE, "..", "..")))
+
+from oracle import ref_shim  # noqa: E402
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def _sym_edges(n, p, gen):
+    """random symmetric directed edge list in make_directed() layout: [i<j half ; flipped half]."""
+    iu = torch.triu_indices(n, n, 1)
+    keep = torch.rand(iu.shape[1], generator=gen) < p
+    half = iu[:, keep].t().contiguous()
+    return half  # undirected (j > i), sorted row-major like get_neighbor_list
+
+
+def _save(name, store):
+    path = os.path.join(HERE, name)
+    np.savez_compressed(path, **store)
+    print("wrote", path, "%.1f KB" % (os.path.getsize(path) / 1024))
+
+
+def _state(prefix, module, store):
+    for k, v in module.state_dict().items():
+        store["%s/P/%s" % (prefix, k)] = _np(v)
+
+
+def _grads(prefix, module, store):
+    for k, p in module.named_parameters():
+        if p.grad is not None:
+            store["%s/G/%s" % (prefix, k)] = _np(p.grad)
+
+
+def blocks(ref_conv):
+    gen = torch.Generator().manual_seed(7)
+    F, R, N, cutoff = 16, 4, 11, 4.0
+    store = {"meta/F": F, "meta/R": R, "meta/N": N, "meta/cutoff": cutoff}
+    xyz = torch.randn(N, 3, generator=gen) * 1.5
+    half = _sym_edges(N, 0.6, gen)
+    nbrs, _ = ref_conv.make_directed(half)
+    r = xyz[nbrs[:, 1]] - xyz[nbrs[:, 0]]
+    store["in/xyz"], store["in/half"], store["in/nbrs"], store["in/r"] = map(_np, (xyz, half, nbrs, r))
+
+    def rnd(*shape):
+        return torch.randn(*shape, generator=gen)
+
+    torch.manual_seed(11)
+    # --- EquiMessageBlock (K=3) and EquiMessageCross (K=4) ---------------------------------
+    for tag, cls in (("k3", ref_conv.EquiMessageBlock), ("k4", ref_conv.EquiMessageCross)):
+        blk = cls(feat_dim=F, activation="swish", n_rbf=R, cutoff=cutoff, dropout=0.0)
+        for p in blk.parameters():          # biases are zero-initialised: make them matter
+            if p.dim() == 1:
+                p.data.normal_(0, 0.3, generator=gen)
+        s = rnd(N, F).requires_grad_()
+        v = rnd(N, F, 3).requires_grad_()
+        ds, dv = blk(s, v, r, nbrs)
+        gs, gv = rnd(N, F), rnd(N, F, 3)
+        ((ds * gs).sum() + (dv * gv).sum()).backward()
+        _state(tag, blk, store)
+        _grads(tag, blk, store)
+        for k, t in (("s", s), ("v", v), ("ds", ds), ("dv", dv), ("gs", gs), ("gv", gv),
+                     ("grad_s", s.grad), ("grad_v", v.grad)):
+            store["%s/%s" % (tag, k)] = _np(t)
+    # edge-weighted variant of K=3 (diffpool caller, conv.py:528-533)
+    blk = ref_conv.EquiMessageBlock(feat_dim=F, activation="swish", n_rbf=R, cutoff=cutoff, dropout=0.0)
+    s, v, w = rnd(N, F), rnd(N, F, 3), torch.rand(nbrs.shape[0], generator=gen)
+    ds, dv = blk(s, v, r, nbrs, edge_wgt=w)
+    _state("k3w", blk, store)
+    for k, t in (("s", s), ("v", v), ("w", w), ("ds", ds), ("dv", dv)):
+        store["k3w/%s" % k] = _np(t)
+    # --- EquiMessagePsuedo (K=9) --------------------------------------------------------------
+    blk = ref_conv.EquiMessagePsuedo(feat_dim=F, activation="swish", n_rbf=R, cutoff=cutoff, dropout=0.0)
+    for p in blk.parameters():
+        if p.dim() == 1:
+            p.data.normal_(0, 0.3, generator=gen)
+    ins = [rnd(N, F).requires_grad_(), rnd(N, F).requires_grad_(),
+           rnd(N, F, 3).requires_grad_(), rnd(N, F, 3).requires_grad_()]
+    outs = blk(ins[0], ins[1], ins[2], ins[3], r, nbrs)
+    gouts = [rnd(*o.shape) for o in outs]
+    sum((o * g).sum() for o, g in zip(outs, gouts)).backward()
+    _state("k9", blk, store)
+    _grads("k9", blk, store)
+    for k, t in zip(("s", "sbar", "v", "vbar"), ins):
+        store["k9/%s" % k] = _np(t)
+        store["k9/grad_%s" % k] = _np(t.grad)
+    for k, t, g in zip(("ds", "dsbar", "dv", "dvbar"), outs, gouts):
+        store["k9/%s" % k] = _np(t)
+        store["k9/g_%s" % k] = _np(g)
+    # --- UpdateBlock ---------------------------------------------------------------------------
+    blk = ref_conv.UpdateBlock(feat_dim=F, activation="swish", dropout=0.0)
+    for p in blk.parameters():
+        if p.dim() == 1:
+            p.data.normal_(0, 0.3, generator=gen)
+    s = rnd(N, F).requires_grad_()
+    v = rnd(N, F, 3).requires_grad_()
+    ds, dv = blk(s, v)
+    gs, gv = rnd(N, F), rnd(N, F, 3)
+    ((ds * gs).sum() + (dv * gv).sum()).backward()
+    _state("upd", blk, store)
+    _grads("upd", blk, store)
+    for k, t in (("s", s), ("v", v), ("ds", ds), ("dv", dv), ("gs", gs), ("gv", gv),
+                 ("grad_s", s.grad), ("grad_v", v.grad)):
+        store["upd/%s" % k] = _np(t)
+    # --- ContractiveMessageBlock ---------------------------------------------------------------
+    blk = ref_conv.ContractiveMessageBlock(feat_dim=F, activation="swish", n_rbf=R, cutoff=20.0, dropout=0.0)
+    for p in blk.parameters():
+        if p.dim() == 1:
+            p.data.normal_(0, 0.3, generator=gen)
+    mapping = torch.tensor([0, 0, 1, 0, 2, 2, 1, 1, 2, 0, 1])
+    cg_xyz = torch.stack([xyz[mapping == b].mean(0) for b in range(3)])
+    r_iI = xyz - cg_xyz[mapping]
+    s = rnd(N, F).requires_grad_()
+    v = rnd(N, F, 3).requires_grad_()
+    dS, dV = blk(s, v, r_iI, mapping)
+    gS, gV = rnd(*dS.shape), rnd(*dV.shape)
+    ((dS * gS).sum() + (dV * gV).sum()).backward()
+    _state("con", blk, store)
+    _grads("con", blk, store)
+    for k, t in (("s", s), ("v", v), ("r_iI", r_iI), ("mapping", mapping), ("dS", dS), ("dV", dV),
+                 ("gS", gS), ("gV", gV), ("grad_s", s.grad), ("grad_v", v.grad)):
+        store["con/%s" % k] = _np(t)
+    _save("blocks_small.npz", store)
+
+
+def _molecule_batch(ref_data, gen, n_conf, n_atoms, mapping, atom_cutoff, cg_cutoff, spread):
+    samples = []
+    n_cg = int(mapping.max()) + 1
+    for _ in range(n_conf):
+        xyz = torch.randn(n_atoms, 3, generator=gen) * spread
+        z = torch.randint(1, 9, (n_atoms,), generator=gen).float()
+        cg_xyz = torch.stack([xyz[mapping == b].mean(0) for b in range(n_cg)])
+        nbr = ref_data.get_neighbor_list(xyz, "cpu", atom_cutoff, True)
+        cg_nbr = ref_data.get_neighbor_list(cg_xyz, "cpu", cg_cutoff, True)
+        bonds = torch.stack([torch.arange(n_atoms - 1), torch.arange(1, n_atoms)], 1)
+        samples.append({
+            "nxyz": torch.cat([z[:, None], xyz], 1),
+            "CG_nxyz": torch.cat([torch.arange(n_cg).float()[:, None], cg_xyz], 1),
+            "CG_mapping": mapping.clone(), "nbr_list": nbr, "CG_nbr_list": cg_nbr,
+            "bond_edge_list": bonds, "num_atoms": torch.tensor(n_atoms), "num_CGs": torch.tensor(n_cg),
+        })
+    return ref_data.CG_collate(samples)
+
+
+def cgvae_small(ref_cgvae, ref_data):
+    from torch import nn
+    gen = torch.Generator().manual_seed(21)
+    F, R, enc, dec = 24, 5, 2, 2
+    atom_cutoff, cg_cutoff = 3.5, 6.0
+    mapping = torch.tensor([0, 0, 0, 1, 1, 2, 2, 2, 2])
+    store = {}
+    for tag, breaksym in (("vae_sym", True), ("vae_nosym", False)):
+        batch = _molecule_batch(ref_data, gen, 3, 9, mapping, atom_cutoff, cg_cutoff, 1.4)
+        torch.manual_seed(123)
+        dec_net = ref_cgvae.EquivariantPsuedoDecoder(n_atom_basis=F, n_rbf=R, cutoff=atom_cutoff,
+                                                     num_conv=dec, activation="swish", breaksym=breaksym)
+        enc_net = ref_cgvae.EquiEncoder(n_conv=enc, n_atom_basis=F, n_rbf=R, cutoff=cg_cutoff,
+                                        activation="swish", cg_mp=False, dir_mp=False)
+        prior = ref_cgvae.CGprior(n_conv=enc, n_atom_basis=F, n_rbf=R, cutoff=cg_cutoff,
+                                  activation="swish", dir_mp=False)
+        mu_net = nn.Sequential(nn.Linear(F, F), nn.ReLU(), nn.Linear(F, F))
+        sg_net = nn.Sequential(nn.Linear(F, F), nn.ReLU(), nn.Linear(F, F))
+        model = ref_cgvae.CGequiVAE(enc_net, dec_net, mu_net, sg_net, 3, feature_dim=F, prior_net=prior,
+                                    det=False, equivariant=True)
+        # reparametrize draws torch.randn_like(sigma): reseed right before forward and
+        # regenerate the same eps afterwards (same generator state, same shape).
+        torch.manual_seed(999)
+        mu, sigma, pmu, pstd, xyz, xyz_recon = model(batch)
+        torch.manual_seed(999)
+        eps = torch.randn_like(sigma)
+        recon = (xyz_recon - xyz).pow(2).mean()
+        kl = 0.5 * ((sigma.pow(2) / pstd.pow(2)).sum(-1) + ((mu - pmu).pow(2) / pstd).sum(-1)
+                    + torch.log(pstd.pow(2)).sum(-1) - torch.log(sigma.pow(2)).sum(-1) - sigma.shape[-1]).mean()
+        e = batch["bond_edge_list"]
+        gd = ((xyz_recon[e[:, 0]] - xyz_recon[e[:, 1]]).pow(2).sum(-1) + 1e-6).sqrt()
+        dd = ((xyz[e[:, 0]] - xyz[e[:, 1]]).pow(2).sum(-1) + 1e-6).sqrt()
+        gl = (gd - dd).pow(2).mean()
+        beta, gamma = 0.05, 25.0
+        loss = recon + kl * beta + gl * gamma
+        loss.backward()
+        chan = model.CG2ChannelIdx(batch["CG_mapping"])
+        _state(tag, model, store)
+        _grads(tag, model, store)
+        for k, t in batch.items():
+            store["%s/batch/%s" % (tag, k)] = _np(t)
+        for k, t in (("eps", eps), ("mu", mu), ("sigma", sigma), ("pmu", pmu), ("pstd", pstd),
+                     ("xyz_recon", xyz_recon), ("loss", loss), ("recon", recon), ("kl", kl), ("graph", gl),
+                     ("chan", chan)):
+            store["%s/%s" % (tag, k)] = _np(t)
+        store["%s/meta" % tag] = np.array([F, R, enc, dec, atom_cutoff, cg_cutoff, int(breaksym), beta, gamma])
+    _save("cgvae_small.npz", store)
+
+
+def pcn_small(ref_cgvae, ref_data):
+    gen = torch.Generator().manual_seed(33)
+    F, R, dec, cutoff = 16, 4, 2, 9.0
+    n_res, per = 7, 4
+    store = {}
+    for tag, cross_flag in (("pcn_cross", True), ("pcn_plain", False)):
+        ca = torch.cumsum(torch.randn(n_res, 3, generator=gen) * 2.2, 0)
+        mapping = torch.arange(n_res).repeat_interleave(per)
+        xyz = ca[mapping] + torch.randn(n_res * per, 3, generator=gen)
+        ca_idx = torch.arange(n_res) * per + 1
+        xyz[ca_idx] = ca
+        batch = {
+            "xyz": xyz, "ca_xyz": ca, "res": torch.randint(0, 20, (n_res,), generator=gen),
+            "cg_map": mapping, "bond_edge_list": torch.stack([torch.arange(n_res * per - 1),
+                                                               torch.arange(1, n_res * per)], 1),
+            "CG_nbr_list": ref_data.get_neighbor_list(ca, "cpu", cutoff, True),
+            "seq": ["A" * n_res], "ca_idx": ca_idx,
+        }
+        torch.manual_seed(5)
+        net = ref_cgvae.EquivariantDecoder(n_atom_basis=F, n_rbf=R, cutoff=cutoff, num_conv=dec,
+                                           activation="swish", cross_flag=cross_flag)
+        model = ref_cgvae.PCN(net, feature_dim=F, offset=False)
+        out = model(batch)
+        xyz_recon = out[5]
+        loss = (xyz_recon - xyz).pow(2).mean()
+        loss.backward()
+        _state(tag, model, store)
+        _grads(tag, model, store)
+        for k, t in batch.items():
+            if k != "seq":
+                store["%s/batch/%s" % (tag, k)] = _np(t)
+        store["%s/xyz_recon" % tag] = _np(xyz_recon)
+        store["%s/loss" % tag] = _np(loss)
+        store["%s/meta" % tag] = np.array([F, R, dec, cutoff, int(cross_flag)])
+    _save("pcn_small.npz", store)
+
+
+def graphs(ref_data, ref_cgvae):
+    gen = torch.Generator().manual_seed(5)
+    store = {}
+    # jittered lattice (distances cluster near the cutoff -> stresses the <= comparison) + gaussian cloud
+    g = torch.arange(7).float()
+    lat = torch.stack(torch.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3) * 1.5
+    lat = lat + (torch.rand(lat.shape, generator=gen) - 0.5) * 0.2
+    cloud = torch.randn(257, 3, generator=gen) * 3.0
+    exact = torch.stack(torch.meshgrid(g[:5], g[:5], g[:5], indexing="ij"), -1).reshape(-1, 3)  # ties at d == cutoff
+    for name, pts, cuts in (("lattice", lat, (1.5, 2.6, 4.5)), ("cloud", cloud, (0.7, 2.0, 5.0)),
+                            ("exact", exact, (1.0, 2.0, 3.0))):
+        store["%s/xyz" % name] = _np(pts)
+        for c in cuts:
+            store["%s/und_%g" % (name, c)] = _np(ref_data.get_neighbor_list(pts, "cpu", c, True))
+            store["%s/dir_%g" % (name, c)] = _np(ref_data.get_neighbor_list(pts, "cpu", c, False))
+    model = ref_cgvae.CGequiVAE.__new__(ref_cgvae.CGequiVAE)
+    for i, m in enumerate((torch.tensor([0, 0, 1, 0, 2, 2, 1, 1, 2, 0, 1]),
+                           torch.randint(0, 13, (200,), generator=gen),
+                           torch.arange(40).repeat_interleave(5),
+                           torch.tensor([3, 3, 3, 7, 7, 0]))):
+        store["chan/%d/mapping" % i] = _np(m)
+        store["chan/%d/index" % i] = _np(ref_cgvae.CGequiVAE.CG2ChannelIdx(model, m))
+    _save("graphs.npz", store)
+
+
+def main():
+    torch.set_num_threads(1)
+    ref_modules, ref_conv, ref_cgvae, ref_data = ref_shim.import_reference()
+    blocks(ref_conv)
+    cgvae_small(ref_cgvae, ref_data)
+    pcn_small(ref_cgvae, ref_data)
+    graphs(ref_data, ref_cgvae)
+
+
+if __name__ == "__main__":
+    main()
