@@ -1,0 +1,80 @@
+// Shared helpers for libcgvae_sm100.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <atomic>
+#include <algorithm>
+
+#include "../../include/cgvae_b200.h"
+
+namespace cgvae {
+
+constexpr int kNumSM = 148;  // B200: 2 dies x 74 SMs
+
+extern thread_local char g_err[512];
+extern std::atomic<unsigned long long> g_launches;
+
+inline int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+// call after every kernel launch: counts the launch and converts launch errors to a return code
+inline int launched(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail((int)e, "%s: %s", what, cudaGetErrorString(e));
+  return 0;
+}
+
+#define CGVAE_REQUIRE(cond, ...)                      \
+  do {                                                \
+    if (!(cond)) return ::cgvae::fail(-1, __VA_ARGS__); \
+  } while (0)
+
+#define CGVAE_CUDA(expr)                                                               \
+  do {                                                                                 \
+    cudaError_t _e = (expr);                                                           \
+    if (_e != cudaSuccess) return ::cgvae::fail((int)_e, "%s: %s", #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+__device__ __forceinline__ float warp_sum(float x) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  return x;
+}
+
+__device__ __forceinline__ float swish_f(float z) { return z / (1.0f + expf(-z)); }
+// d/dz [z * sigmoid(z)] = sig * (1 + z * (1 - sig))
+__device__ __forceinline__ float dswish_f(float z) {
+  float sig = 1.0f / (1.0f + expf(-z));
+  return sig * (1.0f + z * (1.0f - sig));
+}
+
+__device__ __forceinline__ float act_fwd(int act, float z) {
+  switch (act) {
+    case CGVAE_ACT_SWISH: return swish_f(z);
+    case CGVAE_ACT_RELU: return z > 0.f ? z : 0.f;
+    case CGVAE_ACT_TANH: return tanhf(z);
+    default: return z;
+  }
+}
+__device__ __forceinline__ float act_bwd(int act, float z) {
+  switch (act) {
+    case CGVAE_ACT_SWISH: return dswish_f(z);
+    case CGVAE_ACT_RELU: return z > 0.f ? 1.f : 0.f;
+    case CGVAE_ACT_TANH: { float t = tanhf(z); return 1.f - t * t; }
+    default: return 1.f;
+  }
+}
+
+}  // namespace cgvae

@@ -1,0 +1,261 @@
+// Dense fp32 contractions (node phi-MLPs, UpdateBlock mixes, weight / input gradients).
+// Round-1 implementation: register-tiled SIMT FMA kernel, three operand forms, fused epilogue
+// (bias, pre-activation copy, activation, activation-backward, residual add), deterministic
+// split-K for skinny problems (decoder graphs have 12..96 rows: weight streaming bound).
+#include "common.cuh"
+
+namespace cgvae {
+
+constexpr int BK = 16;
+
+struct Epilogue {
+  const float* bias;   // [N] or null
+  int act;             // forward activation applied to the value
+  float* z_out;        // pre-activation copy or null
+  const float* z_in;   // saved pre-activation for activation backward, or null
+  int dact;            // activation code for z_in
+  const float* add;    // residual [M][N] (ld = ldc) or null
+};
+
+__device__ __forceinline__ float apply_epilogue(const Epilogue& ep, float v, int64_t m, int64_t n, int64_t ldc) {
+  if (ep.bias) v += ep.bias[n];
+  if (ep.z_out) ep.z_out[m * ldc + n] = v;
+  v = act_fwd(ep.act, v);
+  if (ep.z_in) v *= act_bwd(ep.dact, ep.z_in[m * ldc + n]);
+  if (ep.add) v += ep.add[m * ldc + n];
+  return v;
+}
+
+// Loads a [ROWS x BK] operand tile into smem laid out as tile[k][row] (row stride ROWS+4).
+// KCONTIG: global element (row, k) at ptr[row*ld + k] ; else at ptr[k*ld + row].
+template <int ROWS, bool KCONTIG, int NTHREADS>
+struct TileLoader {
+  static constexpr int NVEC = ROWS * BK / 4;
+  static constexpr int PER_THREAD = (NVEC + NTHREADS - 1) / NTHREADS;
+  float4 reg[PER_THREAD];
+
+  __device__ __forceinline__ void fetch(const float* __restrict__ ptr, int64_t ld, int64_t row0, int64_t nrows, int64_t k0,
+                                        int64_t kend, bool vec_ok, int tid) {
+#pragma unroll
+    for (int p = 0; p < PER_THREAD; ++p) {
+      const int v = tid + p * NTHREADS;
+      float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (v < NVEC) {
+        if (KCONTIG) {
+          const int r = v / (BK / 4), kq = v % (BK / 4);
+          const int64_t row = row0 + r, k = k0 + kq * 4;
+          if (row < nrows) {
+            const float* src = ptr + row * ld + k;
+            if (vec_ok && k + 3 < kend) {
+              val = *reinterpret_cast<const float4*>(src);
+            } else {
+              if (k + 0 < kend) val.x = src[0];
+              if (k + 1 < kend) val.y = src[1];
+              if (k + 2 < kend) val.z = src[2];
+              if (k + 3 < kend) val.w = src[3];
+            }
+          }
+        } else {
+          const int kk = v / (ROWS / 4), rq = v % (ROWS / 4);
+          const int64_t k = k0 + kk, row = row0 + rq * 4;
+          if (k < kend) {
+            const float* src = ptr + k * ld + row;
+            if (vec_ok && row + 3 < nrows) {
+              val = *reinterpret_cast<const float4*>(src);
+            } else {
+              if (row + 0 < nrows) val.x = src[0];
+              if (row + 1 < nrows) val.y = src[1];
+              if (row + 2 < nrows) val.z = src[2];
+              if (row + 3 < nrows) val.w = src[3];
+            }
+          }
+        }
+      }
+      reg[p] = val;
+    }
+  }
+
+  __device__ __forceinline__ void store(float (*tile)[ROWS + 4], int tid) {
+#pragma unroll
+    for (int p = 0; p < PER_THREAD; ++p) {
+      const int v = tid + p * NTHREADS;
+      if (v < NVEC) {
+        if (KCONTIG) {
+          const int r = v / (BK / 4), kq = v % (BK / 4);
+          tile[kq * 4 + 0][r] = reg[p].x;
+          tile[kq * 4 + 1][r] = reg[p].y;
+          tile[kq * 4 + 2][r] = reg[p].z;
+          tile[kq * 4 + 3][r] = reg[p].w;
+        } else {
+          const int kk = v / (ROWS / 4), rq = v % (ROWS / 4);
+          *reinterpret_cast<float4*>(&tile[kk][rq * 4]) = reg[p];
+        }
+      }
+    }
+  }
+};
+
+// C tile BM x BN per CTA, TM x TN per thread, (BM/TM)*(BN/TN) threads.  gridDim.z = split-K factor:
+// splits > 1 write raw partial sums to `partial[z][M][N]` and the epilogue runs in splitk_reduce_kernel.
+template <int BM, int BN, int TM, int TN, bool A_KC, bool B_KC>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN)) gemm_kernel(
+    const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb, float* __restrict__ C, int64_t ldc,
+    int64_t M, int64_t N, int64_t K, int64_t k_per_split, Epilogue ep, float* __restrict__ partial, bool a_vec, bool b_vec) {
+  constexpr int NT = (BM / TM) * (BN / TN);
+  __shared__ __align__(16) float As[2][BK][BM + 4];
+  __shared__ __align__(16) float Bs[2][BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid % (BN / TN), ty = tid / (BN / TN);
+  const int64_t m0 = (int64_t)blockIdx.y * BM, n0 = (int64_t)blockIdx.x * BN;
+  const int64_t kbeg = (int64_t)blockIdx.z * k_per_split;
+  const int64_t kend = min(K, kbeg + k_per_split);
+
+  TileLoader<BM, A_KC, NT> la;
+  TileLoader<BN, B_KC, NT> lb;
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  int buf = 0;
+  if (kbeg < kend) {
+    la.fetch(A, lda, m0, M, kbeg, kend, a_vec, tid);
+    lb.fetch(B, ldb, n0, N, kbeg, kend, b_vec, tid);
+    la.store(As[0], tid);
+    lb.store(Bs[0], tid);
+  }
+  __syncthreads();
+  for (int64_t k0 = kbeg; k0 < kend; k0 += BK) {
+    const bool more = k0 + BK < kend;
+    if (more) {
+      la.fetch(A, lda, m0, M, k0 + BK, kend, a_vec, tid);
+      lb.fetch(B, ldb, n0, N, k0 + BK, kend, b_vec, tid);
+    }
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float a[TM], b[TN];
+#pragma unroll
+      for (int i = 0; i < TM; ++i) a[i] = As[buf][k][ty * TM + i];
+#pragma unroll
+      for (int j = 0; j < TN; ++j) b[j] = Bs[buf][k][tx * TN + j];
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (more) {
+      la.store(As[buf ^ 1], tid);
+      lb.store(Bs[buf ^ 1], tid);
+    }
+    __syncthreads();
+    buf ^= 1;
+  }
+
+  const bool split = gridDim.z > 1;
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int64_t m = m0 + ty * TM + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int64_t n = n0 + tx * TN + j;
+      if (n >= N) continue;
+      if (split) partial[((int64_t)blockIdx.z * M + m) * N + n] = acc[i][j];
+      else C[m * ldc + n] = apply_epilogue(ep, acc[i][j], m, n, ldc);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ partial, int splits, int64_t M, int64_t N,
+                                                            float* __restrict__ C, int64_t ldc, Epilogue ep) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * N) return;
+  const int64_t m = idx / N, n = idx % N;
+  float v = 0.f;
+  for (int s = 0; s < splits; ++s) v += partial[(int64_t)s * M * N + idx];  // fixed order: deterministic
+  C[m * ldc + n] = apply_epilogue(ep, v, m, n, ldc);
+}
+
+// column sums: out[n] = sum_m X[m][n]; one thread per column per row-chunk, two-stage, fixed order.
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X, int64_t ldx, int64_t M, int64_t N,
+                                                     float* __restrict__ out) {
+  // blockDim = (32, 8): 32 columns x 8 row-lanes
+  __shared__ float red[8][33];
+  const int64_t n = (int64_t)blockIdx.x * 32 + threadIdx.x;
+  float s = 0.f;
+  if (n < N)
+    for (int64_t m = threadIdx.y; m < M; m += 8) s += X[m * ldx + n];
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) t += red[r][threadIdx.x];
+    out[n] = t;
+  }
+}
+
+template <int BM, int BN, int TM, int TN>
+static int launch_gemm(int form, const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t M,
+                       int64_t N, int64_t K, const Epilogue& ep, float* ws, size_t ws_bytes, cudaStream_t st) {
+  constexpr int NT = (BM / TM) * (BN / TN);
+  const int64_t tiles = ceil_div(M, BM) * ceil_div(N, BN);
+  // split-K only when the output grid leaves most of the 148 SMs idle and K is deep
+  int splits = 1;
+  if (ws != nullptr && tiles < kNumSM && K >= 8 * BK) {
+    splits = (int)std::min<int64_t>(ceil_div(2 * kNumSM, tiles), K / (4 * BK));
+    const int64_t cap = (int64_t)(ws_bytes / (sizeof(float) * (size_t)(M * N)));
+    splits = (int)std::max<int64_t>(1, std::min<int64_t>(splits, cap));
+  }
+  int64_t k_per_split = ceil_div(ceil_div(K, splits), BK) * BK;
+  splits = (int)ceil_div(K, k_per_split);
+  if (splits < 1) splits = 1;
+  const bool a_kc = (form != CGVAE_GEMM_TN), b_kc = (form == CGVAE_GEMM_NT);
+  const bool a_vec = aligned16(A) && (lda % 4 == 0), b_vec = aligned16(B) && (ldb % 4 == 0);
+  dim3 grid((unsigned)ceil_div(N, BN), (unsigned)ceil_div(M, BM), (unsigned)splits);
+  float* partial = splits > 1 ? ws : nullptr;
+  if (a_kc && b_kc)
+    gemm_kernel<BM, BN, TM, TN, true, true><<<grid, NT, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, k_per_split, ep, partial, a_vec, b_vec);
+  else if (a_kc && !b_kc)
+    gemm_kernel<BM, BN, TM, TN, true, false><<<grid, NT, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, k_per_split, ep, partial, a_vec, b_vec);
+  else
+    gemm_kernel<BM, BN, TM, TN, false, false><<<grid, NT, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, k_per_split, ep, partial, a_vec, b_vec);
+  if (int rc = launched("gemm")) return rc;
+  if (splits > 1) {
+    splitk_reduce_kernel<<<(unsigned)ceil_div(M * N, 256), 256, 0, st>>>(partial, splits, M, N, C, ldc, ep);
+    return launched("gemm_splitk_reduce");
+  }
+  return 0;
+}
+
+}  // namespace cgvae
+
+using namespace cgvae;
+
+extern "C" {
+
+int cgvae_gemm(int form, const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t M, int64_t N,
+               int64_t K, const float* bias, int act, float* z_out, const float* z_in, int dact, const float* add,
+               void* ws, size_t ws_bytes, cgvae_stream_t stream) {
+  CGVAE_REQUIRE(form >= 0 && form <= 2, "gemm: bad form %d", form);
+  CGVAE_REQUIRE(M >= 0 && N >= 0 && K >= 0, "gemm: negative size");
+  if (M == 0 || N == 0) return 0;
+  CGVAE_REQUIRE(A && B && C, "gemm: null operand");
+  CGVAE_REQUIRE(ldc >= N, "gemm: ldc < N");
+  Epilogue ep{bias, act, z_out, z_in, dact, add};
+  cudaStream_t st = (cudaStream_t)stream;
+  float* wsf = reinterpret_cast<float*>(ws);
+  if (M <= 16) return launch_gemm<16, 32, 1, 2>(form, A, lda, B, ldb, C, ldc, M, N, K, ep, wsf, ws_bytes, st);
+  if (M <= 32) return launch_gemm<32, 32, 2, 2>(form, A, lda, B, ldb, C, ldc, M, N, K, ep, wsf, ws_bytes, st);
+  return launch_gemm<64, 64, 4, 4>(form, A, lda, B, ldb, C, ldc, M, N, K, ep, wsf, ws_bytes, st);
+}
+
+int cgvae_colsum(const float* X, int64_t ldx, int64_t M, int64_t N, float* out, cgvae_stream_t stream) {
+  if (N == 0) return 0;
+  CGVAE_REQUIRE(X && out, "colsum: null pointer");
+  colsum_kernel<<<(unsigned)ceil_div(N, 32), dim3(32, 8), 0, (cudaStream_t)stream>>>(X, ldx, M, N, out);
+  return launched("colsum");
+}
+
+}  // extern "C"

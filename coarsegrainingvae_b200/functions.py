@@ -1,0 +1,217 @@
+"""Autograd nodes of the hot path: every forward and every backward is a short sequence of C-ABI
+kernel launches (ops.py); PyTorch only owns memory and the tape.  Gradients flow to features and
+parameters, never to coordinates (geometry comes from data: cgvae.py:276-280).
+
+Backward formulas: SURVEY.md Appendix A (checked against the oracle's autograd in tests/).
+"""
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import ops
+
+SWISH = 1
+
+
+def _phi_forward(s, W1, b1, W2, b2, act=SWISH):
+    a1, z1 = ops.linear_fwd(s, W1, b1, act, save_pre=True)
+    phi = ops.linear_fwd(a1, W2, b2, 0)
+    return a1, z1, phi
+
+
+def _phi_backward(g_phi2d, s, a1, z1, W1, W2, add_to_gs, act=SWISH):
+    """backward of phi = Dense2(act(Dense1(s))) given g_phi [N, K*F]; returns gs (+add), gW1, gb1, gW2, gb2."""
+    gz1 = ops.linear_bwd_input(g_phi2d, W2, z_in=z1, dact=act)            # (g_phi W2) * act'(z1)
+    gW2 = ops.linear_bwd_weight(g_phi2d, a1)
+    gb2 = ops.colsum(g_phi2d)
+    gs = ops.linear_bwd_input(gz1, W1, add=add_to_gs)
+    gW1 = ops.linear_bwd_weight(gz1, s)
+    gb1 = ops.colsum(gz1)
+    return gs, gW1, gb1, gW2, gb2
+
+
+class MLP2(Function):
+    """y = Dense2(act(Dense1(x))): the phi-MLP of InvariantMessage (conv.py:41-49) and the Linear-act-Linear heads
+    (atom_munet / atom_sigmanet scripts/run_ala.py:184-185, CGprior.mu / .sigma cgvae.py:368-369)."""
+
+    @staticmethod
+    def forward(ctx, act, x, W1, b1, W2, b2):
+        x = x.contiguous()
+        a1, z1, y = _phi_forward(x, W1, b1, W2, b2, act)
+        ctx.act = act
+        ctx.save_for_backward(x, a1, z1, W1, W2)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        x, a1, z1, W1, W2 = ctx.saved_tensors
+        gx, gW1, gb1, gW2, gb2 = _phi_backward(gy.contiguous(), x, a1, z1, W1, W2, None, ctx.act)
+        return None, gx, gW1, gb1, gW2, gb2
+
+
+class MessageBlock(Function):
+    """InvariantMessage + EquiMessageBlock (n_split 3, conv.py:505-563) / EquiMessageCross (4, conv.py:358-402) /
+    ContractiveMessageBlock (3 on the atoms->beads graph, conv.py:703-733).
+
+    mode 'self'  : out = (s, v) + message   (stack use, residual of cgvae.py:287-288 fused)
+    mode 'delta' : out = message            (the reference block API)
+    mode 'other' : out = (res_s, res_v) + message, residual state on the receiver set (contraction)
+    v None means v == 0 (first layer of every stack) and skips the vector gathers.
+    """
+
+    @staticmethod
+    def forward(ctx, geom, n_split, mode, s, v, res_s, res_v, W1, b1, W2, b2, Wf, bf):
+        s = s.contiguous()
+        a1, z1, phi = _phi_forward(s, W1, b1, W2, b2)
+        N, F = s.shape
+        phi3 = phi.view(N, n_split, F)
+        if mode == "self":
+            rs, rv = s, v
+        elif mode == "other":
+            rs, rv = res_s, res_v
+        else:
+            rs, rv = None, None
+        out_s, out_v, q = ops.message_fwd(n_split, phi3, v, v if n_split == 4 else None, geom, Wf, bf, rs, rv,
+                                          want_q=(n_split == 4 and v is not None))
+        ctx.geom, ctx.n_split, ctx.mode = geom, n_split, mode
+        ctx.v_none = v is None
+        ctx.res_v_none = res_v is None
+        ctx.save_for_backward(s, v, a1, z1, phi3, q, W1, W2, Wf, bf)
+        return out_s, out_v
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_s, g_v):
+        s, v, a1, z1, phi3, q, W1, W2, Wf, bf = ctx.saved_tensors
+        g_s, g_v = g_s.contiguous(), g_v.contiguous()
+        n_split, mode = ctx.n_split, ctx.mode
+        residual = mode == "self"
+        # with v == 0 and a fused residual the sender-side pass-through still applies (v_out = 0 + dv):
+        g_phi, g_v_send, dWf, dbf = ops.message_bwd(n_split, phi3, v, v if n_split == 4 else None, q, ctx.geom, Wf, bf,
+                                                    g_s, g_v, residual and not ctx.v_none)
+        N, F = s.shape
+        gs, gW1, gb1, gW2, gb2 = _phi_backward(g_phi.view(N, n_split * F), s, a1, z1, W1, W2,
+                                               g_s if residual else None)
+        gv = None if ctx.v_none else g_v_send
+        g_res_s = g_s if mode == "other" else None
+        g_res_v = g_v if (mode == "other" and not ctx.res_v_none) else None
+        return None, None, None, gs, gv, g_res_s, g_res_v, gW1, gb1, gW2, gb2, dWf, dbf
+
+
+class Message9Block(Function):
+    """InvariantMessage (9 splits) + EquiMessagePsuedo, conv.py:180-242; residual adds of cgvae.py:108-111 fused."""
+
+    @staticmethod
+    def forward(ctx, geom, residual, s, sbar, v, vbar, W1, b1, W2, b2, Wf, bf):
+        s, sbar, v, vbar = s.contiguous(), sbar.contiguous(), v.contiguous(), vbar.contiguous()
+        a1, z1, phi = _phi_forward(s, W1, b1, W2, b2)
+        N, F = s.shape
+        phi3 = phi.view(N, 9, F)
+        outs = ops.message9_fwd(phi3, s, sbar, v, vbar, geom, Wf, bf, residual)
+        ctx.geom, ctx.residual = geom, residual
+        ctx.save_for_backward(s, sbar, v, vbar, a1, z1, phi3, W1, W2, Wf, bf)
+        return tuple(outs)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_s, g_sbar, g_v, g_vbar):
+        s, sbar, v, vbar, a1, z1, phi3, W1, W2, Wf, bf = ctx.saved_tensors
+        gi_s, gi_sbar, gi_v, gi_vbar, g_phi, dWf, dbf = ops.message9_bwd(
+            phi3, s, sbar, v, vbar, ctx.geom, Wf, bf, ctx.residual,
+            g_s.contiguous(), g_sbar.contiguous(), g_v.contiguous(), g_vbar.contiguous())
+        N, F = s.shape
+        gs, gW1, gb1, gW2, gb2 = _phi_backward(g_phi.view(N, 9 * F), s, a1, z1, W1, W2, gi_s)
+        return None, None, gs, gi_sbar, gi_v, gi_vbar, gW1, gb1, gW2, gb2, dWf, dbf
+
+
+class UpdateBlockFn(Function):
+    """UpdateBlock.forward conv.py:588-616 on planar vectors; residual of cgvae.py:122-123 optionally fused."""
+
+    @staticmethod
+    def forward(ctx, residual, s, v, U, V, A0, c0, A1, c1):
+        s, v = s.contiguous(), v.contiguous()
+        N, F = s.shape
+        v2 = v.view(3 * N, F)
+        Uv = ops.linear_fwd(v2, U, None, 0).view(N, 3, F)
+        Vv = ops.linear_fwd(v2, V, None, 0).view(N, 3, F)
+        x = ops.update_norm_fwd(s, Vv)
+        h, z = ops.linear_fwd(x, A0, c0, SWISH, save_pre=True)
+        q = ops.linear_fwd(h, A1, c1, 0).view(N, 3, F)
+        s_out, v_out = ops.update_combine_fwd(s, v, Uv, Vv, q, residual)
+        ctx.residual = residual
+        ctx.save_for_backward(v, Uv, Vv, x, h, z, q, U, V, A0, A1)
+        return s_out, v_out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_s, g_v):
+        v, Uv, Vv, x, h, z, q, U, V, A0, A1 = ctx.saved_tensors
+        g_s, g_v = g_s.contiguous(), g_v.contiguous()
+        N, _, F = v.shape
+        gq, gUv, gVv = ops.update_combine_bwd(Uv, Vv, q, g_s, g_v)
+        gq2 = gq.view(N, 3 * F)
+        gz = ops.linear_bwd_input(gq2, A1, z_in=z, dact=SWISH)
+        gA1 = ops.linear_bwd_weight(gq2, h)
+        gc1 = ops.colsum(gq2)
+        gx = ops.linear_bwd_input(gz, A0)
+        gA0 = ops.linear_bwd_weight(gz, x)
+        gc0 = ops.colsum(gz)
+        gs_in = ops.update_norm_bwd(x, Vv, gx, g_s, gVv, ctx.residual)      # adds the norm path into gVv in place
+        v2 = v.view(3 * N, F)
+        gUv2, gVv2 = gUv.view(3 * N, F), gVv.view(3 * N, F)
+        gv_in = ops.linear_bwd_input(gUv2, U, add=g_v.view(3 * N, F) if ctx.residual else None)
+        gv_in = ops.linear_bwd_input(gVv2, V, add=gv_in).view(N, 3, F)
+        gU = ops.linear_bwd_weight(gUv2, v2)
+        gV = ops.linear_bwd_weight(gVv2, v2)
+        return None, gs_in, gv_in, gU, gV, gA0, gc0, gA1, gc1
+
+
+class SegmentReduce(Function):
+    """scatter_mean / scatter_add over beads (cgvae.py:297-298): X [N,...] -> [n_beads,...]."""
+
+    @staticmethod
+    def forward(ctx, seg, mean, X):
+        ctx.seg, ctx.mean = seg, mean
+        return ops.segment_reduce_fwd(X.contiguous(), seg, mean)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        return None, None, ops.segment_reduce_bwd(g.contiguous(), ctx.seg, ctx.mean)
+
+
+class EmbeddingLookup(Function):
+    """nn.Embedding(100, F, padding_idx=0) lookup (cgvae.py:273,380,591); deterministic gradient."""
+
+    @staticmethod
+    def forward(ctx, table, idx, padding_idx):
+        idx = idx.to(torch.int64).contiguous()
+        ctx.padding_idx = padding_idx
+        ctx.n_rows = table.shape[0]
+        ctx.save_for_backward(idx)
+        return ops.gather_rows(table, idx)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        (idx,) = ctx.saved_tensors
+        seg = ops.build_segments(idx, ctx.n_rows)
+        gt = ops.segment_reduce_fwd(g.contiguous(), seg, False)
+        if ctx.padding_idx is not None:
+            gt[ctx.padding_idx].zero_()
+        return gt, None, None
+
+
+class Lift(Function):
+    """bead -> atom lifting (cgvae.py:466-482; PCN cgvae.py:556-576): V [Nc,3,F] -> xyz [N,3]."""
+
+    @staticmethod
+    def forward(ctx, seg, mode, pin, V, cg_xyz):
+        ctx.seg, ctx.mode, ctx.pin, ctx.F = seg, mode, pin, V.shape[-1]
+        return ops.lift_fwd(V.contiguous(), cg_xyz, seg, mode, pin)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        return None, None, None, ops.lift_bwd(g.contiguous(), ctx.seg, ctx.F, ctx.mode, ctx.pin), None

@@ -1,0 +1,476 @@
+"""Tensor-level wrappers over the C ABI (include/cgvae_b200.h).
+
+Every function here takes CUDA tensors, allocates outputs / scratch with torch (PyTorch owns all
+memory), and launches hand-written sm_100a kernels on the current stream through ctypes.  There is no
+CPU path: a non-CUDA tensor raises.  Layouts: scalars [N,F]; vectors planar [N,3,F]; phi [N,K,F].
+"""
+import numpy as np
+import torch
+
+from . import _lib
+
+ACT_CODES = {None: 0, "none": 0, "linear": 0, "swish": 1, "ReLU": 2, "relu": 2, "Tanh": 3, "tanh": 3}
+GEMM_NT, GEMM_NN, GEMM_TN = 0, 1, 2
+
+
+def _p(t):
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("coarsegrainingvae_b200 runs on CUDA tensors only (sm_100a kernels, no CPU fallback); "
+                               "got a %s tensor" % t.device)
+
+
+def _f32(t):
+    if t.dtype != torch.float32:
+        raise RuntimeError("expected float32, got %s" % t.dtype)
+    return t.contiguous()
+
+
+def launch_count():
+    return _lib.launch_count()
+
+
+# --------------------------------------------------------------------------------------------------
+# graphs
+# --------------------------------------------------------------------------------------------------
+
+class Graph(object):
+    """Receiver CSR + sender CSR of a directed edge list, plus cached per-edge geometry.
+
+    rowptr[n_recv+1], col[E] (sender per slot), eid[E] (original edge id per slot),
+    rowptr_t[n_send+1], col_t[E] (receiver), perm_t[E] (receiver-CSR slot of the same edge).
+    """
+
+    def __init__(self, n_recv, n_send, n_edges, rowptr, col, eid, rowptr_t, col_t, perm_t):
+        self.n_recv, self.n_send, self.n_edges = int(n_recv), int(n_send), int(n_edges)
+        self.rowptr, self.col, self.eid = rowptr, col, eid
+        self.rowptr_t, self.col_t, self.perm_t = rowptr_t, col_t, perm_t
+
+
+class Geometry(object):
+    """basis[E,RB] = [rbf*env | env | 0...], unit[E,4] = (ux,uy,uz,d) in receiver-CSR order."""
+
+    def __init__(self, graph, basis, unit, n_rbf, rb, cutoff):
+        self.graph, self.basis, self.unit = graph, basis, unit
+        self.n_rbf, self.rb, self.cutoff = int(n_rbf), int(rb), float(cutoff)
+
+
+class Segments(object):
+    """bead CSR: rowptr[n_beads+1], atoms[N] ascending per bead, slot[N], rank[N] (int64), mapping[N]."""
+
+    def __init__(self, n_beads, mapping, rowptr, atoms, slot, rank):
+        self.n_beads, self.mapping = int(n_beads), mapping
+        self.rowptr, self.atoms, self.slot, self.rank = rowptr, atoms, slot, rank
+        self.n = int(mapping.shape[0])
+
+
+def rb_for(n_rbf):
+    """padded basis width: R+1 rounded up to a multiple of 4 (float4 edge records)."""
+    rb = ((n_rbf + 1 + 3) // 4) * 4
+    if rb < 8:
+        rb = 8
+    if rb > 16:
+        raise RuntimeError("n_rbf up to 15 supported (got %d)" % n_rbf)
+    return rb
+
+
+def rbf_coefficients(n_rbf, cutoff, device):
+    """n * pi / cutoff evaluated exactly like the reference (modules.py:145,156): fp32 tensor ops."""
+    n = torch.arange(1, n_rbf + 1).float()
+    return (n * np.pi / cutoff).to(device)
+
+
+def exclusive_scan(counts_i32, out_dtype=torch.int64):
+    _need_cuda(counts_i32)
+    lib = _lib.load()
+    n = counts_i32.shape[0]
+    out = torch.empty(n + 1, dtype=out_dtype, device=counts_i32.device)
+    if out_dtype == torch.int64:
+        _lib.check(lib.cgvae_exclusive_scan(_p(counts_i32), n, _p(out), _stream()), "exclusive_scan")
+    else:
+        _lib.check(lib.cgvae_scan_i32(_p(counts_i32), n, _p(out), _stream()), "scan_i32")
+    return out
+
+
+def radius_graph(xyz, cutoff, undirected=True, frame_ptr=None, use_cells=None):
+    """get_neighbor_list (data.py:65-82) on the GPU, optionally batched over frames.
+
+    xyz [n,3] fp32 CUDA; frame_ptr int64 [n_frames+1] (defaults to one frame).  Returns int64 [E,2]
+    sorted by (i, j) -- identical, bit for bit, to the reference's per-frame lists offset and
+    concatenated by CG_collate (data.py:255-270).  One host read (the edge count).
+    """
+    _need_cuda(xyz)
+    lib = _lib.load()
+    xyz = _f32(xyz)
+    n = xyz.shape[0]
+    dev = xyz.device
+    if frame_ptr is None:
+        frame_ptr = torch.tensor([0, n], dtype=torch.int64, device=dev)
+        max_frame = n
+    else:
+        frame_ptr = frame_ptr.to(device=dev, dtype=torch.int64).contiguous()
+        max_frame = None
+    n_frames = frame_ptr.shape[0] - 1
+    if use_cells is None:
+        if max_frame is None:
+            max_frame = int((frame_ptr[1:] - frame_ptr[:-1]).max().item()) if n_frames > 0 else 0
+        use_cells = max_frame > 1024
+    if n == 0:
+        return torch.zeros((0, 2), dtype=torch.int64, device=dev)
+    ws_bytes = int(lib.cgvae_radius_graph_ws_bytes(n, n_frames)) if use_cells else 0
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+    deg = torch.empty(n, dtype=torch.int32, device=dev)
+    st = _stream()
+    _lib.check(lib.cgvae_radius_graph_count(_p(xyz), n, _p(frame_ptr), n_frames, float(np.float32(cutoff)), int(bool(undirected)),
+                                            int(bool(use_cells)), _p(deg), _p(ws), ws_bytes, st), "radius_graph_count")
+    rowptr = exclusive_scan(deg, torch.int64)
+    n_edges = int(rowptr[-1].item())
+    pairs = torch.empty((n_edges, 2), dtype=torch.int64, device=dev)
+    if n_edges:
+        _lib.check(lib.cgvae_radius_graph_fill(_p(xyz), n, _p(frame_ptr), n_frames, float(np.float32(cutoff)), int(bool(undirected)),
+                                               int(bool(use_cells)), _p(rowptr), _p(pairs), _p(ws), ws_bytes, st),
+                   "radius_graph_fill")
+    return pairs
+
+
+def edge_orientation(pairs):
+    """(any(col0 > col1), any(col1 > col0)) -- the two host reads of make_directed (conv.py:12-13)."""
+    _need_cuda(pairs)
+    lib = _lib.load()
+    flags = torch.empty(2, dtype=torch.int32, device=pairs.device)
+    pairs = pairs.contiguous()
+    _lib.check(lib.cgvae_edge_orientation(_p(pairs), pairs.shape[0], _p(flags), _stream()), "edge_orientation")
+    f = flags.tolist()
+    return bool(f[0]), bool(f[1])
+
+
+def build_graph(pairs, n_recv, n_send=None):
+    """CSR views of a directed int64 edge list [E,2] (col 0 receiver, col 1 sender)."""
+    _need_cuda(pairs)
+    lib = _lib.load()
+    if n_send is None:
+        n_send = n_recv
+    pairs = pairs.to(torch.int64).contiguous()
+    E = pairs.shape[0]
+    dev = pairs.device
+    st = _stream()
+    deg_r = torch.empty(n_recv, dtype=torch.int32, device=dev)
+    deg_s = torch.empty(n_send, dtype=torch.int32, device=dev)
+    _lib.check(lib.cgvae_csr_count(_p(pairs), E, n_recv, n_send, _p(deg_r), _p(deg_s), st), "csr_count")
+    rowptr = exclusive_scan(deg_r, torch.int32)
+    rowptr_t = exclusive_scan(deg_s, torch.int32)
+    col = torch.empty(E, dtype=torch.int32, device=dev)
+    eid = torch.empty(E, dtype=torch.int32, device=dev)
+    col_t = torch.empty(E, dtype=torch.int32, device=dev)
+    perm_t = torch.empty(E, dtype=torch.int32, device=dev)
+    scratch = torch.empty(n_recv + n_send + 2 * E + 4, dtype=torch.int32, device=dev)
+    _lib.check(lib.cgvae_csr_fill(_p(pairs), E, n_recv, n_send, _p(rowptr), _p(rowptr_t), _p(scratch), _p(col), _p(eid),
+                                  _p(col_t), _p(perm_t), st), "csr_fill")
+    return Graph(n_recv, n_send, E, rowptr, col, eid, rowptr_t, col_t, perm_t)
+
+
+def build_segments(mapping, n_beads):
+    """bead CSR + CG2ChannelIdx ranks (cgvae.py:451-460) for an int64 mapping [N]."""
+    _need_cuda(mapping)
+    lib = _lib.load()
+    mapping = mapping.to(torch.int64).contiguous()
+    n = mapping.shape[0]
+    dev = mapping.device
+    st = _stream()
+    deg = torch.empty(n_beads, dtype=torch.int32, device=dev)
+    _lib.check(lib.cgvae_segment_count(_p(mapping), n, n_beads, _p(deg), st), "segment_count")
+    rowptr = exclusive_scan(deg, torch.int32)
+    atoms = torch.empty(n, dtype=torch.int32, device=dev)
+    slot = torch.empty(n, dtype=torch.int32, device=dev)
+    rank = torch.empty(n, dtype=torch.int64, device=dev)
+    scratch = torch.empty(n_beads + 4, dtype=torch.int32, device=dev)
+    _lib.check(lib.cgvae_segment_rank(_p(mapping), n, n_beads, _p(rowptr), _p(scratch), _p(atoms), _p(slot), _p(rank), st),
+               "segment_rank")
+    return Segments(n_beads, mapping, rowptr, atoms, slot, rank)
+
+
+def contraction_graph(seg):
+    """atoms -> beads bipartite graph of ContractiveMessageBlock (conv.py:725-731): receiver = bead,
+    sender = atom; receiver CSR is the bead CSR, the sender CSR has exactly one edge per atom."""
+    dev = seg.mapping.device
+    n = seg.n
+    rowptr_t = torch.arange(n + 1, dtype=torch.int32, device=dev)
+    col_t = seg.mapping.to(torch.int32)
+    return Graph(seg.n_beads, n, n, seg.rowptr, seg.atoms, seg.atoms, rowptr_t, col_t, seg.slot)
+
+
+def edge_geometry(graph, xyz_send, xyz_recv, n_rbf, cutoff, edge_wgt=None, r_edge=None):
+    """per-edge basis / unit vectors in receiver-CSR order, from coordinates or from r_edge [E,3]
+    (original edge order)."""
+    _need_cuda(xyz_send, xyz_recv, r_edge)
+    lib = _lib.load()
+    dev = (r_edge if r_edge is not None else xyz_send).device
+    rb = rb_for(n_rbf)
+    E = graph.n_edges
+    basis = torch.empty((E, rb), dtype=torch.float32, device=dev)
+    unit = torch.empty((E, 4), dtype=torch.float32, device=dev)
+    coef = rbf_coefficients(n_rbf, cutoff, dev)
+    xs = _f32(xyz_send) if xyz_send is not None else None
+    xr = _f32(xyz_recv) if xyz_recv is not None else None
+    re = _f32(r_edge) if r_edge is not None else None
+    w = _f32(edge_wgt) if edge_wgt is not None else None
+    _lib.check(lib.cgvae_edge_geometry(_p(xs), _p(xr), _p(re), _p(graph.rowptr), _p(graph.col), graph.n_recv, E, _p(coef), n_rbf, rb,
+                                       float(np.float32(cutoff)), _p(w), _p(graph.eid), _p(basis), _p(unit), _stream()),
+               "edge_geometry")
+    return Geometry(graph, basis, unit, n_rbf, rb, cutoff)
+
+
+# --------------------------------------------------------------------------------------------------
+# dense
+# --------------------------------------------------------------------------------------------------
+
+_SPLITK_WS_BYTES = 32 << 20
+
+
+def gemm(form, A, B, M, N, K, bias=None, act=0, z_out=False, z_in=None, dact=0, add=None, out=None):
+    """C[M,N] = epilogue(op(A) op(B)); see cgvae_gemm in the header.  A, B 2-D contiguous views."""
+    _need_cuda(A, B)
+    lib = _lib.load()
+    dev = A.device
+    C = out if out is not None else torch.empty((M, N), dtype=torch.float32, device=dev)
+    Z = torch.empty((M, N), dtype=torch.float32, device=dev) if z_out else None
+    ws = torch.empty(_SPLITK_WS_BYTES, dtype=torch.uint8, device=dev) if (M <= 64 and K >= 512) else None
+    _lib.check(lib.cgvae_gemm(form, _p(A), A.stride(0), _p(B), B.stride(0), _p(C), C.stride(0), M, N, K, _p(bias), act, _p(Z),
+                              _p(z_in), dact, _p(add), _p(ws), _SPLITK_WS_BYTES if ws is not None else 0, _stream()), "gemm")
+    return (C, Z) if z_out else C
+
+
+def linear_fwd(x, W, b, act=0, save_pre=False):
+    """y = act(x W^T + b)   (Dense.forward, modules.py:99-112)"""
+    M, K = x.shape
+    N = W.shape[0]
+    return gemm(GEMM_NT, x, W, M, N, K, bias=b, act=act, z_out=save_pre)
+
+
+def linear_bwd_input(gy, W, z_in=None, dact=0, add=None):
+    """gx = (gy W) [* act'(z_in)] [+ add]"""
+    M, N = gy.shape
+    K = W.shape[1]
+    return gemm(GEMM_NN, gy, W, M, K, N, z_in=z_in, dact=dact, add=add)
+
+
+def linear_bwd_weight(gy, x):
+    """gW[out,in] = gy^T x"""
+    rows, n_out = gy.shape
+    n_in = x.shape[1]
+    return gemm(GEMM_TN, gy, x, n_out, n_in, rows)
+
+
+def colsum(X):
+    _need_cuda(X)
+    lib = _lib.load()
+    M, N = X.shape
+    out = torch.empty(N, dtype=torch.float32, device=X.device)
+    _lib.check(lib.cgvae_colsum(_p(X), X.stride(0), M, N, _p(out), _stream()), "colsum")
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# message layers
+# --------------------------------------------------------------------------------------------------
+
+def message_fwd(n_split, phi, v_send, v_recv, geom, Wf, bf, res_s, res_v, want_q=False):
+    """returns (out_s [n_recv,F], out_v [n_recv,3,F], q or None).  v_send None == all-zero vectors."""
+    _need_cuda(phi)
+    lib = _lib.load()
+    g = geom.graph
+    F = phi.shape[-1]
+    dev = phi.device
+    out_s = torch.empty((g.n_recv, F), dtype=torch.float32, device=dev)
+    out_v = torch.empty((g.n_recv, 3, F), dtype=torch.float32, device=dev)
+    q = torch.empty((g.n_recv, 3, F), dtype=torch.float32, device=dev) if (want_q and n_split == 4) else None
+    _lib.check(lib.cgvae_message_fwd(n_split, _p(phi), _p(v_send), _p(v_recv), _p(g.rowptr), _p(g.col), _p(geom.basis),
+                                     _p(geom.unit), _p(Wf), _p(bf), g.n_recv, g.n_send, F, geom.n_rbf, geom.rb, _p(res_s),
+                                     _p(res_v), int(v_send is None), _p(out_s), _p(out_v), _p(q), _stream()), "message_fwd")
+    return out_s, out_v, q
+
+
+def message_bwd(n_split, phi, v_send, v_recv, q, geom, Wf, bf, g_out_s, g_out_v, residual):
+    """returns (g_phi [n_send,K,F], g_v_send [n_send,3,F], dWf [K*F,R], dbf [K*F])."""
+    _need_cuda(phi)
+    lib = _lib.load()
+    g = geom.graph
+    F = phi.shape[-1]
+    dev = phi.device
+    g_phi = torch.empty((g.n_send, n_split, F), dtype=torch.float32, device=dev)
+    g_v = torch.empty((g.n_send, 3, F), dtype=torch.float32, device=dev)
+    dWf = torch.empty((n_split * F, geom.n_rbf), dtype=torch.float32, device=dev)
+    dbf = torch.empty((n_split * F,), dtype=torch.float32, device=dev)
+    ws_bytes = int(lib.cgvae_message_bwd_ws_bytes(n_split, F, geom.rb, g.n_send))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    _lib.check(lib.cgvae_message_bwd(n_split, _p(phi), _p(v_send), _p(v_recv), _p(q), _p(g.rowptr_t), _p(g.col_t), _p(g.perm_t),
+                                     _p(geom.basis), _p(geom.unit), _p(Wf), _p(bf), g.n_recv, g.n_send, F, geom.n_rbf, geom.rb,
+                                     _p(g_out_s), _p(g_out_v), int(bool(residual)), int(v_send is None), _p(g_phi), _p(g_v),
+                                     _p(dWf), _p(dbf), _p(ws), ws_bytes, _stream()), "message_bwd")
+    return g_phi, g_v, dWf, dbf
+
+
+def message9_fwd(phi, s, sbar, v, vbar, geom, Wf, bf, residual):
+    _need_cuda(phi)
+    lib = _lib.load()
+    g = geom.graph
+    n, F = s.shape
+    outs = [torch.empty_like(s), torch.empty_like(sbar), torch.empty_like(v), torch.empty_like(vbar)]
+    _lib.check(lib.cgvae_message9_fwd(_p(phi), _p(s), _p(sbar), _p(v), _p(vbar), _p(g.rowptr), _p(g.col), _p(geom.basis),
+                                      _p(geom.unit), _p(Wf), _p(bf), n, F, geom.n_rbf, geom.rb, int(bool(residual)),
+                                      _p(outs[0]), _p(outs[1]), _p(outs[2]), _p(outs[3]), _stream()), "message9_fwd")
+    return outs
+
+
+def message9_bwd(phi, s, sbar, v, vbar, geom, Wf, bf, residual, g_s, g_sbar, g_v, g_vbar):
+    """returns (gi_s, gi_sbar, gi_v, gi_vbar, g_phi [n,9,F], dWf [9F,R], dbf [9F])."""
+    _need_cuda(phi)
+    lib = _lib.load()
+    g = geom.graph
+    n, F = s.shape
+    dev = s.device
+    gi = [torch.empty_like(s), torch.empty_like(sbar), torch.empty_like(v), torch.empty_like(vbar)]
+    g_phi = torch.empty((n, 9, F), dtype=torch.float32, device=dev)
+    gw = torch.empty((g.n_edges, 9 * F), dtype=torch.float32, device=dev)
+    _lib.check(lib.cgvae_message9_bwd(_p(phi), _p(s), _p(sbar), _p(v), _p(vbar), _p(g.rowptr), _p(g.col), _p(g.rowptr_t),
+                                      _p(g.col_t), _p(g.perm_t), _p(geom.basis), _p(geom.unit), _p(Wf), _p(bf), n, F, geom.n_rbf,
+                                      geom.rb, int(bool(residual)), _p(g_s), _p(g_sbar), _p(g_v), _p(g_vbar), _p(gi[0]),
+                                      _p(gi[1]), _p(gi[2]), _p(gi[3]), _p(g_phi), _p(gw), _stream()), "message9_bwd")
+    # dWf[9F,R] = gw^T basis[:, :R] ; dbf[9F] = gw^T basis[:, R]   (DistanceEmbed weight / bias gradients)
+    R = geom.n_rbf
+    E = g.n_edges
+    if E > 0:
+        dWf = gemm(GEMM_TN, gw, geom.basis, 9 * F, R, E)
+        dbf = gemm(GEMM_TN, gw, geom.basis[:, R:], 9 * F, 1, E).reshape(9 * F)
+    else:
+        dWf = torch.zeros((9 * F, R), dtype=torch.float32, device=dev)
+        dbf = torch.zeros((9 * F,), dtype=torch.float32, device=dev)
+    return gi[0], gi[1], gi[2], gi[3], g_phi, dWf, dbf
+
+
+# --------------------------------------------------------------------------------------------------
+# update block, pooling, lifting
+# --------------------------------------------------------------------------------------------------
+
+def update_norm_fwd(s, Vv):
+    _need_cuda(s)
+    lib = _lib.load()
+    N, F = s.shape
+    x = torch.empty((N, 2 * F), dtype=torch.float32, device=s.device)
+    _lib.check(lib.cgvae_update_norm_fwd(_p(s), _p(Vv), N, F, _p(x), _stream()), "update_norm_fwd")
+    return x
+
+
+def update_combine_fwd(s, v, Uv, Vv, q, residual):
+    _need_cuda(Uv)
+    lib = _lib.load()
+    N, _, F = Uv.shape
+    s_out = torch.empty((N, F), dtype=torch.float32, device=Uv.device)
+    v_out = torch.empty((N, 3, F), dtype=torch.float32, device=Uv.device)
+    _lib.check(lib.cgvae_update_combine_fwd(_p(s), _p(v), _p(Uv), _p(Vv), _p(q), N, F, int(bool(residual)), _p(s_out), _p(v_out),
+                                            _stream()), "update_combine_fwd")
+    return s_out, v_out
+
+
+def update_combine_bwd(Uv, Vv, q, g_s, g_v):
+    _need_cuda(Uv)
+    lib = _lib.load()
+    N, _, F = Uv.shape
+    gq = torch.empty_like(q)
+    gUv = torch.empty_like(Uv)
+    gVv = torch.empty_like(Vv)
+    _lib.check(lib.cgvae_update_combine_bwd(_p(Uv), _p(Vv), _p(q), _p(g_s), _p(g_v), N, F, _p(gq), _p(gUv), _p(gVv), _stream()),
+               "update_combine_bwd")
+    return gq, gUv, gVv
+
+
+def update_norm_bwd(x, Vv, gx, g_s, gVv, residual):
+    """in place on gVv; returns gs_in"""
+    _need_cuda(x)
+    lib = _lib.load()
+    N, _, F = Vv.shape
+    gs_in = torch.empty((N, F), dtype=torch.float32, device=x.device)
+    _lib.check(lib.cgvae_update_norm_bwd(_p(x), _p(Vv), _p(gx), _p(g_s), N, F, int(bool(residual)), _p(gs_in), _p(gVv), _stream()),
+               "update_norm_bwd")
+    return gs_in
+
+
+def segment_reduce_fwd(X, seg, mean):
+    _need_cuda(X)
+    lib = _lib.load()
+    X = _f32(X)
+    W = int(np.prod(X.shape[1:]))
+    out = torch.empty((seg.n_beads,) + tuple(X.shape[1:]), dtype=torch.float32, device=X.device)
+    _lib.check(lib.cgvae_segment_reduce_fwd(_p(X), _p(seg.rowptr), _p(seg.atoms), seg.n_beads, W, int(bool(mean)), _p(out),
+                                            _stream()), "segment_reduce_fwd")
+    return out
+
+
+def segment_reduce_bwd(g_out, seg, mean):
+    _need_cuda(g_out)
+    lib = _lib.load()
+    g_out = _f32(g_out)
+    W = int(np.prod(g_out.shape[1:]))
+    g_X = torch.empty((seg.n,) + tuple(g_out.shape[1:]), dtype=torch.float32, device=g_out.device)
+    _lib.check(lib.cgvae_segment_reduce_bwd(_p(g_out), _p(seg.mapping), _p(seg.rowptr), seg.n, W, int(bool(mean)), _p(g_X),
+                                            _stream()), "segment_reduce_bwd")
+    return g_X
+
+
+def gather_rows(table, idx):
+    _need_cuda(table, idx)
+    lib = _lib.load()
+    idx = idx.to(torch.int64).contiguous()
+    W = table.shape[1]
+    out = torch.empty((idx.shape[0], W), dtype=torch.float32, device=table.device)
+    _lib.check(lib.cgvae_gather_rows(_p(table), _p(idx), idx.shape[0], W, _p(out), _stream()), "gather_rows")
+    return out
+
+
+def lift_fwd(V, cg_xyz, seg, mode, pin):
+    _need_cuda(V, cg_xyz)
+    lib = _lib.load()
+    F = V.shape[-1]
+    out = torch.empty((seg.n, 3), dtype=torch.float32, device=V.device)
+    _lib.check(lib.cgvae_lift_fwd(_p(V), _p(_f32(cg_xyz)), _p(seg.mapping), _p(seg.rank), _p(seg.rowptr), _p(seg.atoms), _p(pin),
+                                  seg.n, seg.n_beads, F, mode, _p(out), _stream()), "lift_fwd")
+    return out
+
+
+def lift_bwd(g_xyz, seg, F, mode, pin):
+    _need_cuda(g_xyz)
+    lib = _lib.load()
+    g_V = torch.empty((seg.n_beads, 3, F), dtype=torch.float32, device=g_xyz.device)
+    _lib.check(lib.cgvae_lift_bwd(_p(_f32(g_xyz)), _p(seg.mapping), _p(seg.rank), _p(seg.rowptr), _p(seg.atoms), _p(pin), seg.n,
+                                  seg.n_beads, F, mode, _p(g_V), _stream()), "lift_bwd")
+    return g_V
+
+
+def vec_to_planar(v_nf3):
+    _need_cuda(v_nf3)
+    lib = _lib.load()
+    v_nf3 = _f32(v_nf3)
+    N, F, _ = v_nf3.shape
+    out = torch.empty((N, 3, F), dtype=torch.float32, device=v_nf3.device)
+    _lib.check(lib.cgvae_vec_to_planar(_p(v_nf3), N, F, _p(out), _stream()), "vec_to_planar")
+    return out
+
+
+def vec_from_planar(v_n3f):
+    _need_cuda(v_n3f)
+    lib = _lib.load()
+    v_n3f = _f32(v_n3f)
+    N, _, F = v_n3f.shape
+    out = torch.empty((N, F, 3), dtype=torch.float32, device=v_n3f.device)
+    _lib.check(lib.cgvae_vec_from_planar(_p(v_n3f), N, F, _p(out), _stream()), "vec_from_planar")
+    return out

@@ -1,0 +1,221 @@
+/*
+ * cgvae_b200.h -- C ABI of libcgvae_sm100.so: the B200 (sm_100a) implementation of the CGVAE
+ * equivariant message-passing hot path.
+ *
+ * The reference (wwang2/CoarseGrainingVAE) has no FFI of its own: the path sits behind plain
+ * nn.Module.forward calls that bottom out in ATen ops and torch_scatter.
+ * Each entry point below therefore names the reference Python interface it replaces
+ * (file:line under /root/reference/CoarseGrainingVAE).  The reference-side binding (ctypes) is
+ * shown in INTEGRATION.md; coarsegrainingvae_b200/_lib.py is that binding.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is DEVICE memory owned by the caller
+ *    (PyTorch allocates), 16-byte aligned, contiguous.  Kernels never allocate, free or
+ *    retain pointers; scratch is passed in (`ws`, size from the matching *_ws_bytes()).
+ *  - all launches go on `stream`; no host synchronisation inside (CUDA-graph capturable);
+ *    output sizes that depend on data (edge counts) are left in device memory for the caller
+ *    to read (the last element of the scanned offsets).
+ *  - return 0 on success, <0 argument error, >0 cudaError_t; text via cgvae_last_error()
+ *    (thread-local).  All entry points are re-entrant (autograd calls backward from worker
+ *    threads).
+ *  - layouts: scalars s[N][F]; vectors v[N][3][F] ("planar": xyz major, channel minor);
+ *    phi[N][K][F]; filter weights in the reference's native nn.Linear layout Wf[K*F][R],
+ *    bf[K*F]; dense weights W[out][in].
+ *  - graphs: receiver-major CSR (rowptr[n_recv+1], col[E] = sender) with per-edge data in CSR
+ *    order (basis[E][RB], unit[E][4]); sender-major CSR (rowptr_t[n_send+1], col_t[E] =
+ *    receiver, perm_t[E] = CSR slot of the same edge in receiver order) for the backward.
+ *    Internal index arrays are int32; edge lists crossing the boundary are the reference's
+ *    int64 [E][2] (column 0 receiver, column 1 sender).
+ */
+#ifndef CGVAE_B200_H_
+#define CGVAE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* cgvae_stream_t; /* cudaStream_t */
+
+#define CGVAE_ABI_VERSION 1
+
+/* activation codes (reference modules.py:32-42 `layer_types`) */
+enum { CGVAE_ACT_NONE = 0, CGVAE_ACT_SWISH = 1, CGVAE_ACT_RELU = 2, CGVAE_ACT_TANH = 3 };
+/* GEMM operand forms */
+enum { CGVAE_GEMM_NT = 0, /* C[M,N] = A[M,K] * B[N,K]^T   (y = x W^T, Dense.forward modules.py:101) */
+       CGVAE_GEMM_NN = 1, /* C[M,N] = A[M,K] * B[K,N]     (grad_in = grad_out W)                    */
+       CGVAE_GEMM_TN = 2  /* C[M,N] = A[K,M]^T * B[K,N]   (grad_W = grad_out^T x)                   */ };
+
+int cgvae_abi_version(void);
+const char* cgvae_last_error(void);
+/* number of kernels launched by this library in the calling process (bench.py `gpu_launches`) */
+unsigned long long cgvae_launch_count(void);
+
+/* ------------------------------------------------------------------ graph builders (integer) */
+
+/* get_neighbor_list, data.py:65-82 -- all pairs with fp32 |x_i-x_j| <= cutoff, i != j, within the
+ * same frame (frame_ptr[n_frames+1] atom offsets: the per-frame loop of
+ * CGDataset.generate_neighbor_list data.py:207-225 plus the CG_collate offsets data.py:255-270).
+ * undirected != 0 keeps j > i.  Two calls: count (fills deg[n], per-atom neighbour count) then,
+ * after an exclusive scan into rowptr[n+1], fill (writes out[E][2] int64, sorted by (i, j)).
+ * `use_cells` != 0: cell-list search (cells of edge >= cutoff per frame); 0: tiled brute force.
+ * ws: cgvae_radius_graph_ws_bytes(n, n_frames).  Bit-exact vs the reference. */
+size_t cgvae_radius_graph_ws_bytes(int64_t n, int64_t n_frames);
+int cgvae_radius_graph_count(const float* xyz, int64_t n, const int64_t* frame_ptr, int64_t n_frames,
+                             float cutoff, int undirected, int use_cells, int32_t* deg, void* ws,
+                             size_t ws_bytes, cgvae_stream_t stream);
+int cgvae_radius_graph_fill(const float* xyz, int64_t n, const int64_t* frame_ptr, int64_t n_frames,
+                            float cutoff, int undirected, int use_cells, const int64_t* rowptr,
+                            int64_t* out_pairs, void* ws, size_t ws_bytes, cgvae_stream_t stream);
+
+/* exclusive scan of int32 counts into int64 offsets out[n+1] (out[n] = total). */
+int cgvae_exclusive_scan(const int32_t* counts, int64_t n, int64_t* out, cgvae_stream_t stream);
+
+/* make_directed, conv.py:10-20 -- flags[0] = any(col0 > col1), flags[1] = any(col1 > col0) (device
+ * int32[2], zeroed by the call); the caller appends the flipped list when not both are set. */
+int cgvae_edge_orientation(const int64_t* pairs, int64_t n_edges, int32_t* flags, cgvae_stream_t stream);
+
+/* Receiver CSR + sender CSR of a directed edge list (replaces scatter_add(index=nbrs[:,0]) call
+ * sites conv.py:223-240,392-400,553-561).  key_col = 0 builds rows over column 0.
+ *   cgvae_csr_count : deg_r[n_recv], deg_s[n_send] (int32, zeroed by the call)
+ *   cgvae_csr_fill  : rowptr_r/rowptr_s are int32 exclusive scans (n+1).  Writes, in the original
+ *                     edge order within every row (deterministic): col[E] (sender), eid[E] (original
+ *                     edge id of each CSR slot), col_t[E] (receiver), perm_t[E] (receiver-CSR slot). */
+int cgvae_csr_count(const int64_t* pairs, int64_t n_edges, int64_t n_recv, int64_t n_send,
+                    int32_t* deg_r, int32_t* deg_s, cgvae_stream_t stream);
+int cgvae_scan_i32(const int32_t* counts, int64_t n, int32_t* out, cgvae_stream_t stream);
+int cgvae_csr_fill(const int64_t* pairs, int64_t n_edges, int64_t n_recv, int64_t n_send,
+                   const int32_t* rowptr_r, const int32_t* rowptr_s, int32_t* scratch /* n_recv+n_send+2E int32 */,
+                   int32_t* col, int32_t* eid, int32_t* col_t, int32_t* perm_t, cgvae_stream_t stream);
+
+/* CG2ChannelIdx, cgvae.py:451-460 -- rank[n] = #{m < n : mapping[m] == mapping[n]}; also the bead
+ * CSR (rowptr_b[n_beads+1] given by the caller from cgvae_csr_count/scan; atoms[n] in ascending
+ * order per bead).  Exact. */
+int cgvae_segment_count(const int64_t* mapping, int64_t n, int64_t n_beads, int32_t* deg, cgvae_stream_t stream);
+int cgvae_segment_rank(const int64_t* mapping, int64_t n, int64_t n_beads, const int32_t* rowptr_b,
+                       int32_t* scratch /* n_beads int32 */, int32_t* atoms, int32_t* slot_of_atom, int64_t* rank,
+                       cgvae_stream_t stream);
+
+/* ------------------------------------------------------------------ edge geometry (fp32) */
+
+/* preprocess_r conv.py:25-29 + PainnRadialBasis modules.py:148-172 + CosineEnvelope modules.py:52-58,
+ * for the edges of a CSR: edge in slot e is (recv <- send).  r = xs[send] - xr[recv]
+ * (cgvae.py:276,280,383; for the contraction graph xr = cg_xyz, send = atom).
+ * basis[e][r] = rbf_r * env (r < R), basis[e][R] = env (bias column), zero padded to RB;
+ * unit[e] = (ux, uy, uz, d).  coef[R] = n*pi/cutoff computed by the host exactly as the reference.
+ * edge_wgt (nullable, indexed by ORIGINAL edge id through eid) is folded into the basis
+ * (conv.py:528-533).  r_edge (nullable): per-edge displacement [E][3] in ORIGINAL edge order, used instead
+ * of the coordinates when the caller passes r_ij directly (block-level forward signatures). */
+int cgvae_edge_geometry(const float* xyz_send, const float* xyz_recv, const float* r_edge, const int32_t* rowptr,
+                        const int32_t* col, int64_t n_recv, int64_t n_edges, const float* coef, int R, int RB, float cutoff,
+                        const float* edge_wgt, const int32_t* eid, float* basis, float* unit,
+                        cgvae_stream_t stream);
+
+/* ------------------------------------------------------------------ dense contractions */
+
+/* Dense / nn.Linear forward and backward contractions (modules.py:75-114, conv.py:41-49,568-586).
+ * C = epilogue(op(A) op(B)) with epilogue, in order: + bias[N] (nullable); z_out = value (nullable,
+ * pre-activation copy, ld = ldc); act; * dact(z_in) when z_in != NULL (activation backward with the
+ * saved pre-activation, act code `dact`); + add[M,N] (nullable residual, ld = ldc). fp32 FMA.
+ * ws (nullable): scratch for deterministic split-K when the output grid cannot fill 148 SMs. */
+int cgvae_gemm(int form, const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
+               int64_t M, int64_t N, int64_t K, const float* bias, int act, float* z_out,
+               const float* z_in, int dact, const float* add, void* ws, size_t ws_bytes,
+               cgvae_stream_t stream);
+/* out[N] = sum over rows of X[M][N] (bias gradients); deterministic. */
+int cgvae_colsum(const float* X, int64_t ldx, int64_t M, int64_t N, float* out, cgvae_stream_t stream);
+
+/* ------------------------------------------------------------------ message blocks */
+
+/* One fused message layer = gather phi/v at the sender, filter w = basis*[Wf;bf], channel mixing and
+ * deterministic CSR segment reduction into receivers, residual add.
+ *   n_split 3: EquiMessageBlock.forward conv.py:505-563 and ContractiveMessageBlock.forward
+ *              conv.py:703-733 (bipartite graph atoms -> beads)
+ *   n_split 4: EquiMessageCross.forward conv.py:358-402 (v_recv = v; also writes q[n_recv][3][F] =
+ *              sum_e m3 * v_j, saved for the backward)
+ * phi[n_send][K][F], v_send[n_send][3][F]; res_s/res_v nullable residuals (cgvae.py:287-288);
+ * v_is_zero != 0 skips the v gathers (first layer of every stack: cgvae.py:274,90). */
+int cgvae_message_fwd(int n_split, const float* phi, const float* v_send, const float* v_recv,
+                      const int32_t* rowptr, const int32_t* col, const float* basis, const float* unit,
+                      const float* Wf, const float* bf, int64_t n_recv, int64_t n_send, int F, int R, int RB,
+                      const float* res_s, const float* res_v, int v_is_zero,
+                      float* out_s, float* out_v, float* q, cgvae_stream_t stream);
+
+/* Backward of the above, reduced by SENDER over the transposed CSR (deterministic):
+ * g_phi[n_send][K][F], g_v_send[n_send][3][F] (+= g_out_v pass-through when `residual`),
+ * dWf[K*F][R], dbf[K*F].  n_split 4 also adds the receiver-side term q x g_out_v.
+ * ws: cgvae_message_bwd_ws_bytes(n_split, F, RB, n_send). */
+size_t cgvae_message_bwd_ws_bytes(int n_split, int F, int RB, int64_t n_send);
+int cgvae_message_bwd(int n_split, const float* phi, const float* v_send, const float* v_recv, const float* q,
+                      const int32_t* rowptr_t, const int32_t* col_t, const int32_t* perm_t,
+                      const float* basis, const float* unit, const float* Wf, const float* bf,
+                      int64_t n_recv, int64_t n_send, int F, int R, int RB,
+                      const float* g_out_s, const float* g_out_v, int residual, int v_is_zero,
+                      float* g_phi, float* g_v_send, float* dWf, float* dbf,
+                      void* ws, size_t ws_bytes, cgvae_stream_t stream);
+
+/* EquiMessagePsuedo.forward conv.py:180-242 (9 splits) and its backward.  State (s, sbar, v, vbar)
+ * on one node set; residual adds fused (cgvae.py:108-111).  The backward also needs the receiver CSR
+ * (receiver-side gradient terms) and writes gw[E][9][F] (per-edge filter gradient, original CSR slot
+ * order) from which the caller forms dWf = basis^T gw with cgvae_gemm(TN). */
+int cgvae_message9_fwd(const float* phi, const float* s, const float* sbar, const float* v, const float* vbar,
+                       const int32_t* rowptr, const int32_t* col, const float* basis, const float* unit,
+                       const float* Wf, const float* bf, int64_t n, int F, int R, int RB, int residual,
+                       float* out_s, float* out_sbar, float* out_v, float* out_vbar, cgvae_stream_t stream);
+int cgvae_message9_bwd(const float* phi, const float* s, const float* sbar, const float* v, const float* vbar,
+                       const int32_t* rowptr, const int32_t* col,
+                       const int32_t* rowptr_t, const int32_t* col_t, const int32_t* perm_t,
+                       const float* basis, const float* unit, const float* Wf, const float* bf,
+                       int64_t n, int F, int R, int RB, int residual,
+                       const float* g_s, const float* g_sbar, const float* g_v, const float* g_vbar,
+                       float* gi_s, float* gi_sbar, float* gi_v, float* gi_vbar, float* g_phi, float* gw,
+                       cgvae_stream_t stream);
+
+/* ------------------------------------------------------------------ update block (conv.py:588-616) */
+
+/* x[N][2F] = [ s | sqrt(sum_c (Vv_c^2 + 1e-10)) ]   (conv.py:600-601) */
+int cgvae_update_norm_fwd(const float* s, const float* Vv, int64_t N, int F, float* x, cgvae_stream_t stream);
+/* v_out = v + Uv*a_vv ; s_out = s + <Uv,Vv>*a_sv + a_ss,  q[N][3][F] = (a_vv,a_sv,a_ss)  (conv.py:603-614);
+ * residual == 0 returns the deltas only (the reference block API). */
+int cgvae_update_combine_fwd(const float* s, const float* v, const float* Uv, const float* Vv, const float* q,
+                             int64_t N, int F, int residual, float* s_out, float* v_out, cgvae_stream_t stream);
+/* -> gq[N][3][F], gUv[N][3][F], gVv[N][3][F] (the part that does not pass through the norm) */
+int cgvae_update_combine_bwd(const float* Uv, const float* Vv, const float* q, const float* g_s, const float* g_v,
+                             int64_t N, int F, float* gq, float* gUv, float* gVv, cgvae_stream_t stream);
+/* gs_in = g_s + gx[:, :F] ; gVv += gx[:, F:] * Vv / nrm  (nrm = x[:, F:]) */
+int cgvae_update_norm_bwd(const float* x, const float* Vv, const float* gx, const float* g_s,
+                          int64_t N, int F, int residual, float* gs_in, float* gVv, cgvae_stream_t stream);
+
+/* ------------------------------------------------------------------ pooling and lifting */
+
+/* scatter_mean / scatter_add over the bead CSR (torch_scatter call sites cgvae.py:297-298,479;
+ * datasets.py:487).  X[N][W] -> out[n_beads][W]; mean divides by max(count,1).  Backward gathers. */
+int cgvae_segment_reduce_fwd(const float* X, const int32_t* rowptr_b, const int32_t* atoms, int64_t n_beads,
+                             int64_t W, int mean, float* out, cgvae_stream_t stream);
+int cgvae_segment_reduce_bwd(const float* g_out, const int64_t* mapping, const int32_t* rowptr_b, int64_t N,
+                             int64_t W, int mean, float* g_X, cgvae_stream_t stream);
+/* Embedding gather (cgvae.py:273,380,591): out[n] = table[idx[n]] ; idx int64. */
+int cgvae_gather_rows(const float* table, const int64_t* idx, int64_t N, int64_t W, float* out,
+                      cgvae_stream_t stream);
+
+/* Bead -> atom lifting, CGequiVAE.decoder cgvae.py:466-482 / PCN.decoder cgvae.py:556-576:
+ * rel[n] = V[mapping[n]][:, rank[n]] ; mode 1: rel -= bead mean (offset=True); mode 2: rel[n] = 0 where
+ * pin[n] != 0 (PCN C-alpha re-anchoring cgvae.py:569-571); xyz_out = rel + cg_xyz[mapping].
+ * Backward writes g_V[n_beads][3][F] (zero filled by the call). */
+int cgvae_lift_fwd(const float* V, const float* cg_xyz, const int64_t* mapping, const int64_t* rank,
+                   const int32_t* rowptr_b, const int32_t* atoms, const uint8_t* pin, int64_t N, int64_t n_beads,
+                   int F, int mode, float* xyz_out, cgvae_stream_t stream);
+int cgvae_lift_bwd(const float* g_xyz, const int64_t* mapping, const int64_t* rank, const int32_t* rowptr_b,
+                   const int32_t* atoms, const uint8_t* pin, int64_t N, int64_t n_beads, int F, int mode,
+                   float* g_V, cgvae_stream_t stream);
+
+/* layout conversion at the module boundary: reference v[N][F][3] <-> planar v[N][3][F] */
+int cgvae_vec_to_planar(const float* v_nf3, int64_t N, int F, float* v_n3f, cgvae_stream_t stream);
+int cgvae_vec_from_planar(const float* v_n3f, int64_t N, int F, float* v_nf3, cgvae_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CGVAE_B200_H_ */
