@@ -112,11 +112,14 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) gemm_kernel(
 
   TileLoader<BM, A_KC, NT> la;
   TileLoader<BN, B_KC, NT> lb;
-  float acc[TM][TN];
+  // two-level accumulation: `acc` is folded into `tot` every kFold k-tiles so the rounding error grows with
+  // sqrt(kFold*BK) + sqrt(K/(kFold*BK)) instead of sqrt(K) (weight gradients reduce over up to 1e5 rows)
+  constexpr int kFold = 16;
+  float acc[TM][TN], tot[TM][TN];
 #pragma unroll
   for (int i = 0; i < TM; ++i)
 #pragma unroll
-    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < TN; ++j) { acc[i][j] = 0.f; tot[i][j] = 0.f; }
 
   int buf = 0;
   if (kbeg < kend) {
@@ -126,6 +129,7 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) gemm_kernel(
     lb.store(Bs[0], tid);
   }
   __syncthreads();
+  int fold = 0;
   for (int64_t k0 = kbeg; k0 < kend; k0 += BK) {
     const bool more = k0 + BK < kend;
     if (more) {
@@ -148,9 +152,20 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) gemm_kernel(
       la.store(As[buf ^ 1], tid);
       lb.store(Bs[buf ^ 1], tid);
     }
+    if (++fold == kFold) {
+      fold = 0;
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) { tot[i][j] += acc[i][j]; acc[i][j] = 0.f; }
+    }
     __syncthreads();
     buf ^= 1;
   }
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] += tot[i][j];
 
   const bool split = gridDim.z > 1;
 #pragma unroll

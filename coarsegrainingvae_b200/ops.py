@@ -40,6 +40,36 @@ def launch_count():
     return _lib.launch_count()
 
 
+class KernelTimer(object):
+    """Optional CUDA-event timing of individual kernel launches on the launching stream (bench.py uses it for the
+    live roofline figure).  ``records[name]`` = list of (start_event, end_event, meta)."""
+
+    def __init__(self, names):
+        self.names = set(names)
+        self.records = {}
+
+    def begin(self, name):
+        if name not in self.names:
+            return None
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(torch.cuda.current_stream())
+        return ev
+
+    def end(self, name, start, meta):
+        if start is None:
+            return
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(torch.cuda.current_stream())
+        self.records.setdefault(name, []).append((start, ev, meta))
+
+    def summary(self):
+        """name -> list of (milliseconds, meta); call after a synchronize."""
+        return {k: [(a.elapsed_time(b), m) for a, b, m in v] for k, v in self.records.items()}
+
+
+TIMER = None      # set to a KernelTimer to time launches; None (default) adds no events
+
+
 # --------------------------------------------------------------------------------------------------
 # graphs
 # --------------------------------------------------------------------------------------------------
@@ -244,7 +274,8 @@ def gemm(form, A, B, M, N, K, bias=None, act=0, z_out=False, z_in=None, dact=0, 
     dev = A.device
     C = out if out is not None else torch.empty((M, N), dtype=torch.float32, device=dev)
     Z = torch.empty((M, N), dtype=torch.float32, device=dev) if z_out else None
-    ws = torch.empty(_SPLITK_WS_BYTES, dtype=torch.uint8, device=dev) if (M <= 64 and K >= 512) else None
+    tiles = ((M + 63) // 64) * ((N + 63) // 64) if M > 32 else ((N + 31) // 32)
+    ws = torch.empty(_SPLITK_WS_BYTES, dtype=torch.uint8, device=dev) if (tiles < 148 and K >= 512) else None
     _lib.check(lib.cgvae_gemm(form, _p(A), A.stride(0), _p(B), B.stride(0), _p(C), C.stride(0), M, N, K, _p(bias), act, _p(Z),
                               _p(z_in), dact, _p(add), _p(ws), _SPLITK_WS_BYTES if ws is not None else 0, _stream()), "gemm")
     return (C, Z) if z_out else C
@@ -294,9 +325,13 @@ def message_fwd(n_split, phi, v_send, v_recv, geom, Wf, bf, res_s, res_v, want_q
     out_s = torch.empty((g.n_recv, F), dtype=torch.float32, device=dev)
     out_v = torch.empty((g.n_recv, 3, F), dtype=torch.float32, device=dev)
     q = torch.empty((g.n_recv, 3, F), dtype=torch.float32, device=dev) if (want_q and n_split == 4) else None
+    t0 = TIMER.begin("message_fwd") if TIMER is not None else None
     _lib.check(lib.cgvae_message_fwd(n_split, _p(phi), _p(v_send), _p(v_recv), _p(g.rowptr), _p(g.col), _p(geom.basis),
                                      _p(geom.unit), _p(Wf), _p(bf), g.n_recv, g.n_send, F, geom.n_rbf, geom.rb, _p(res_s),
                                      _p(res_v), int(v_send is None), _p(out_s), _p(out_v), _p(q), _stream()), "message_fwd")
+    if t0 is not None:
+        TIMER.end("message_fwd", t0, dict(n_split=n_split, E=g.n_edges, n_recv=g.n_recv, n_send=g.n_send, F=F,
+                                          R=geom.n_rbf, v_zero=v_send is None))
     return out_s, out_v, q
 
 
@@ -313,10 +348,14 @@ def message_bwd(n_split, phi, v_send, v_recv, q, geom, Wf, bf, g_out_s, g_out_v,
     dbf = torch.empty((n_split * F,), dtype=torch.float32, device=dev)
     ws_bytes = int(lib.cgvae_message_bwd_ws_bytes(n_split, F, geom.rb, g.n_send))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    t0 = TIMER.begin("message_bwd") if TIMER is not None else None
     _lib.check(lib.cgvae_message_bwd(n_split, _p(phi), _p(v_send), _p(v_recv), _p(q), _p(g.rowptr_t), _p(g.col_t), _p(g.perm_t),
                                      _p(geom.basis), _p(geom.unit), _p(Wf), _p(bf), g.n_recv, g.n_send, F, geom.n_rbf, geom.rb,
                                      _p(g_out_s), _p(g_out_v), int(bool(residual)), int(v_send is None), _p(g_phi), _p(g_v),
                                      _p(dWf), _p(dbf), _p(ws), ws_bytes, _stream()), "message_bwd")
+    if t0 is not None:
+        TIMER.end("message_bwd", t0, dict(n_split=n_split, E=g.n_edges, n_recv=g.n_recv, n_send=g.n_send, F=F,
+                                          R=geom.n_rbf, v_zero=v_send is None))
     return g_phi, g_v, dWf, dbf
 
 

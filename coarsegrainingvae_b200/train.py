@@ -1,0 +1,128 @@
+"""Training / sampling steps around the hot path: the loss assembly and optimiser step of
+scripts/utils.py:81-157 and the ensemble loop of scripts/sampling.py:252-284 of the reference, kept on
+the device with no host round trips except the loss read the reference also does.
+
+The model forward / backward runs in the sm_100a kernels; the loss terms, gradient clipping and Adam
+are small element-wise / reduction passes (SURVEY.md section 8f lists their fusion as the next step) and use
+torch device ops on a single flat gradient buffer.
+"""
+import torch
+
+EPS = 1e-6          # scripts/utils.py:27
+
+
+def kl_divergence(mu1, std1, mu2, std2):
+    """scripts/utils.py:81-86 -- note the reference divides (mu1-mu2)^2 by std2, not std2^2; kept."""
+    return 0.5 * ((std1.pow(2) / std2.pow(2)).sum(-1) + ((mu1 - mu2).pow(2) / std2).sum(-1)
+                  + torch.log(std2.pow(2)).sum(-1) - torch.log(std1.pow(2)).sum(-1) - std1.shape[-1]).mean()
+
+
+def training_loss(outputs, xyz, bond_edge_list, beta, gamma):
+    """scripts/utils.py:117-141: MSE + beta*KL + gamma*bond-graph loss, all on the device (the reference moves the
+    edge list and the target coordinates to the CPU first: utils.py:127-128)."""
+    mu, sigma, pmu, pstd, _, xyz_recon = outputs
+    recon = (xyz_recon - xyz).pow(2).mean()
+    loss = recon
+    kl = graph = None
+    if mu is not None:
+        kl = kl_divergence(mu, sigma, pmu, pstd)
+        loss = loss + kl * beta
+    if gamma != 0.0:
+        a, b = bond_edge_list[:, 0], bond_edge_list[:, 1]
+        gen = ((xyz_recon[a] - xyz_recon[b]).pow(2).sum(-1) + EPS).sqrt()
+        dat = ((xyz[a] - xyz[b]).pow(2).sum(-1) + EPS).sqrt()
+        graph = (gen - dat).pow(2).mean()
+        loss = loss + graph * gamma
+    return loss, recon, kl, graph
+
+
+class FlatGrads(object):
+    """One contiguous fp32 buffer holding the gradients of the parameters that actually receive one
+    (two thirds of the reference's parameters are constructed and never used: SURVEY.md section 5).  ``p.grad`` of each
+    such parameter is a view into the buffer, so backward accumulates in place, the data-parallel all-reduce is ONE
+    collective on ONE tensor, and clipping is two passes over it."""
+
+    def __init__(self, params):
+        self.params = [p for p in params]
+        n = sum(p.numel() for p in self.params)
+        dev = self.params[0].device if self.params else "cpu"
+        dtype = self.params[0].dtype if self.params else torch.float32
+        self.flat = torch.zeros(n, dtype=dtype, device=dev)
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def zero_(self):
+        self.flat.zero_()
+
+    def allreduce_mean_(self, group=None):
+        """gradient exchange of data-parallel training: one all-reduce(sum) over NVLink, then 1/world."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()):
+            return
+        world = dist.get_world_size(group)
+        if world == 1:
+            return
+        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+        self.flat.mul_(1.0 / world)
+
+    def clip_(self, max_norm):
+        """torch.nn.utils.clip_grad_norm_ semantics (scripts/utils.py:156) on the flat buffer; returns the norm."""
+        norm = torch.linalg.vector_norm(self.flat)
+        coef = torch.clamp(max_norm / (norm + 1e-6), max=1.0)
+        self.flat.mul_(coef)
+        return norm
+
+
+def used_parameters(model, run_backward):
+    """names and parameters that receive a gradient in one backward pass (``run_backward()`` must do one)."""
+    for p in model.parameters():
+        p.grad = None
+    run_backward()
+    return [(k, p) for k, p in model.named_parameters() if p.grad is not None]
+
+
+class TrainStep(object):
+    """one optimisation step of scripts/utils.py::loop (train=True branch): forward, loss, backward, [all-reduce],
+    clip_grad_norm_(0.01), Adam."""
+
+    def __init__(self, model, beta, gamma, lr=1e-4, max_norm=0.01, group=None, xyz_key="nxyz"):
+        self.model, self.beta, self.gamma = model, beta, gamma
+        self.max_norm, self.group, self.xyz_key = max_norm, group, xyz_key
+        self.lr = lr
+        self.flat = None
+        self.opt = None
+
+    def _loss(self, batch, eps):
+        out = self.model(batch, eps=eps) if eps is not None else self.model(batch)
+        xyz = out[4]
+        return training_loss(out, xyz, batch["bond_edge_list"], self.beta, self.gamma)[0]
+
+    def prepare(self, batch, eps=None):
+        """discover the used parameters with one dry backward and lay their gradients out in one flat buffer."""
+        used = used_parameters(self.model, lambda: self._loss(batch, eps).backward())
+        self.flat = FlatGrads([p for _, p in used])
+        fused = self.flat.flat.is_cuda
+        self.opt = torch.optim.Adam(self.flat.params, lr=self.lr, fused=fused)
+        return [k for k, _ in used]
+
+    def forward_backward(self, batch, eps=None):
+        self.flat.zero_()
+        loss = self._loss(batch, eps)
+        loss.backward()
+        return loss
+
+    def step(self, batch, eps=None):
+        loss = self.forward_backward(batch, eps)
+        self.flat.allreduce_mean_(self.group)
+        self.flat.clip_(self.max_norm)
+        self.opt.step()
+        return loss
+
+
+@torch.no_grad()
+def sample_ensemble_member(model, cg_xyz, CG_nbr_list, mapping, num_CGs, H_prior_mu, H_prior_sigma, eps, graphs=None):
+    """scripts/sampling.py:276-279: H = mu + eps*sigma, then the decoder."""
+    H = H_prior_mu + eps * H_prior_sigma
+    return model.decoder(cg_xyz, CG_nbr_list, H, H, mapping, num_CGs, graphs=graphs)

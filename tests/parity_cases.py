@@ -28,17 +28,32 @@ def _oracle_params(module, prefix=""):
             for k, v in module.state_dict().items()}
 
 
-def _check_grads(module, P, tol, prefix=""):
+def _check_grads(module, P, tol, prefix="", P64=None):
+    """every parameter gradient vs the oracle's autograd.  With ``P64`` (the same oracle evaluated in float64 = ground
+    truth) the criterion becomes conditioning-aware: the kernel's error against the truth must be below ``tol`` OR below
+    twice the error the fp32 oracle itself makes on that tensor (the raw fp32-vs-fp32 difference is then bounded by the
+    triangle inequality and is returned for reporting).
+    (Needed for the UpdateBlock norm path: d sqrt(sum(Vv^2+1e-10)) / dVv divides by ~1e-5 when v is still ~0, which
+    amplifies fp32 rounding in *both* implementations -- conv.py:600.)"""
     n = 0
+    worst = 0.0
     for k, p in module.named_parameters():
         og = P[prefix + k].grad
         if og is None or float(og.abs().max()) == 0.0:
             assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
+            continue
+        assert p.grad is not None, k
+        raw = rel_err(p.grad, og)
+        if P64 is None:
+            assert raw < tol, (k, raw)
         else:
-            assert p.grad is not None, k
-            assert rel_err(p.grad, og) < tol, (k, rel_err(p.grad, og))
-            n += 1
+            truth = P64[prefix + k].grad
+            e_kernel, e_ref = rel_err(p.grad, truth), rel_err(og, truth)
+            assert e_kernel < max(tol, 2.0 * e_ref), (k, e_kernel, e_ref)
+        worst = max(worst, raw)
+        n += 1
     assert n > 0
+    return worst
 
 
 def _check_golden_grads(module, G, tol):
