@@ -19,14 +19,14 @@ def _phi_forward(s, W1, b1, W2, b2, act=SWISH):
     return a1, z1, phi
 
 
-def _phi_backward(g_phi2d, s, a1, z1, W1, W2, add_to_gs, act=SWISH):
+def _phi_backward(g_phi2d, s, a1, z1, W1, b1, W2, b2, add_to_gs, act=SWISH):
     """backward of phi = Dense2(act(Dense1(s))) given g_phi [N, K*F]; returns gs (+add), gW1, gb1, gW2, gb2."""
     gz1 = ops.linear_bwd_input(g_phi2d, W2, z_in=z1, dact=act)            # (g_phi W2) * act'(z1)
-    gW2 = ops.linear_bwd_weight(g_phi2d, a1)
-    gb2 = ops.colsum(g_phi2d)
+    gW2 = ops.linear_bwd_weight(g_phi2d, a1, W2)
+    gb2 = ops.colsum(g_phi2d, b2)
     gs = ops.linear_bwd_input(gz1, W1, add=add_to_gs)
-    gW1 = ops.linear_bwd_weight(gz1, s)
-    gb1 = ops.colsum(gz1)
+    gW1 = ops.linear_bwd_weight(gz1, s, W1)
+    gb1 = ops.colsum(gz1, b1)
     return gs, gW1, gb1, gW2, gb2
 
 
@@ -39,14 +39,14 @@ class MLP2(Function):
         x = x.contiguous()
         a1, z1, y = _phi_forward(x, W1, b1, W2, b2, act)
         ctx.act = act
-        ctx.save_for_backward(x, a1, z1, W1, W2)
+        ctx.save_for_backward(x, a1, z1, W1, b1, W2, b2)
         return y
 
     @staticmethod
     @once_differentiable
     def backward(ctx, gy):
-        x, a1, z1, W1, W2 = ctx.saved_tensors
-        gx, gW1, gb1, gW2, gb2 = _phi_backward(gy.contiguous(), x, a1, z1, W1, W2, None, ctx.act)
+        x, a1, z1, W1, b1, W2, b2 = ctx.saved_tensors
+        gx, gW1, gb1, gW2, gb2 = _phi_backward(gy.contiguous(), x, a1, z1, W1, b1, W2, b2, None, ctx.act)
         return None, gx, gW1, gb1, gW2, gb2
 
 
@@ -77,13 +77,13 @@ class MessageBlock(Function):
         ctx.geom, ctx.n_split, ctx.mode = geom, n_split, mode
         ctx.v_none = v is None
         ctx.res_v_none = res_v is None
-        ctx.save_for_backward(s, v, a1, z1, phi3, q, W1, W2, Wf, bf)
+        ctx.save_for_backward(s, v, a1, z1, phi3, q, W1, b1, W2, b2, Wf, bf)
         return out_s, out_v
 
     @staticmethod
     @once_differentiable
     def backward(ctx, g_s, g_v):
-        s, v, a1, z1, phi3, q, W1, W2, Wf, bf = ctx.saved_tensors
+        s, v, a1, z1, phi3, q, W1, b1, W2, b2, Wf, bf = ctx.saved_tensors
         g_s, g_v = g_s.contiguous(), g_v.contiguous()
         n_split, mode = ctx.n_split, ctx.mode
         residual = mode == "self"
@@ -91,7 +91,7 @@ class MessageBlock(Function):
         g_phi, g_v_send, dWf, dbf = ops.message_bwd(n_split, phi3, v, v if n_split == 4 else None, q, ctx.geom, Wf, bf,
                                                     g_s, g_v, residual and not ctx.v_none)
         N, F = s.shape
-        gs, gW1, gb1, gW2, gb2 = _phi_backward(g_phi.view(N, n_split * F), s, a1, z1, W1, W2,
+        gs, gW1, gb1, gW2, gb2 = _phi_backward(g_phi.view(N, n_split * F), s, a1, z1, W1, b1, W2, b2,
                                                g_s if residual else None)
         gv = None if ctx.v_none else g_v_send
         g_res_s = g_s if mode == "other" else None
@@ -110,18 +110,18 @@ class Message9Block(Function):
         phi3 = phi.view(N, 9, F)
         outs = ops.message9_fwd(phi3, s, sbar, v, vbar, geom, Wf, bf, residual)
         ctx.geom, ctx.residual = geom, residual
-        ctx.save_for_backward(s, sbar, v, vbar, a1, z1, phi3, W1, W2, Wf, bf)
+        ctx.save_for_backward(s, sbar, v, vbar, a1, z1, phi3, W1, b1, W2, b2, Wf, bf)
         return tuple(outs)
 
     @staticmethod
     @once_differentiable
     def backward(ctx, g_s, g_sbar, g_v, g_vbar):
-        s, sbar, v, vbar, a1, z1, phi3, W1, W2, Wf, bf = ctx.saved_tensors
+        s, sbar, v, vbar, a1, z1, phi3, W1, b1, W2, b2, Wf, bf = ctx.saved_tensors
         gi_s, gi_sbar, gi_v, gi_vbar, g_phi, dWf, dbf = ops.message9_bwd(
             phi3, s, sbar, v, vbar, ctx.geom, Wf, bf, ctx.residual,
             g_s.contiguous(), g_sbar.contiguous(), g_v.contiguous(), g_vbar.contiguous())
         N, F = s.shape
-        gs, gW1, gb1, gW2, gb2 = _phi_backward(g_phi.view(N, 9 * F), s, a1, z1, W1, W2, gi_s)
+        gs, gW1, gb1, gW2, gb2 = _phi_backward(g_phi.view(N, 9 * F), s, a1, z1, W1, b1, W2, b2, gi_s)
         return None, None, gs, gi_sbar, gi_v, gi_vbar, gW1, gb1, gW2, gb2, dWf, dbf
 
 
@@ -140,30 +140,30 @@ class UpdateBlockFn(Function):
         q = ops.linear_fwd(h, A1, c1, 0).view(N, 3, F)
         s_out, v_out = ops.update_combine_fwd(s, v, Uv, Vv, q, residual)
         ctx.residual = residual
-        ctx.save_for_backward(v, Uv, Vv, x, h, z, q, U, V, A0, A1)
+        ctx.save_for_backward(v, Uv, Vv, x, h, z, q, U, V, A0, c0, A1, c1)
         return s_out, v_out
 
     @staticmethod
     @once_differentiable
     def backward(ctx, g_s, g_v):
-        v, Uv, Vv, x, h, z, q, U, V, A0, A1 = ctx.saved_tensors
+        v, Uv, Vv, x, h, z, q, U, V, A0, c0, A1, c1 = ctx.saved_tensors
         g_s, g_v = g_s.contiguous(), g_v.contiguous()
         N, _, F = v.shape
         gq, gUv, gVv = ops.update_combine_bwd(Uv, Vv, q, g_s, g_v)
         gq2 = gq.view(N, 3 * F)
         gz = ops.linear_bwd_input(gq2, A1, z_in=z, dact=SWISH)
-        gA1 = ops.linear_bwd_weight(gq2, h)
-        gc1 = ops.colsum(gq2)
+        gA1 = ops.linear_bwd_weight(gq2, h, A1)
+        gc1 = ops.colsum(gq2, c1)
         gx = ops.linear_bwd_input(gz, A0)
-        gA0 = ops.linear_bwd_weight(gz, x)
-        gc0 = ops.colsum(gz)
+        gA0 = ops.linear_bwd_weight(gz, x, A0)
+        gc0 = ops.colsum(gz, c0)
         gs_in = ops.update_norm_bwd(x, Vv, gx, g_s, gVv, ctx.residual)      # adds the norm path into gVv in place
         v2 = v.view(3 * N, F)
         gUv2, gVv2 = gUv.view(3 * N, F), gVv.view(3 * N, F)
         gv_in = ops.linear_bwd_input(gUv2, U, add=g_v.view(3 * N, F) if ctx.residual else None)
         gv_in = ops.linear_bwd_input(gVv2, V, add=gv_in).view(N, 3, F)
-        gU = ops.linear_bwd_weight(gUv2, v2)
-        gV = ops.linear_bwd_weight(gVv2, v2)
+        gU = ops.linear_bwd_weight(gUv2, v2, U)
+        gV = ops.linear_bwd_weight(gVv2, v2, V)
         return None, gs_in, gv_in, gU, gV, gA0, gc0, gA1, gc1
 
 
@@ -189,15 +189,15 @@ class EmbeddingLookup(Function):
         idx = idx.to(torch.int64).contiguous()
         ctx.padding_idx = padding_idx
         ctx.n_rows = table.shape[0]
-        ctx.save_for_backward(idx)
+        ctx.save_for_backward(idx, table)
         return ops.gather_rows(table, idx)
 
     @staticmethod
     @once_differentiable
     def backward(ctx, g):
-        (idx,) = ctx.saved_tensors
+        idx, table = ctx.saved_tensors
         seg = ops.build_segments(idx, ctx.n_rows)
-        gt = ops.segment_reduce_fwd(g.contiguous(), seg, False)
+        gt = ops.segment_reduce_fwd(g.contiguous(), seg, False, param=table)
         if ctx.padding_idx is not None:
             gt[ctx.padding_idx].zero_()
         return gt, None, None

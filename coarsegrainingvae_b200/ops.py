@@ -19,7 +19,14 @@ def _p(t):
     return t.data_ptr()
 
 
+_raw_stream = torch._C._cuda_getCurrentRawStream if hasattr(torch._C, "_cuda_getCurrentRawStream") else None
+
+
 def _stream():
+    # torch.cuda.current_stream() costs ~65 us per call in this torch build (it re-probes device availability);
+    # the raw accessor is a plain C call.  ~500 launches per training step go through here.
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -68,6 +75,23 @@ class KernelTimer(object):
 
 
 TIMER = None      # set to a KernelTimer to time launches; None (default) adds no events
+
+# Optional gradient sinks: data_ptr of a parameter -> (flat buffer, offset).  When a training step registers its flat
+# gradient buffer here (train.FlatGrads), the weight / bias / filter gradient kernels write straight into that buffer and
+# autograd adopts the view as ``p.grad`` -- no per-parameter accumulate kernels, no flatten copy before the all-reduce.
+# Valid only when every registered parameter is used once per backward (true for every model of the reference).
+GRAD_SINK = {}
+
+
+def _grad_out(param, shape):
+    hit = GRAD_SINK.get(param.data_ptr()) if GRAD_SINK else None
+    if hit is None or param.grad is not None:
+        return torch.empty(shape, dtype=param.dtype, device=param.device)
+    flat, off = hit
+    n = 1
+    for s in shape:
+        n *= s
+    return flat[off:off + n].view(shape)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -295,18 +319,19 @@ def linear_bwd_input(gy, W, z_in=None, dact=0, add=None):
     return gemm(GEMM_NN, gy, W, M, K, N, z_in=z_in, dact=dact, add=add)
 
 
-def linear_bwd_weight(gy, x):
-    """gW[out,in] = gy^T x"""
+def linear_bwd_weight(gy, x, param=None):
+    """gW[out,in] = gy^T x (written into the parameter's gradient sink when one is registered)"""
     rows, n_out = gy.shape
     n_in = x.shape[1]
-    return gemm(GEMM_TN, gy, x, n_out, n_in, rows)
+    out = _grad_out(param, (n_out, n_in)) if param is not None else None
+    return gemm(GEMM_TN, gy, x, n_out, n_in, rows, out=out)
 
 
-def colsum(X):
+def colsum(X, param=None):
     _need_cuda(X)
     lib = _lib.load()
     M, N = X.shape
-    out = torch.empty(N, dtype=torch.float32, device=X.device)
+    out = _grad_out(param, (N,)) if param is not None else torch.empty(N, dtype=torch.float32, device=X.device)
     _lib.check(lib.cgvae_colsum(_p(X), X.stride(0), M, N, _p(out), _stream()), "colsum")
     return out
 
@@ -335,7 +360,7 @@ def message_fwd(n_split, phi, v_send, v_recv, geom, Wf, bf, res_s, res_v, want_q
     return out_s, out_v, q
 
 
-def message_bwd(n_split, phi, v_send, v_recv, q, geom, Wf, bf, g_out_s, g_out_v, residual):
+def message_bwd(n_split, phi, v_send, v_recv, q, geom, Wf, bf, g_out_s, g_out_v, residual, sink=True):
     """returns (g_phi [n_send,K,F], g_v_send [n_send,3,F], dWf [K*F,R], dbf [K*F])."""
     _need_cuda(phi)
     lib = _lib.load()
@@ -344,8 +369,8 @@ def message_bwd(n_split, phi, v_send, v_recv, q, geom, Wf, bf, g_out_s, g_out_v,
     dev = phi.device
     g_phi = torch.empty((g.n_send, n_split, F), dtype=torch.float32, device=dev)
     g_v = torch.empty((g.n_send, 3, F), dtype=torch.float32, device=dev)
-    dWf = torch.empty((n_split * F, geom.n_rbf), dtype=torch.float32, device=dev)
-    dbf = torch.empty((n_split * F,), dtype=torch.float32, device=dev)
+    dWf = _grad_out(Wf, (n_split * F, geom.n_rbf)) if sink else torch.empty((n_split * F, geom.n_rbf), dtype=torch.float32, device=dev)
+    dbf = _grad_out(bf, (n_split * F,)) if sink else torch.empty((n_split * F,), dtype=torch.float32, device=dev)
     ws_bytes = int(lib.cgvae_message_bwd_ws_bytes(n_split, F, geom.rb, g.n_send))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     t0 = TIMER.begin("message_bwd") if TIMER is not None else None
@@ -389,8 +414,8 @@ def message9_bwd(phi, s, sbar, v, vbar, geom, Wf, bf, residual, g_s, g_sbar, g_v
     R = geom.n_rbf
     E = g.n_edges
     if E > 0:
-        dWf = gemm(GEMM_TN, gw, geom.basis, 9 * F, R, E)
-        dbf = gemm(GEMM_TN, gw, geom.basis[:, R:], 9 * F, 1, E).reshape(9 * F)
+        dWf = gemm(GEMM_TN, gw, geom.basis, 9 * F, R, E, out=_grad_out(Wf, (9 * F, R)))
+        dbf = gemm(GEMM_TN, gw, geom.basis[:, R:], 9 * F, 1, E, out=_grad_out(bf, (9 * F,)).view(9 * F, 1)).reshape(9 * F)
     else:
         dWf = torch.zeros((9 * F, R), dtype=torch.float32, device=dev)
         dbf = torch.zeros((9 * F,), dtype=torch.float32, device=dev)
@@ -444,12 +469,13 @@ def update_norm_bwd(x, Vv, gx, g_s, gVv, residual):
     return gs_in
 
 
-def segment_reduce_fwd(X, seg, mean):
+def segment_reduce_fwd(X, seg, mean, param=None):
     _need_cuda(X)
     lib = _lib.load()
     X = _f32(X)
     W = int(np.prod(X.shape[1:]))
-    out = torch.empty((seg.n_beads,) + tuple(X.shape[1:]), dtype=torch.float32, device=X.device)
+    shape = (seg.n_beads,) + tuple(X.shape[1:])
+    out = _grad_out(param, shape) if param is not None else torch.empty(shape, dtype=torch.float32, device=X.device)
     _lib.check(lib.cgvae_segment_reduce_fwd(_p(X), _p(seg.rowptr), _p(seg.atoms), seg.n_beads, W, int(bool(mean)), _p(out),
                                             _stream()), "segment_reduce_fwd")
     return out

@@ -38,9 +38,11 @@ def training_loss(outputs, xyz, bond_edge_list, beta, gamma):
 
 class FlatGrads(object):
     """One contiguous fp32 buffer holding the gradients of the parameters that actually receive one
-    (two thirds of the reference's parameters are constructed and never used: SURVEY.md section 5).  ``p.grad`` of each
-    such parameter is a view into the buffer, so backward accumulates in place, the data-parallel all-reduce is ONE
-    collective on ONE tensor, and clipping is two passes over it."""
+    (two thirds of the reference's parameters are constructed and never used: SURVEY.md section 5).  On CUDA the
+    buffer is registered as the gradient SINK of those parameters (ops.GRAD_SINK): the weight / bias / filter gradient
+    kernels write straight into it and autograd adopts the views as ``p.grad`` -- no accumulate kernels, no zero fill,
+    no flatten copy; the data-parallel all-reduce is ONE collective on ONE tensor and clipping is two passes over it.
+    On CPU (tests) ``p.grad`` is pre-set to views and autograd accumulates in place."""
 
     def __init__(self, params):
         self.params = [p for p in params]
@@ -48,13 +50,39 @@ class FlatGrads(object):
         dev = self.params[0].device if self.params else "cpu"
         dtype = self.params[0].dtype if self.params else torch.float32
         self.flat = torch.zeros(n, dtype=dtype, device=dev)
+        self.sink = self.flat.is_cuda
+        self.views = []
         off = 0
         for p in self.params:
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            self.views.append((off, p.numel()))
+            if self.sink:
+                from . import ops
+                ops.GRAD_SINK[p.data_ptr()] = (self.flat, off)
+                p.grad = None
+            else:
+                p.grad = self.flat[off:off + p.numel()].view_as(p)
             off += p.numel()
 
     def zero_(self):
-        self.flat.zero_()
+        if self.sink:
+            for p in self.params:          # every region is fully overwritten by its kernel: nothing to clear
+                p.grad = None
+        else:
+            self.flat.zero_()
+
+    def check_adopted(self):
+        """after a backward: every parameter's .grad must alias its region of the flat buffer."""
+        base = self.flat.data_ptr()
+        for p, (off, n) in zip(self.params, self.views):
+            if p.grad is None or p.grad.data_ptr() != base + 4 * off:
+                return False
+        return True
+
+    def release(self):
+        if self.sink:
+            from . import ops
+            for p in self.params:
+                ops.GRAD_SINK.pop(p.data_ptr(), None)
 
     def allreduce_mean_(self, group=None):
         """gradient exchange of data-parallel training: one all-reduce(sum) over NVLink, then 1/world."""
@@ -105,6 +133,10 @@ class TrainStep(object):
         self.flat = FlatGrads([p for _, p in used])
         fused = self.flat.flat.is_cuda
         self.opt = torch.optim.Adam(self.flat.params, lr=self.lr, fused=fused)
+        if self.flat.sink:                 # verify once that autograd adopts the sink views (else fall back to copies)
+            self.forward_backward(batch, eps)
+            if not self.flat.check_adopted():
+                raise RuntimeError("gradient sink views were not adopted by autograd")
         return [k for k, _ in used]
 
     def forward_backward(self, batch, eps=None):

@@ -128,7 +128,7 @@ def gemm(form, A, B, M, N, K, bias=None, act=0, z_out=False, z_in=None, dact=0, 
     return (C, Z) if z_out else C
 
 
-def colsum(X):
+def colsum(X, param=None):
     return X.sum(0)
 
 
@@ -169,7 +169,7 @@ def message_fwd(n_split, phi, v_send, v_recv, geom, Wf, bf, res_s, res_v, want_q
     return out_s, out_v, (q if want_q else None)
 
 
-def message_bwd(n_split, phi, v_send, v_recv, q, geom, Wf, bf, g_out_s, g_out_v, residual):
+def message_bwd(n_split, phi, v_send, v_recv, q, geom, Wf, bf, g_out_s, g_out_v, residual, sink=True):
     g = geom.graph
     F = phi.shape[-1]
     K = n_split
@@ -306,7 +306,7 @@ def update_norm_bwd(x, Vv, gx, g_s, gVv, residual):
     return gx[:, :F] + g_s if residual else gx[:, :F].clone()
 
 
-def segment_reduce_fwd(X, seg, mean):
+def segment_reduce_fwd(X, seg, mean, param=None):
     out = torch.zeros((seg.n_beads,) + tuple(X.shape[1:]), dtype=X.dtype).index_add_(0, seg.mapping, X)
     if mean:
         cnt = (seg.rowptr[1:] - seg.rowptr[:-1]).clamp(min=1).to(X.dtype)

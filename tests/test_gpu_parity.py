@@ -315,3 +315,33 @@ def test_message_layer_full_size_equivariance():
         ds_r, dv_r = blk(s0.to(DEV), (v0 @ Q.t()).to(DEV), r @ Q.t().to(DEV), nbrs)
     assert rel_err(ds_r, ds) < 1e-5
     assert rel_err(dv_r, dv @ Q.t().to(DEV)) < 1e-5
+
+
+def test_train_step_gradient_sink_matches_plain_autograd():
+    """train.TrainStep makes the weight-gradient kernels write straight into one flat buffer (ops.GRAD_SINK); the
+    gradients must be bit-identical to the plain autograd path and alias the buffer."""
+    from coarsegrainingvae_b200.factory import build_cgvae
+    from coarsegrainingvae_b200.train import TrainStep, training_loss
+    cfg = dict(synthetic.CONFIGS["c1_dipeptide"])
+    cfg.update(batch=3, n_basis=64, enc_nconv=2, dec_nconv=2)
+    batch = _to(synthetic.cgvae_batch(cfg, 0, _gpu_radius, cg.CG_collate), DEV)
+    torch.manual_seed(5)
+    model = build_cgvae(cfg["n_basis"], cfg["n_rbf"], cfg["enc_nconv"], cfg["dec_nconv"], cfg["atom_cutoff"],
+                        cfg["cg_cutoff"], cfg["n_cgs"]).to(DEV)
+    eps = torch.randn(9, 64, device=DEV)
+    out = model(batch, eps=eps)
+    training_loss(out, out[4], batch["bond_edge_list"], cfg["beta"], cfg["gamma"])[0].backward()
+    plain = {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+    step = TrainStep(model, cfg["beta"], cfg["gamma"])
+    used = step.prepare(batch, eps)
+    assert sorted(used) == sorted(plain)
+    step.forward_backward(batch, eps)
+    assert step.flat.check_adopted()
+    for k, p in model.named_parameters():
+        if k in plain:
+            assert torch.equal(p.grad, plain[k]), k
+    before = step.flat.flat.clone()
+    loss = step.step(batch, eps)
+    assert torch.isfinite(loss) and not torch.equal(before, step.flat.flat)   # clipped in place
+    step.flat.release()
+    assert not ops.GRAD_SINK
