@@ -30,9 +30,9 @@ SIGNATURES = {
     "cgvae_radius_graph_fill": (_INT, [_P, _I64, _P, _I64, _F32, _INT, _INT, _P, _P, _P, _SZ, _P]),
     "cgvae_exclusive_scan": (_INT, [_P, _I64, _P, _P]),
     "cgvae_edge_orientation": (_INT, [_P, _I64, _P, _P]),
-    "cgvae_csr_count": (_INT, [_P, _I64, _I64, _I64, _P, _P, _P]),
+    "cgvae_csr_count": (_INT, [_P, _I64, _P, _INT, _I64, _I64, _P, _P, _P]),
     "cgvae_scan_i32": (_INT, [_P, _I64, _P, _P]),
-    "cgvae_csr_fill": (_INT, [_P, _I64, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "cgvae_csr_fill": (_INT, [_P, _I64, _P, _INT, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _P]),
     "cgvae_segment_count": (_INT, [_P, _I64, _I64, _P, _P]),
     "cgvae_segment_rank": (_INT, [_P, _I64, _I64, _P, _P, _P, _P, _P, _P]),
     "cgvae_edge_geometry": (_INT, [_P, _P, _P, _P, _P, _I64, _I64, _P, _INT, _INT, _F32, _P, _P, _P, _P, _P]),
@@ -44,7 +44,7 @@ SIGNATURES = {
     "cgvae_message_bwd": (_INT, [_INT, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _INT, _INT, _INT, _P, _P,
                                  _INT, _INT, _P, _P, _P, _P, _P, _SZ, _P]),
     "cgvae_message9_fwd": (_INT, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _INT, _INT, _INT, _INT, _P, _P, _P, _P, _P]),
-    "cgvae_message9_bwd": (_INT, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _INT, _INT, _INT, _INT,
+    "cgvae_message9_bwd": (_INT, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _INT, _INT, _INT, _INT,
                                   _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "cgvae_update_norm_fwd": (_INT, [_P, _P, _I64, _INT, _P, _P]),
     "cgvae_update_combine_fwd": (_INT, [_P, _P, _P, _P, _P, _I64, _INT, _INT, _P, _P, _P]),

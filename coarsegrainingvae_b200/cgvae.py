@@ -18,15 +18,21 @@ class BatchGraphs(object):
     """CSR graphs and segment tables of one batch, built once and shared by encoder / prior / decoder
     (the reference re-runs make_directed in each of them: cgvae.py:270-271,378,87,165)."""
 
-    def __init__(self):
+    def __init__(self, nbr_count=None, cg_nbr_count=None):
         self.atom = None      # ops.Graph over atoms (directed)
         self.cg = None        # ops.Graph over beads (directed)
         self.seg = None       # ops.Segments (mapping)
         self.contract = None  # ops.Graph atoms -> beads
         self._geom = {}
+        # static-shape mode (CUDA-graph replay): nbr_list / CG_nbr_list are one-directional lists padded to a fixed
+        # capacity and these int64 device scalars hold the live row counts; the flipped half of make_directed is
+        # generated inside the CSR kernels and no host read happens.
+        self.counts = {"atom": nbr_count, "cg": cg_nbr_count}
 
-    @staticmethod
-    def _directed_graph(nbr_list, n_nodes, already_directed=False):
+    def directed_graph(self, which, nbr_list, n_nodes, already_directed=False):
+        count = self.counts.get(which)
+        if count is not None:
+            return ops.build_graph(nbr_list, n_nodes, symmetrize=True, n_edges_dev=count)
         pairs = nbr_list if already_directed else make_directed(nbr_list)[0]
         return ops.build_graph(pairs, n_nodes)
 
@@ -70,7 +76,7 @@ class EquivariantPsuedoDecoder(nn.Module):
     def forward(self, cg_xyz, CG_nbr_list, mapping, S, graphs=None, planar=False):
         g = graphs if graphs is not None else BatchGraphs()
         if g.cg is None:
-            g.cg = BatchGraphs._directed_graph(CG_nbr_list, S.shape[0])
+            g.cg = g.directed_graph("cg", CG_nbr_list, S.shape[0])
         geom = g.geometry("cg", cg_xyz, cg_xyz, self.n_rbf, self.cutoff)
         n, f = S.shape
         V = torch.zeros(n, 3, f, device=S.device, dtype=S.dtype)
@@ -100,7 +106,7 @@ class EquivariantDecoder(nn.Module):
     def forward(self, cg_xyz, CG_nbr_list, mapping, H, graphs=None, planar=False):
         g = graphs if graphs is not None else BatchGraphs()
         if g.cg is None:
-            g.cg = BatchGraphs._directed_graph(CG_nbr_list, H.shape[0])
+            g.cg = g.directed_graph("cg", CG_nbr_list, H.shape[0])
         geom = g.geometry("cg", cg_xyz, cg_xyz, self.n_rbf, self.cutoff)
         V = None  # zero until the first message layer has run
         for i, message_block in enumerate(self.message_blocks):
@@ -144,7 +150,7 @@ class EquiEncoder(nn.Module):
     def forward(self, z, xyz, cg_xyz, mapping, nbr_list, cg_nbr_list, graphs=None, num_beads=None):
         g = graphs if graphs is not None else BatchGraphs()
         if g.atom is None:
-            g.atom = BatchGraphs._directed_graph(nbr_list, xyz.shape[0], already_directed=self.dir_mp)
+            g.atom = g.directed_graph("atom", nbr_list, xyz.shape[0], already_directed=self.dir_mp)
         if g.seg is None:
             g.seg = ops.build_segments(mapping, _num_beads(mapping, num_beads))
         if g.contract is None:
@@ -185,7 +191,7 @@ class CGprior(nn.Module):
     def forward(self, cg_z, cg_xyz, cg_nbr_list, graphs=None):
         g = graphs if graphs is not None else BatchGraphs()
         if g.cg is None:
-            g.cg = BatchGraphs._directed_graph(cg_nbr_list, cg_xyz.shape[0])
+            g.cg = g.directed_graph("cg", cg_nbr_list, cg_xyz.shape[0])
         geom = g.geometry("cg", cg_xyz, cg_xyz, self.n_rbf, self.cutoff)
         h = _embed(self.atom_embed, cg_z)
         v = None
@@ -258,7 +264,7 @@ class CGequiVAE(nn.Module):
     def forward(self, batch, eps=None):
         atomic_nums, cg_z, xyz, cg_xyz, nbr_list, CG_nbr_list, mapping, num_CGs = self.get_inputs(batch)
         xyz, cg_xyz = xyz.contiguous(), cg_xyz.contiguous()
-        g = batch.get('_graphs') or BatchGraphs()
+        g = batch.get('_graphs') or BatchGraphs(batch.get('nbr_count'), batch.get('CG_nbr_count'))
         S_I, s_i = self.encoder(atomic_nums, xyz, cg_xyz, mapping, nbr_list, CG_nbr_list, graphs=g,
                                 num_beads=cg_xyz.shape[0])
         if self.prior_net:
@@ -314,5 +320,5 @@ class PCN(nn.Module):
         cg_z, xyz, cg_xyz, nbr_list, CG_nbr_list, mapping, num_CGs = self.get_inputs(batch)
         S_I = _embed(self.embedding, cg_z)
         xyz_recon = self.decoder(cg_xyz.contiguous(), CG_nbr_list, S_I, batch['ca_idx'], mapping, num_CGs,
-                                 graphs=batch.get('_graphs'))
+                                 graphs=batch.get('_graphs') or BatchGraphs(None, batch.get('CG_nbr_count')))
         return None, None, None, None, xyz, xyz_recon

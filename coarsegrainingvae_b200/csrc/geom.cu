@@ -21,6 +21,12 @@ __global__ void __launch_bounds__(256) edge_geometry_kernel(
     float* __restrict__ unit) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= E) return;
+  if (e >= rowptr[n_recv]) {
+    // tail of a static-capacity graph (CUDA-graph replay): neutral records, so padded rows contribute exact zeros
+    reinterpret_cast<float4*>(unit)[e] = make_float4(0.f, 0.f, 0.f, 1.f);
+    for (int r = 0; r < RB; ++r) basis[e * RB + r] = 0.f;
+    return;
+  }
   float rx, ry, rz;
   if (r_edge != nullptr) {
     // block-level API: the caller supplies r_ij per edge in its original edge order

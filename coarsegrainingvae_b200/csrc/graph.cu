@@ -364,38 +364,61 @@ __global__ void edge_orientation_kernel(const int64_t* __restrict__ pairs, int64
   if (__any_sync(0xffffffffu, down) && (threadIdx.x & 31) == 0) atomicOr(&flags[1], 1);
 }
 
-__global__ void csr_count_kernel(const int64_t* __restrict__ pairs, int64_t E, int32_t* __restrict__ deg_r, int32_t* __restrict__ deg_s) {
+// Directed edge d of an edge list.  Plain list: d < n -> pairs[d].  symmetrize (make_directed, conv.py:19:
+// cat([nbrs, nbrs.flip(1)])): d < n -> pairs[d]; n <= d < 2n -> pairs[d-n] flipped.  n comes from device memory when
+// n_dev != nullptr (static-capacity lists replayed inside a CUDA graph), else from the host argument.
+__device__ __forceinline__ bool directed_edge(const int64_t* __restrict__ pairs, int64_t d, int64_t n_host,
+                                              const int64_t* __restrict__ n_dev, int symmetrize, int64_t& i, int64_t& j) {
+  const int64_t n = n_dev ? *n_dev : n_host;
+  if (d < n) { i = pairs[2 * d]; j = pairs[2 * d + 1]; return true; }
+  if (symmetrize && d < 2 * n) { i = pairs[2 * (d - n) + 1]; j = pairs[2 * (d - n)]; return true; }
+  return false;
+}
+
+__global__ void csr_count_kernel(const int64_t* __restrict__ pairs, int64_t E, const int64_t* __restrict__ n_dev, int symmetrize,
+                                 int32_t* __restrict__ deg_r, int32_t* __restrict__ deg_s) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= E) return;
-  atomicAdd(&deg_r[pairs[2 * e]], 1);
-  atomicAdd(&deg_s[pairs[2 * e + 1]], 1);
+  int64_t i, j;
+  if (!directed_edge(pairs, e, E, n_dev, symmetrize, i, j)) return;
+  atomicAdd(&deg_r[i], 1);
+  atomicAdd(&deg_s[j], 1);
 }
 
 // place edge ids into their receiver row / sender row (arbitrary order; rows are sorted afterwards)
-__global__ void csr_place_kernel(const int64_t* __restrict__ pairs, int64_t E, const int32_t* __restrict__ rowptr_r,
-                                 const int32_t* __restrict__ rowptr_s, int32_t* __restrict__ cursor_r, int32_t* __restrict__ cursor_s,
+__global__ void csr_place_kernel(const int64_t* __restrict__ pairs, int64_t E, const int64_t* __restrict__ n_dev, int symmetrize,
+                                 const int32_t* __restrict__ rowptr_r, const int32_t* __restrict__ rowptr_s,
+                                 int32_t* __restrict__ cursor_r, int32_t* __restrict__ cursor_s,
                                  int32_t* __restrict__ eid_r, int32_t* __restrict__ eid_s) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= E) return;
-  const int64_t i = pairs[2 * e], j = pairs[2 * e + 1];
+  int64_t i, j;
+  if (!directed_edge(pairs, e, E, n_dev, symmetrize, i, j)) return;
   eid_r[rowptr_r[i] + atomicAdd(&cursor_r[i], 1)] = (int32_t)e;
   eid_s[rowptr_s[j] + atomicAdd(&cursor_s[j], 1)] = (int32_t)e;
 }
 
-__global__ void csr_finish_r_kernel(const int64_t* __restrict__ pairs, int64_t E, const int32_t* __restrict__ eid_r,
+// slots t < total (= rowptr[n_rows], read on the device) are live; the tail of a static-capacity graph is zeroed
+__global__ void csr_finish_r_kernel(const int64_t* __restrict__ pairs, int64_t E, const int64_t* __restrict__ n_dev, int symmetrize,
+                                    int64_t cap, const int32_t* __restrict__ total, const int32_t* __restrict__ eid_r,
                                     int32_t* __restrict__ col, int32_t* __restrict__ slot_of_edge) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= E) return;
+  if (t >= cap) return;
+  if (t >= *total) { col[t] = 0; return; }
   const int e = eid_r[t];
-  col[t] = (int32_t)pairs[2 * (int64_t)e + 1];
+  int64_t i, j;
+  directed_edge(pairs, e, E, n_dev, symmetrize, i, j);
+  col[t] = (int32_t)j;
   slot_of_edge[e] = (int32_t)t;
 }
-__global__ void csr_finish_s_kernel(const int64_t* __restrict__ pairs, int64_t E, const int32_t* __restrict__ eid_s,
+__global__ void csr_finish_s_kernel(const int64_t* __restrict__ pairs, int64_t E, const int64_t* __restrict__ n_dev, int symmetrize,
+                                    int64_t cap, const int32_t* __restrict__ total, const int32_t* __restrict__ eid_s,
                                     const int32_t* __restrict__ slot_of_edge, int32_t* __restrict__ col_t, int32_t* __restrict__ perm_t) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= E) return;
+  if (t >= cap) return;
+  if (t >= *total) { col_t[t] = 0; perm_t[t] = 0; return; }
   const int e = eid_s[t];
-  col_t[t] = (int32_t)pairs[2 * (int64_t)e];
+  int64_t i, j;
+  directed_edge(pairs, e, E, n_dev, symmetrize, i, j);
+  col_t[t] = (int32_t)i;
   perm_t[t] = slot_of_edge[e];
 }
 
@@ -513,21 +536,23 @@ int cgvae_edge_orientation(const int64_t* pairs, int64_t n_edges, int32_t* flags
   return launched("edge_orientation");
 }
 
-int cgvae_csr_count(const int64_t* pairs, int64_t n_edges, int64_t n_recv, int64_t n_send, int32_t* deg_r, int32_t* deg_s,
-                    cgvae_stream_t stream) {
+int cgvae_csr_count(const int64_t* pairs, int64_t n_edges, const int64_t* n_edges_dev, int symmetrize, int64_t n_recv,
+                    int64_t n_send, int32_t* deg_r, int32_t* deg_s, cgvae_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  CGVAE_REQUIRE(n_edges >= 0 && n_edges < INT_MAX && deg_r && deg_s, "csr_count: bad arguments");
+  const int64_t cap = symmetrize ? 2 * n_edges : n_edges;
+  CGVAE_REQUIRE(n_edges >= 0 && cap < INT_MAX && deg_r && deg_s, "csr_count: bad arguments");
   CGVAE_CUDA(cudaMemsetAsync(deg_r, 0, sizeof(int32_t) * (size_t)n_recv, st));
   CGVAE_CUDA(cudaMemsetAsync(deg_s, 0, sizeof(int32_t) * (size_t)n_send, st));
-  if (n_edges == 0) return 0;
-  csr_count_kernel<<<(unsigned)ceil_div(n_edges, 256), 256, 0, st>>>(pairs, n_edges, deg_r, deg_s);
+  if (cap == 0) return 0;
+  csr_count_kernel<<<(unsigned)ceil_div(cap, 256), 256, 0, st>>>(pairs, n_edges, n_edges_dev, symmetrize, deg_r, deg_s);
   return launched("csr_count");
 }
 
-int cgvae_csr_fill(const int64_t* pairs, int64_t n_edges, int64_t n_recv, int64_t n_send, const int32_t* rowptr_r,
-                   const int32_t* rowptr_s, int32_t* scratch, int32_t* col, int32_t* eid, int32_t* col_t, int32_t* perm_t,
-                   cgvae_stream_t stream) {
+int cgvae_csr_fill(const int64_t* pairs, int64_t n_edges_in, const int64_t* n_edges_dev, int symmetrize, int64_t n_recv,
+                   int64_t n_send, const int32_t* rowptr_r, const int32_t* rowptr_s, int32_t* scratch, int32_t* col, int32_t* eid,
+                   int32_t* col_t, int32_t* perm_t, cgvae_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n_edges = symmetrize ? 2 * n_edges_in : n_edges_in;   // capacity in directed edges
   if (n_edges == 0) return 0;
   CGVAE_REQUIRE(pairs && rowptr_r && rowptr_s && scratch && col && eid && col_t && perm_t, "csr_fill: null pointer");
   // scratch: cursor_r[n_recv] | cursor_s[n_send] | eid_s[E] | slot_of_edge[E]
@@ -537,7 +562,7 @@ int cgvae_csr_fill(const int64_t* pairs, int64_t n_edges, int64_t n_recv, int64_
   int32_t* slot_of_edge = eid_s + n_edges;
   CGVAE_CUDA(cudaMemsetAsync(cursor_r, 0, sizeof(int32_t) * (size_t)(n_recv + n_send), st));
   const unsigned gb = (unsigned)ceil_div(n_edges, 256);
-  csr_place_kernel<<<gb, 256, 0, st>>>(pairs, n_edges, rowptr_r, rowptr_s, cursor_r, cursor_s, eid, eid_s);
+  csr_place_kernel<<<gb, 256, 0, st>>>(pairs, n_edges_in, n_edges_dev, symmetrize, rowptr_r, rowptr_s, cursor_r, cursor_s, eid, eid_s);
   if (int rc = launched("csr_place")) return rc;
   // rows were filled in atomic (arbitrary) order: sorting by edge id makes the layout deterministic and
   // keeps the reference's edge-list order inside every row
@@ -545,9 +570,11 @@ int cgvae_csr_fill(const int64_t* pairs, int64_t n_edges, int64_t n_recv, int64_
   if (int rc = launched("csr_sort_r")) return rc;
   sort_rows_kernel<<<(unsigned)ceil_div(n_send, kSortWarps), kSortWarps * 32, 0, st>>>(rowptr_s, n_send, eid_s);
   if (int rc = launched("csr_sort_s")) return rc;
-  csr_finish_r_kernel<<<gb, 256, 0, st>>>(pairs, n_edges, eid, col, slot_of_edge);
+  csr_finish_r_kernel<<<gb, 256, 0, st>>>(pairs, n_edges_in, n_edges_dev, symmetrize, n_edges, rowptr_r + n_recv, eid, col,
+                                          slot_of_edge);
   if (int rc = launched("csr_finish_r")) return rc;
-  csr_finish_s_kernel<<<gb, 256, 0, st>>>(pairs, n_edges, eid_s, slot_of_edge, col_t, perm_t);
+  csr_finish_s_kernel<<<gb, 256, 0, st>>>(pairs, n_edges_in, n_edges_dev, symmetrize, n_edges, rowptr_s + n_send, eid_s,
+                                          slot_of_edge, col_t, perm_t);
   return launched("csr_finish_s");
 }
 

@@ -571,7 +571,7 @@ int cgvae_message9_fwd(const float* phi, const float* s, const float* sbar, cons
 int cgvae_message9_bwd(const float* phi, const float* s, const float* sbar, const float* v, const float* vbar,
                        const int32_t* rowptr, const int32_t* col, const int32_t* rowptr_t, const int32_t* col_t,
                        const int32_t* perm_t, const float* basis, const float* unit, const float* Wf, const float* bf, int64_t n,
-                       int F, int R, int RB, int residual, const float* g_s, const float* g_sbar, const float* g_v,
+                       int64_t n_edge_slots, int F, int R, int RB, int residual, const float* g_s, const float* g_sbar, const float* g_v,
                        const float* g_vbar, float* gi_s, float* gi_sbar, float* gi_v, float* gi_vbar, float* g_phi, float* gw,
                        cgvae_stream_t stream) {
   CGVAE_REQUIRE(RB <= kMaxRB9 && R + 1 <= RB && RB % 4 == 0, "message9_bwd: bad RB=%d R=%d", RB, R);
@@ -579,6 +579,8 @@ int cgvae_message9_bwd(const float* phi, const float* s, const float* sbar, cons
   CGVAE_REQUIRE(phi && s && sbar && v && vbar && rowptr && col && rowptr_t && col_t && perm_t && basis && unit && Wf && bf && g_s &&
                     g_sbar && g_v && g_vbar && gi_s && gi_sbar && gi_v && gi_vbar && g_phi && gw, "message9_bwd: null pointer");
   dim3 grid((unsigned)ceil_div(n, kMsgWarps), (unsigned)ceil_div(F, 32));
+  // gw rows of unused (padded) edge slots must read as zero in the dWf = gw^T basis contraction
+  CGVAE_CUDA(cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)n_edge_slots * 9 * (size_t)F, (cudaStream_t)stream));
   message9_bwd_kernel<<<grid, kMsgWarps * 32, 0, (cudaStream_t)stream>>>(phi, s, sbar, v, vbar, rowptr, col, rowptr_t, col_t, perm_t,
                                                                          basis, unit, Wf, bf, n, F, R, RB, residual, g_s, g_sbar,
                                                                          g_v, g_vbar, gi_s, gi_sbar, gi_v, gi_vbar, g_phi, gw);

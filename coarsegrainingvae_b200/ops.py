@@ -138,10 +138,19 @@ def rb_for(n_rbf):
     return rb
 
 
+_COEF_CACHE = {}
+
+
 def rbf_coefficients(n_rbf, cutoff, device):
-    """n * pi / cutoff evaluated exactly like the reference (modules.py:145,156): fp32 tensor ops."""
-    n = torch.arange(1, n_rbf + 1).float()
-    return (n * np.pi / cutoff).to(device)
+    """n * pi / cutoff evaluated exactly like the reference (modules.py:145,156): fp32 CPU tensor ops, then kept on the
+    device (cached: a pageable H2D copy per layer would serialise the stream and cannot be graph-captured)."""
+    key = (int(n_rbf), float(cutoff), str(device))
+    hit = _COEF_CACHE.get(key)
+    if hit is None:
+        n = torch.arange(1, n_rbf + 1).float()
+        hit = (n * np.pi / cutoff).to(device)
+        _COEF_CACHE[key] = hit
+    return hit
 
 
 def exclusive_scan(counts_i32, out_dtype=torch.int64):
@@ -208,19 +217,25 @@ def edge_orientation(pairs):
     return bool(f[0]), bool(f[1])
 
 
-def build_graph(pairs, n_recv, n_send=None):
-    """CSR views of a directed int64 edge list [E,2] (col 0 receiver, col 1 sender)."""
+def build_graph(pairs, n_recv, n_send=None, symmetrize=False, n_edges_dev=None):
+    """CSR views of an int64 edge list [E,2] (col 0 receiver, col 1 sender).
+
+    symmetrize: ``pairs`` is one-directional and the flipped half of make_directed (conv.py:19) is generated inside the
+    kernels (directed edge E+e = pairs[e] flipped).  n_edges_dev: int64 device scalar with the live number of rows of
+    ``pairs`` (its shape is then a static capacity) -- fixed launch shapes for CUDA-graph replay."""
     _need_cuda(pairs)
     lib = _lib.load()
     if n_send is None:
         n_send = n_recv
     pairs = pairs.to(torch.int64).contiguous()
-    E = pairs.shape[0]
+    E_in = pairs.shape[0]
+    E = 2 * E_in if symmetrize else E_in
     dev = pairs.device
     st = _stream()
+    sym = int(bool(symmetrize))
     deg_r = torch.empty(n_recv, dtype=torch.int32, device=dev)
     deg_s = torch.empty(n_send, dtype=torch.int32, device=dev)
-    _lib.check(lib.cgvae_csr_count(_p(pairs), E, n_recv, n_send, _p(deg_r), _p(deg_s), st), "csr_count")
+    _lib.check(lib.cgvae_csr_count(_p(pairs), E_in, _p(n_edges_dev), sym, n_recv, n_send, _p(deg_r), _p(deg_s), st), "csr_count")
     rowptr = exclusive_scan(deg_r, torch.int32)
     rowptr_t = exclusive_scan(deg_s, torch.int32)
     col = torch.empty(E, dtype=torch.int32, device=dev)
@@ -228,8 +243,8 @@ def build_graph(pairs, n_recv, n_send=None):
     col_t = torch.empty(E, dtype=torch.int32, device=dev)
     perm_t = torch.empty(E, dtype=torch.int32, device=dev)
     scratch = torch.empty(n_recv + n_send + 2 * E + 4, dtype=torch.int32, device=dev)
-    _lib.check(lib.cgvae_csr_fill(_p(pairs), E, n_recv, n_send, _p(rowptr), _p(rowptr_t), _p(scratch), _p(col), _p(eid),
-                                  _p(col_t), _p(perm_t), st), "csr_fill")
+    _lib.check(lib.cgvae_csr_fill(_p(pairs), E_in, _p(n_edges_dev), sym, n_recv, n_send, _p(rowptr), _p(rowptr_t), _p(scratch),
+                                  _p(col), _p(eid), _p(col_t), _p(perm_t), st), "csr_fill")
     return Graph(n_recv, n_send, E, rowptr, col, eid, rowptr_t, col_t, perm_t)
 
 
@@ -407,8 +422,8 @@ def message9_bwd(phi, s, sbar, v, vbar, geom, Wf, bf, residual, g_s, g_sbar, g_v
     g_phi = torch.empty((n, 9, F), dtype=torch.float32, device=dev)
     gw = torch.empty((g.n_edges, 9 * F), dtype=torch.float32, device=dev)
     _lib.check(lib.cgvae_message9_bwd(_p(phi), _p(s), _p(sbar), _p(v), _p(vbar), _p(g.rowptr), _p(g.col), _p(g.rowptr_t),
-                                      _p(g.col_t), _p(g.perm_t), _p(geom.basis), _p(geom.unit), _p(Wf), _p(bf), n, F, geom.n_rbf,
-                                      geom.rb, int(bool(residual)), _p(g_s), _p(g_sbar), _p(g_v), _p(g_vbar), _p(gi[0]),
+                                      _p(g.col_t), _p(g.perm_t), _p(geom.basis), _p(geom.unit), _p(Wf), _p(bf), n, g.n_edges, F,
+                                      geom.n_rbf, geom.rb, int(bool(residual)), _p(g_s), _p(g_sbar), _p(g_v), _p(g_vbar), _p(gi[0]),
                                       _p(gi[1]), _p(gi[2]), _p(gi[3]), _p(g_phi), _p(gw), _stream()), "message9_bwd")
     # dWf[9F,R] = gw^T basis[:, :R] ; dbf[9F] = gw^T basis[:, R]   (DistanceEmbed weight / bias gradients)
     R = geom.n_rbf

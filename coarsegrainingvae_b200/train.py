@@ -17,9 +17,10 @@ def kl_divergence(mu1, std1, mu2, std2):
                   + torch.log(std2.pow(2)).sum(-1) - torch.log(std1.pow(2)).sum(-1) - std1.shape[-1]).mean()
 
 
-def training_loss(outputs, xyz, bond_edge_list, beta, gamma):
+def training_loss(outputs, xyz, bond_edge_list, beta, gamma, bond_count=None):
     """scripts/utils.py:117-141: MSE + beta*KL + gamma*bond-graph loss, all on the device (the reference moves the
-    edge list and the target coordinates to the CPU first: utils.py:127-128)."""
+    edge list and the target coordinates to the CPU first: utils.py:127-128).  ``bond_count`` (device scalar): number of
+    live rows of a zero-padded static-capacity ``bond_edge_list`` -- padded (0, 0) rows contribute exactly 0 to the sum."""
     mu, sigma, pmu, pstd, _, xyz_recon = outputs
     recon = (xyz_recon - xyz).pow(2).mean()
     loss = recon
@@ -31,7 +32,10 @@ def training_loss(outputs, xyz, bond_edge_list, beta, gamma):
         a, b = bond_edge_list[:, 0], bond_edge_list[:, 1]
         gen = ((xyz_recon[a] - xyz_recon[b]).pow(2).sum(-1) + EPS).sqrt()
         dat = ((xyz[a] - xyz[b]).pow(2).sum(-1) + EPS).sqrt()
-        graph = (gen - dat).pow(2).mean()
+        if bond_count is None:
+            graph = (gen - dat).pow(2).mean()
+        else:
+            graph = (gen - dat).pow(2).sum() / bond_count.to(gen.dtype).reshape(())
         loss = loss + graph * gamma
     return loss, recon, kl, graph
 
@@ -115,24 +119,25 @@ class TrainStep(object):
     """one optimisation step of scripts/utils.py::loop (train=True branch): forward, loss, backward, [all-reduce],
     clip_grad_norm_(0.01), Adam."""
 
-    def __init__(self, model, beta, gamma, lr=1e-4, max_norm=0.01, group=None, xyz_key="nxyz"):
+    def __init__(self, model, beta, gamma, lr=1e-4, max_norm=0.01, group=None, capturable=False):
         self.model, self.beta, self.gamma = model, beta, gamma
-        self.max_norm, self.group, self.xyz_key = max_norm, group, xyz_key
+        self.max_norm, self.group = max_norm, group
         self.lr = lr
+        self.capturable = capturable
         self.flat = None
         self.opt = None
 
     def _loss(self, batch, eps):
         out = self.model(batch, eps=eps) if eps is not None else self.model(batch)
         xyz = out[4]
-        return training_loss(out, xyz, batch["bond_edge_list"], self.beta, self.gamma)[0]
+        return training_loss(out, xyz, batch["bond_edge_list"], self.beta, self.gamma, batch.get("bond_count"))[0]
 
     def prepare(self, batch, eps=None):
         """discover the used parameters with one dry backward and lay their gradients out in one flat buffer."""
         used = used_parameters(self.model, lambda: self._loss(batch, eps).backward())
         self.flat = FlatGrads([p for _, p in used])
         fused = self.flat.flat.is_cuda
-        self.opt = torch.optim.Adam(self.flat.params, lr=self.lr, fused=fused)
+        self.opt = torch.optim.Adam(self.flat.params, lr=self.lr, fused=fused, capturable=bool(self.capturable and fused))
         if self.flat.sink:                 # verify once that autograd adopts the sink views (else fall back to copies)
             self.forward_backward(batch, eps)
             if not self.flat.check_adopted():
@@ -151,6 +156,66 @@ class TrainStep(object):
         self.flat.clip_(self.max_norm)
         self.opt.step()
         return loss
+
+
+STATIC_LISTS = (("nbr_list", "nbr_count"), ("CG_nbr_list", "CG_nbr_count"), ("bond_edge_list", "bond_count"))
+
+
+def to_static_batch(batch, capacities):
+    """Pad the variable-length index lists of a collated batch to fixed capacities and add their live row counts
+    (``nbr_count``, ``CG_nbr_count``, ``bond_count``: int64 [1]).  Host-side, once per batch at dataset-preparation time
+    (the reference precomputes the lists themselves once per dataset: scripts/run_ala.py:64-67).  Every tensor of the
+    result has a shape that depends only on (atoms, beads, capacities), which is what CUDA-graph replay needs."""
+    out = dict(batch)
+    for key, count_key in STATIC_LISTS:
+        t = batch[key]
+        cap = int(capacities[key])
+        n = int(t.shape[0])
+        if n > cap:
+            raise ValueError("%s has %d rows, capacity %d" % (key, n, cap))
+        padded = torch.zeros((cap, 2), dtype=torch.int64)
+        padded[:n] = t
+        out[key] = padded
+        out[count_key] = torch.tensor([n], dtype=torch.int64)
+    return out
+
+
+class GraphedTrainStep(object):
+    """The whole optimisation step (CSR build, geometry, forward, loss, backward, [NCCL all-reduce], clip, Adam:
+    ~550 kernel launches at the chignolin config) captured ONCE as a CUDA graph over static-capacity input buffers and
+    replayed per batch -- the step is launch-bound on the host otherwise.  Batches must come from ``to_static_batch``
+    with the capacities used at capture time."""
+
+    def __init__(self, trainer, example_batch, eps):
+        if not trainer.capturable:
+            raise ValueError("TrainStep(capturable=True) required")
+        self.trainer = trainer
+        self.static = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in example_batch.items()}
+        self.eps = eps.clone() if eps is not None else None
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):                 # warm-up on a side stream, as graph capture requires
+            for _ in range(3):
+                trainer.step(self.static, self.eps)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        from . import ops
+        before = ops.launch_count()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = trainer.step(self.static, self.eps)
+        self.launches_per_step = ops.launch_count() - before
+
+    def load(self, batch):
+        for k, v in batch.items():
+            if torch.is_tensor(v):
+                self.static[k].copy_(v, non_blocking=True)
+
+    def step(self, batch):
+        self.load(batch)
+        self.graph.replay()
+        return self.loss
 
 
 @torch.no_grad()

@@ -82,11 +82,17 @@ int cgvae_edge_orientation(const int64_t* pairs, int64_t n_edges, int32_t* flags
  *   cgvae_csr_count : deg_r[n_recv], deg_s[n_send] (int32, zeroed by the call)
  *   cgvae_csr_fill  : rowptr_r/rowptr_s are int32 exclusive scans (n+1).  Writes, in the original
  *                     edge order within every row (deterministic): col[E] (sender), eid[E] (original
- *                     edge id of each CSR slot), col_t[E] (receiver), perm_t[E] (receiver-CSR slot). */
-int cgvae_csr_count(const int64_t* pairs, int64_t n_edges, int64_t n_recv, int64_t n_send,
-                    int32_t* deg_r, int32_t* deg_s, cgvae_stream_t stream);
+ *                     edge id of each CSR slot), col_t[E] (receiver), perm_t[E] (receiver-CSR slot).
+ * symmetrize != 0: `pairs` is the one-directional list and the flipped copy of make_directed
+ * (conv.py:19, cat([nbrs, nbrs.flip(1)])) is generated on the fly: directed edge d >= n is pairs[d-n]
+ * flipped; all outputs then hold 2*n_edges slots.  n_edges_dev (nullable): the live edge count read
+ * from DEVICE memory, with n_edges the static capacity of `pairs` -- this keeps every launch shape
+ * fixed so a whole training step can be replayed as one CUDA graph while the edge count changes. */
+int cgvae_csr_count(const int64_t* pairs, int64_t n_edges, const int64_t* n_edges_dev, int symmetrize,
+                    int64_t n_recv, int64_t n_send, int32_t* deg_r, int32_t* deg_s, cgvae_stream_t stream);
 int cgvae_scan_i32(const int32_t* counts, int64_t n, int32_t* out, cgvae_stream_t stream);
-int cgvae_csr_fill(const int64_t* pairs, int64_t n_edges, int64_t n_recv, int64_t n_send,
+int cgvae_csr_fill(const int64_t* pairs, int64_t n_edges, const int64_t* n_edges_dev, int symmetrize,
+                   int64_t n_recv, int64_t n_send,
                    const int32_t* rowptr_r, const int32_t* rowptr_s, int32_t* scratch /* n_recv+n_send+2E int32 */,
                    int32_t* col, int32_t* eid, int32_t* col_t, int32_t* perm_t, cgvae_stream_t stream);
 
@@ -168,7 +174,7 @@ int cgvae_message9_bwd(const float* phi, const float* s, const float* sbar, cons
                        const int32_t* rowptr, const int32_t* col,
                        const int32_t* rowptr_t, const int32_t* col_t, const int32_t* perm_t,
                        const float* basis, const float* unit, const float* Wf, const float* bf,
-                       int64_t n, int F, int R, int RB, int residual,
+                       int64_t n, int64_t n_edge_slots, int F, int R, int RB, int residual,
                        const float* g_s, const float* g_sbar, const float* g_v, const float* g_vbar,
                        float* gi_s, float* gi_sbar, float* gi_v, float* gi_vbar, float* g_phi, float* gw,
                        cgvae_stream_t stream);

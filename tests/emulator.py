@@ -47,10 +47,14 @@ def edge_orientation(pairs):
     return bool((pairs[:, 0] > pairs[:, 1]).any()), bool((pairs[:, 1] > pairs[:, 0]).any())
 
 
-def build_graph(pairs, n_recv, n_send=None):
+def build_graph(pairs, n_recv, n_send=None, symmetrize=False, n_edges_dev=None):
     if n_send is None:
         n_send = n_recv
     pairs = pairs.to(torch.int64)
+    if n_edges_dev is not None:
+        pairs = pairs[:int(n_edges_dev)]
+    if symmetrize:
+        pairs = torch.cat([pairs, pairs.flip(1)], 0)
     E = pairs.shape[0]
     eid = torch.argsort(pairs[:, 0], stable=True)
     rowptr = torch.zeros(n_recv + 1, dtype=torch.int64)
