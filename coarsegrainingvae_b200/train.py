@@ -198,13 +198,13 @@ class GraphedTrainStep(object):
         with torch.cuda.stream(side):                 # warm-up on a side stream, as graph capture requires
             for _ in range(3):
                 trainer.step(self.static, self.eps)
-        cur.wait_stream(side)
         torch.cuda.synchronize()
         from . import ops
         before = ops.launch_count()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, stream=side):   # same stream as the warm-up: autograd's accumulate nodes match
             self.loss = trainer.step(self.static, self.eps)
+        cur.wait_stream(side)
         self.launches_per_step = ops.launch_count() - before
 
     def load(self, batch):

@@ -368,9 +368,10 @@ def test_graphed_train_step_matches_eager():
     eager.prepare(_to(raw[0], DEV), eps)
     graph_tr = TrainStep(model_b, cfg["beta"], cfg["gamma"], lr=1e-3, capturable=True)
     graph_tr.prepare(static[0], eps)
-    # warm-up steps inside GraphedTrainStep update model_b three times + capture once: replay them on model_a too
+    # the three warm-up steps inside GraphedTrainStep update model_b (the capture itself executes nothing):
+    # take the same three steps on model_a
     graphed = GraphedTrainStep(graph_tr, static[0], eps)
-    for _ in range(4):
+    for _ in range(3):
         eager.step(_to(raw[0], DEV), eps)
     for i in (1, 2, 0, 1):
         la = eager.step(_to(raw[i], DEV), eps)
