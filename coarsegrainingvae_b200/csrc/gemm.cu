@@ -6,7 +6,6 @@
 
 namespace cgvae {
 
-constexpr int BK = 16;
 
 struct Epilogue {
   const float* bias;   // [N] or null
@@ -28,7 +27,7 @@ __device__ __forceinline__ float apply_epilogue(const Epilogue& ep, float v, int
 
 // Loads a [ROWS x BK] operand tile into smem laid out as tile[k][row] (row stride ROWS+4).
 // KCONTIG: global element (row, k) at ptr[row*ld + k] ; else at ptr[k*ld + row].
-template <int ROWS, bool KCONTIG, int NTHREADS>
+template <int ROWS, int BK, bool KCONTIG, int NTHREADS>
 struct TileLoader {
   static constexpr int NVEC = ROWS * BK / 4;
   static constexpr int PER_THREAD = (NVEC + NTHREADS - 1) / NTHREADS;
@@ -75,20 +74,34 @@ struct TileLoader {
     }
   }
 
-  __device__ __forceinline__ void store(float (*tile)[ROWS + 4], int tid) {
+  // smem layouts.  k-major tile[k][row] (row stride ROWS+4): vector reads in the inner loop, used by the large tile.
+  // row-major tile[row][k] (row stride BK+1) for K-contiguous operands of the deep-k skinny tiles: the transposing
+  // scatter of the k-major layout would be an 8-way bank conflict at BK = 64.
+  static constexpr bool ROWMAJOR = KCONTIG && (BK > 16);
+  static constexpr int SMEM_FLOATS = ROWMAJOR ? ROWS * (BK + 1) : BK * (ROWS + 4);
+  __device__ __forceinline__ static float at(const float* tile, int row, int k) {
+    return ROWMAJOR ? tile[row * (BK + 1) + k] : tile[k * (ROWS + 4) + row];
+  }
+
+  __device__ __forceinline__ void store(float* tile, int tid) {
 #pragma unroll
     for (int p = 0; p < PER_THREAD; ++p) {
       const int v = tid + p * NTHREADS;
       if (v < NVEC) {
         if (KCONTIG) {
           const int r = v / (BK / 4), kq = v % (BK / 4);
-          tile[kq * 4 + 0][r] = reg[p].x;
-          tile[kq * 4 + 1][r] = reg[p].y;
-          tile[kq * 4 + 2][r] = reg[p].z;
-          tile[kq * 4 + 3][r] = reg[p].w;
+          if (ROWMAJOR) {
+            float* d = tile + r * (BK + 1) + kq * 4;
+            d[0] = reg[p].x; d[1] = reg[p].y; d[2] = reg[p].z; d[3] = reg[p].w;
+          } else {
+            tile[(kq * 4 + 0) * (ROWS + 4) + r] = reg[p].x;
+            tile[(kq * 4 + 1) * (ROWS + 4) + r] = reg[p].y;
+            tile[(kq * 4 + 2) * (ROWS + 4) + r] = reg[p].z;
+            tile[(kq * 4 + 3) * (ROWS + 4) + r] = reg[p].w;
+          }
         } else {
           const int kk = v / (ROWS / 4), rq = v % (ROWS / 4);
-          *reinterpret_cast<float4*>(&tile[kk][rq * 4]) = reg[p];
+          *reinterpret_cast<float4*>(&tile[kk * (ROWS + 4) + rq * 4]) = reg[p];
         }
       }
     }
@@ -97,24 +110,26 @@ struct TileLoader {
 
 // C tile BM x BN per CTA, TM x TN per thread, (BM/TM)*(BN/TN) threads.  gridDim.z = split-K factor:
 // splits > 1 write raw partial sums to `partial[z][M][N]` and the epilogue runs in splitk_reduce_kernel.
-template <int BM, int BN, int TM, int TN, bool A_KC, bool B_KC>
+template <int BM, int BN, int BK, int TM, int TN, bool A_KC, bool B_KC>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN)) gemm_kernel(
     const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb, float* __restrict__ C, int64_t ldc,
     int64_t M, int64_t N, int64_t K, int64_t k_per_split, Epilogue ep, float* __restrict__ partial, bool a_vec, bool b_vec) {
   constexpr int NT = (BM / TM) * (BN / TN);
-  __shared__ __align__(16) float As[2][BK][BM + 4];
-  __shared__ __align__(16) float Bs[2][BK][BN + 4];
+  using LoaderA = TileLoader<BM, BK, A_KC, NT>;
+  using LoaderB = TileLoader<BN, BK, B_KC, NT>;
+  __shared__ __align__(16) float As[2][LoaderA::SMEM_FLOATS];
+  __shared__ __align__(16) float Bs[2][LoaderB::SMEM_FLOATS];
   const int tid = threadIdx.x;
   const int tx = tid % (BN / TN), ty = tid / (BN / TN);
   const int64_t m0 = (int64_t)blockIdx.y * BM, n0 = (int64_t)blockIdx.x * BN;
   const int64_t kbeg = (int64_t)blockIdx.z * k_per_split;
   const int64_t kend = min(K, kbeg + k_per_split);
 
-  TileLoader<BM, A_KC, NT> la;
-  TileLoader<BN, B_KC, NT> lb;
+  LoaderA la;
+  LoaderB lb;
   // two-level accumulation: `acc` is folded into `tot` every kFold k-tiles so the rounding error grows with
   // sqrt(kFold*BK) + sqrt(K/(kFold*BK)) instead of sqrt(K) (weight gradients reduce over up to 1e5 rows)
-  constexpr int kFold = 16;
+  constexpr int kFold = 256 / BK;
   float acc[TM][TN], tot[TM][TN];
 #pragma unroll
   for (int i = 0; i < TM; ++i)
@@ -140,9 +155,9 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) gemm_kernel(
     for (int k = 0; k < BK; ++k) {
       float a[TM], b[TN];
 #pragma unroll
-      for (int i = 0; i < TM; ++i) a[i] = As[buf][k][ty * TM + i];
+      for (int i = 0; i < TM; ++i) a[i] = LoaderA::at(As[buf], ty * TM + i, k);
 #pragma unroll
-      for (int j = 0; j < TN; ++j) b[j] = Bs[buf][k][tx * TN + j];
+      for (int j = 0; j < TN; ++j) b[j] = LoaderB::at(Bs[buf], tx * TN + j, k);
 #pragma unroll
       for (int i = 0; i < TM; ++i)
 #pragma unroll
@@ -168,16 +183,29 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) gemm_kernel(
     for (int j = 0; j < TN; ++j) acc[i][j] += tot[i][j];
 
   const bool split = gridDim.z > 1;
+  float* dst = split ? partial + (int64_t)blockIdx.z * M * N : C;
+  const int64_t ldd = split ? N : ldc;
+  const int64_t nb = n0 + tx * TN;
+  // a thread owns TN consecutive columns: store them as one vector when the row pointer allows it
+  const bool vec_store = (TN == 2 || TN == 4) && (ldd % TN == 0) && (nb + TN <= N) &&
+                         ((reinterpret_cast<uintptr_t>(dst) & (4 * TN - 1)) == 0);
 #pragma unroll
   for (int i = 0; i < TM; ++i) {
     const int64_t m = m0 + ty * TM + i;
     if (m >= M) continue;
+    float o[TN];
 #pragma unroll
     for (int j = 0; j < TN; ++j) {
-      const int64_t n = n0 + tx * TN + j;
-      if (n >= N) continue;
-      if (split) partial[((int64_t)blockIdx.z * M + m) * N + n] = acc[i][j];
-      else C[m * ldc + n] = apply_epilogue(ep, acc[i][j], m, n, ldc);
+      o[j] = acc[i][j];
+      if (!split && nb + j < N) o[j] = apply_epilogue(ep, acc[i][j], m, nb + j, ldc);
+    }
+    if (vec_store) {
+      if (TN == 4) *reinterpret_cast<float4*>(dst + m * ldd + nb) = make_float4(o[0], o[1], o[2], o[3]);
+      else *reinterpret_cast<float2*>(dst + m * ldd + nb) = make_float2(o[0], o[1]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < TN; ++j)
+        if (nb + j < N) dst[m * ldd + nb + j] = o[j];
     }
   }
 }
@@ -211,7 +239,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X
   }
 }
 
-template <int BM, int BN, int TM, int TN>
+template <int BM, int BN, int BK, int TM, int TN>
 static int launch_gemm(int form, const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t M,
                        int64_t N, int64_t K, const Epilogue& ep, float* ws, size_t ws_bytes, cudaStream_t st) {
   constexpr int NT = (BM / TM) * (BN / TN);
@@ -219,7 +247,7 @@ static int launch_gemm(int form, const float* A, int64_t lda, const float* B, in
   // split-K only when the output grid leaves most of the 148 SMs idle and K is deep
   int splits = 1;
   if (ws != nullptr && tiles < kNumSM && K >= 8 * BK) {
-    splits = (int)std::min<int64_t>(ceil_div(2 * kNumSM, tiles), K / (4 * BK));
+    splits = (int)std::min<int64_t>(ceil_div(2 * kNumSM, tiles), ceil_div(K, 128));
     const int64_t cap = (int64_t)(ws_bytes / (sizeof(float) * (size_t)(M * N)));
     splits = (int)std::max<int64_t>(1, std::min<int64_t>(splits, cap));
   }
@@ -231,11 +259,11 @@ static int launch_gemm(int form, const float* A, int64_t lda, const float* B, in
   dim3 grid((unsigned)ceil_div(N, BN), (unsigned)ceil_div(M, BM), (unsigned)splits);
   float* partial = splits > 1 ? ws : nullptr;
   if (a_kc && b_kc)
-    gemm_kernel<BM, BN, TM, TN, true, true><<<grid, NT, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, k_per_split, ep, partial, a_vec, b_vec);
+    gemm_kernel<BM, BN, BK, TM, TN, true, true><<<grid, NT, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, k_per_split, ep, partial, a_vec, b_vec);
   else if (a_kc && !b_kc)
-    gemm_kernel<BM, BN, TM, TN, true, false><<<grid, NT, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, k_per_split, ep, partial, a_vec, b_vec);
+    gemm_kernel<BM, BN, BK, TM, TN, true, false><<<grid, NT, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, k_per_split, ep, partial, a_vec, b_vec);
   else
-    gemm_kernel<BM, BN, TM, TN, false, false><<<grid, NT, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, k_per_split, ep, partial, a_vec, b_vec);
+    gemm_kernel<BM, BN, BK, TM, TN, false, false><<<grid, NT, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, k_per_split, ep, partial, a_vec, b_vec);
   if (int rc = launched("gemm")) return rc;
   if (splits > 1) {
     splitk_reduce_kernel<<<(unsigned)ceil_div(M * N, 256), 256, 0, st>>>(partial, splits, M, N, C, ldc, ep);
@@ -261,9 +289,10 @@ int cgvae_gemm(int form, const float* A, int64_t lda, const float* B, int64_t ld
   Epilogue ep{bias, act, z_out, z_in, dact, add};
   cudaStream_t st = (cudaStream_t)stream;
   float* wsf = reinterpret_cast<float*>(ws);
-  if (M <= 16) return launch_gemm<16, 32, 1, 2>(form, A, lda, B, ldb, C, ldc, M, N, K, ep, wsf, ws_bytes, st);
-  if (M <= 32) return launch_gemm<32, 32, 2, 2>(form, A, lda, B, ldb, C, ldc, M, N, K, ep, wsf, ws_bytes, st);
-  return launch_gemm<64, 64, 4, 4>(form, A, lda, B, ldb, C, ldc, M, N, K, ep, wsf, ws_bytes, st);
+  // skinny problems (decoder graphs: 12..96 rows) stream the weight matrix: deep k-tiles keep 8-16 KB per CTA in flight
+  if (M <= 16) return launch_gemm<16, 32, 64, 1, 2>(form, A, lda, B, ldb, C, ldc, M, N, K, ep, wsf, ws_bytes, st);
+  if (M <= 32) return launch_gemm<32, 32, 64, 2, 2>(form, A, lda, B, ldb, C, ldc, M, N, K, ep, wsf, ws_bytes, st);
+  return launch_gemm<64, 64, 16, 4, 4>(form, A, lda, B, ldb, C, ldc, M, N, K, ep, wsf, ws_bytes, st);
 }
 
 int cgvae_colsum(const float* X, int64_t ldx, int64_t M, int64_t N, float* out, cgvae_stream_t stream) {

@@ -282,11 +282,21 @@ __device__ __forceinline__ void load3(const float* __restrict__ base, int64_t no
 
 constexpr int kMaxRB9 = 16;
 
+// The slice of split k is the contiguous chunk Wf[(k*F+f0)*R ... +nch*R): read it coalesced and transpose into
+// Wsm[k][r][lane] (the strided per-element gather this replaces dominated the 9-split kernels on tiny graphs).
 __device__ __forceinline__ void stage_filter9(float (*Wsm)[kMaxRB9][32], const float* __restrict__ Wf,
                                               const float* __restrict__ bf, int F, int R, int RB, int f0) {
-  for (int idx = threadIdx.x; idx < 9 * RB * 32; idx += blockDim.x) {
-    const int l = idx & 31, r = (idx >> 5) % RB, k = idx / (32 * RB);
-    Wsm[k][r][l] = filter_entry(Wf, bf, F, R, k, min(f0 + l, F - 1), r);
+  const int nch = min(32, F - f0);
+  for (int k = 0; k < 9; ++k) {
+    const float* src = Wf + ((int64_t)k * F + f0) * R;
+    for (int idx = threadIdx.x; idx < 32 * R; idx += blockDim.x) {
+      const int l = idx / R, r = idx - l * R;
+      Wsm[k][r][l] = (l < nch) ? src[idx] : 0.f;
+    }
+    for (int idx = threadIdx.x; idx < 32 * (RB - R); idx += blockDim.x) {
+      const int l = idx & 31, r = R + (idx >> 5);
+      Wsm[k][r][l] = (r == R && l < nch) ? bf[(int64_t)k * F + f0 + l] : 0.f;
+    }
   }
 }
 

@@ -21,12 +21,17 @@ def _phi_forward(s, W1, b1, W2, b2, act=SWISH):
 
 def _phi_backward(g_phi2d, s, a1, z1, W1, b1, W2, b2, add_to_gs, act=SWISH):
     """backward of phi = Dense2(act(Dense1(s))) given g_phi [N, K*F]; returns gs (+add), gW1, gb1, gW2, gb2."""
+    fork = ops.Fork(g_phi2d.device)
     gz1 = ops.linear_bwd_input(g_phi2d, W2, z_in=z1, dact=act)            # (g_phi W2) * act'(z1)
-    gW2 = ops.linear_bwd_weight(g_phi2d, a1, W2)
-    gb2 = ops.colsum(g_phi2d, b2)
+    with fork.branch():                                                   # parameter gradients: off the critical path
+        gW2 = ops.linear_bwd_weight(g_phi2d, a1, W2)
+        gb2 = ops.colsum(g_phi2d, b2)
+    fork.sync()
     gs = ops.linear_bwd_input(gz1, W1, add=add_to_gs)
-    gW1 = ops.linear_bwd_weight(gz1, s, W1)
-    gb1 = ops.colsum(gz1, b1)
+    with fork.branch():
+        gW1 = ops.linear_bwd_weight(gz1, s, W1)
+        gb1 = ops.colsum(gz1, b1)
+    fork.join()
     return gs, gW1, gb1, gW2, gb2
 
 
@@ -151,19 +156,26 @@ class UpdateBlockFn(Function):
         N, _, F = v.shape
         gq, gUv, gVv = ops.update_combine_bwd(Uv, Vv, q, g_s, g_v)
         gq2 = gq.view(N, 3 * F)
-        gz = ops.linear_bwd_input(gq2, A1, z_in=z, dact=SWISH)
-        gA1 = ops.linear_bwd_weight(gq2, h, A1)
-        gc1 = ops.colsum(gq2, c1)
-        gx = ops.linear_bwd_input(gz, A0)
-        gA0 = ops.linear_bwd_weight(gz, x, A0)
-        gc0 = ops.colsum(gz, c0)
-        gs_in = ops.update_norm_bwd(x, Vv, gx, g_s, gVv, ctx.residual)      # adds the norm path into gVv in place
         v2 = v.view(3 * N, F)
         gUv2, gVv2 = gUv.view(3 * N, F), gVv.view(3 * N, F)
+        fork = ops.Fork(g_s.device)
+        gz = ops.linear_bwd_input(gq2, A1, z_in=z, dact=SWISH)
+        with fork.branch():                                                 # parameter gradients: off the critical path
+            gA1 = ops.linear_bwd_weight(gq2, h, A1)
+            gc1 = ops.colsum(gq2, c1)
+            gU = ops.linear_bwd_weight(gUv2, v2, U)
+        fork.sync()
+        gx = ops.linear_bwd_input(gz, A0)
+        with fork.branch():
+            gA0 = ops.linear_bwd_weight(gz, x, A0)
+            gc0 = ops.colsum(gz, c0)
+        gs_in = ops.update_norm_bwd(x, Vv, gx, g_s, gVv, ctx.residual)      # adds the norm path into gVv in place
+        fork.sync()
         gv_in = ops.linear_bwd_input(gUv2, U, add=g_v.view(3 * N, F) if ctx.residual else None)
         gv_in = ops.linear_bwd_input(gVv2, V, add=gv_in).view(N, 3, F)
-        gU = ops.linear_bwd_weight(gUv2, v2, U)
-        gV = ops.linear_bwd_weight(gVv2, v2, V)
+        with fork.branch():
+            gV = ops.linear_bwd_weight(gVv2, v2, V)
+        fork.join()
         return None, gs_in, gv_in, gU, gV, gA0, gc0, gA1, gc1
 
 

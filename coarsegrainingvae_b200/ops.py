@@ -76,6 +76,49 @@ class KernelTimer(object):
 
 TIMER = None      # set to a KernelTimer to time launches; None (default) adds no events
 
+_SIDE_STREAMS = {}
+FORK_ENABLED = True
+
+
+class Fork(object):
+    """fork / join of a side stream inside one autograd node: weight- and bias-gradient contractions do not feed the
+    rest of the backward pass, so they run on a forked branch and overlap with the input-gradient chain (inside a CUDA
+    graph capture this becomes a parallel branch of the graph).  Every branch is joined before the node returns, so all
+    tensors it touches are still referenced -- no cross-stream allocator hazards."""
+
+    def __init__(self, device):
+        self.enabled = FORK_ENABLED and device.type == "cuda"
+        if not self.enabled:
+            return
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        side = _SIDE_STREAMS.get(idx)
+        if side is None:
+            side = torch.cuda.Stream(device=idx)
+            _SIDE_STREAMS[idx] = side
+        self.side = side
+        self.main = torch.cuda.current_stream(idx)
+        self.sync()
+
+    def sync(self):
+        """side branch sees everything the main stream has enqueued so far"""
+        if self.enabled:
+            ev = torch.cuda.Event()
+            ev.record(self.main)
+            self.side.wait_event(ev)
+
+    def branch(self):
+        if self.enabled:
+            return torch.cuda.stream(self.side)
+        import contextlib
+        return contextlib.nullcontext()
+
+    def join(self):
+        if self.enabled:
+            ev = torch.cuda.Event()
+            ev.record(self.side)
+            self.main.wait_event(ev)
+
+
 # Optional gradient sinks: data_ptr of a parameter -> (flat buffer, offset).  When a training step registers its flat
 # gradient buffer here (train.FlatGrads), the weight / bias / filter gradient kernels write straight into that buffer and
 # autograd adopts the view as ``p.grad`` -- no per-parameter accumulate kernels, no flatten copy before the all-reduce.
@@ -429,8 +472,12 @@ def message9_bwd(phi, s, sbar, v, vbar, geom, Wf, bf, residual, g_s, g_sbar, g_v
     R = geom.n_rbf
     E = g.n_edges
     if E > 0:
-        dWf = gemm(GEMM_TN, gw, geom.basis, 9 * F, R, E, out=_grad_out(Wf, (9 * F, R)))
-        dbf = gemm(GEMM_TN, gw, geom.basis[:, R:], 9 * F, 1, E, out=_grad_out(bf, (9 * F,)).view(9 * F, 1)).reshape(9 * F)
+        # forked branch; it is joined by the caller's next Fork.join() on the same side stream
+        # (functions.Message9Block.backward -> _phi_backward), i.e. before the autograd node returns
+        fork = Fork(dev)
+        with fork.branch():
+            dWf = gemm(GEMM_TN, gw, geom.basis, 9 * F, R, E, out=_grad_out(Wf, (9 * F, R)))
+            dbf = gemm(GEMM_TN, gw, geom.basis[:, R:], 9 * F, 1, E, out=_grad_out(bf, (9 * F,)).view(9 * F, 1)).reshape(9 * F)
     else:
         dWf = torch.zeros((9 * F, R), dtype=torch.float32, device=dev)
         dbf = torch.zeros((9 * F,), dtype=torch.float32, device=dev)

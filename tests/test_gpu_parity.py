@@ -129,8 +129,9 @@ def test_edge_geometry_vs_oracle():
     for R, cutoff in ((8, 8.5), (10, 12.0), (4, 4.0)):    # cutoff < graph radius: exercises the d >= cutoff branch
         geom = ops.edge_geometry(g, _dev(xyz), _dev(xyz), R, cutoff)
         i, j = pairs[g.eid.cpu().numpy(), 0], pairs[g.eid.cpu().numpy(), 1]
-        r = torch.from_numpy(xyz[j] - xyz[i])
-        d, unit, rbf, env = orc.edge_geometry(r, R, cutoff)
+        r = torch.from_numpy(xyz[j] - xyz[i])                 # fp32 difference, as the kernel forms it
+        d, unit, rbf, env = orc.edge_geometry(r.double(), R, cutoff)   # float64 evaluation of the reference formulas
+        assert float((geom.unit[:, :3] ** 2).sum(1).max()) <= 1.0 + 1e-6
         assert rel_err(geom.unit[:, :3], unit) < 1e-6 and rel_err(geom.unit[:, 3], d) < 1e-6  # geometry tolerances
         assert rel_err(geom.basis[:, :R], rbf * env[:, None]) < GEMM_TOL
         assert rel_err(geom.basis[:, R], env) < 1e-6
