@@ -150,11 +150,14 @@ class TrainStep(object):
         loss.backward()
         return loss
 
+    def apply_gradients(self):
+        self.flat.clip_(self.max_norm)
+        self.opt.step()
+
     def step(self, batch, eps=None):
         loss = self.forward_backward(batch, eps)
         self.flat.allreduce_mean_(self.group)
-        self.flat.clip_(self.max_norm)
-        self.opt.step()
+        self.apply_gradients()
         return loss
 
 
@@ -200,10 +203,22 @@ class GraphedTrainStep(object):
                 trainer.step(self.static, self.eps)
         torch.cuda.synchronize()
         from . import ops
+        import torch.distributed as dist
+        self.distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(trainer.group) > 1
         before = ops.launch_count()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph, stream=side):   # same stream as the warm-up: autograd's accumulate nodes match
-            self.loss = trainer.step(self.static, self.eps)
+        self.opt_graph = None
+        if not self.distributed:
+            with torch.cuda.graph(self.graph, stream=side):   # same stream as the warm-up: autograd's accumulate nodes match
+                self.loss = trainer.step(self.static, self.eps)
+        else:
+            # data parallel: the NCCL all-reduce stays an ordinary stream operation between two graphs
+            # (forward+backward | clip+Adam); collectives inside a capture depend on process-group internals
+            with torch.cuda.graph(self.graph, stream=side):
+                self.loss = trainer.forward_backward(self.static, self.eps)
+            self.opt_graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.opt_graph, stream=side, pool=self.graph.pool()):
+                trainer.apply_gradients()
         cur.wait_stream(side)
         self.launches_per_step = ops.launch_count() - before
 
@@ -215,6 +230,9 @@ class GraphedTrainStep(object):
     def step(self, batch):
         self.load(batch)
         self.graph.replay()
+        if self.opt_graph is not None:
+            self.trainer.flat.allreduce_mean_(self.trainer.group)
+            self.opt_graph.replay()
         return self.loss
 
 
