@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <atomic>
 #include <algorithm>
 
@@ -42,6 +43,38 @@ inline int launched(const char* what) {
     cudaError_t _e = (expr);                                                           \
     if (_e != cudaSuccess) return ::cgvae::fail((int)_e, "%s: %s", #expr, cudaGetErrorString(_e)); \
   } while (0)
+
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------
+// A training step is ~450 dependent kernels of a few microseconds each: the launch latency between dependent nodes,
+// not the work, dominates.  Every kernel of this library starts with pdl_wait() (griddepcontrol.wait: blocks until the
+// preceding grid has completed and flushed its writes -- all global-memory accesses come after it, so ordering is exactly
+// that of a plain stream) and pdl_trigger() (griddepcontrol.launch_dependents: lets the NEXT kernel's launch and prologue
+// overlap with this kernel's execution).  Launches carry cudaLaunchAttributeProgrammaticStreamSerialization; set
+// CGVAE_PDL=0 to fall back to fully serialised launches.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#define CGVAE_KERNEL_PROLOGUE() \
+  do {                          \
+    ::cgvae::pdl_wait();        \
+    ::cgvae::pdl_trigger();     \
+  } while (0)
+
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline void launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);   // errors surface through launched()
+}
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 

@@ -3,6 +3,7 @@
 // (bias, pre-activation copy, activation, activation-backward, residual add), deterministic
 // split-K for skinny problems (decoder graphs have 12..96 rows: weight streaming bound).
 #include "common.cuh"
+#include <cooperative_groups.h>
 
 namespace cgvae {
 
@@ -110,10 +111,14 @@ struct TileLoader {
 
 // C tile BM x BN per CTA, TM x TN per thread, (BM/TM)*(BN/TN) threads.  gridDim.z = split-K factor:
 // splits > 1 write raw partial sums to `partial[z][M][N]` and the epilogue runs in splitk_reduce_kernel.
-template <int BM, int BN, int BK, int TM, int TN, bool A_KC, bool B_KC>
+// CLUSTER: the gridDim.z K-slices of one output tile form a thread-block cluster (1,1,S); partial tiles are exchanged
+// through distributed shared memory and summed in slice order (deterministic) -- no global round trip, no second launch.
+template <int BM, int BN, int BK, int TM, int TN, bool A_KC, bool B_KC, bool CLUSTER>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN)) gemm_kernel(
     const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb, float* __restrict__ C, int64_t ldc,
-    int64_t M, int64_t N, int64_t K, int64_t k_per_split, Epilogue ep, float* __restrict__ partial, bool a_vec, bool b_vec) {
+    int64_t M, int64_t N, int64_t K, int64_t k_per_split, Epilogue ep, float* __restrict__ partial,
+    int* __restrict__ counters, bool a_vec, bool b_vec) {
+  CGVAE_KERNEL_PROLOGUE();
   constexpr int NT = (BM / TM) * (BN / TN);
   using LoaderA = TileLoader<BM, BK, A_KC, NT>;
   using LoaderB = TileLoader<BN, BK, B_KC, NT>;
@@ -182,6 +187,27 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) gemm_kernel(
 #pragma unroll
     for (int j = 0; j < TN; ++j) acc[i][j] += tot[i][j];
 
+  if constexpr (CLUSTER) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ __align__(16) float red[BM * BN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) red[(ty * TM + i) * BN + tx * TN + j] = acc[i][j];
+    cluster.sync();
+    const int S = (int)cluster.num_blocks();
+    const int rank = (int)cluster.block_rank();
+    // every CTA of the cluster finishes a strided share of the tile; slices are added in order 0..S-1
+    for (int idx = rank * NT + tid; idx < BM * BN; idx += S * NT) {
+      const int64_t m = m0 + idx / BN, n = n0 + idx % BN;
+      float v = 0.f;
+      for (int z = 0; z < S; ++z) v += *cluster.map_shared_rank(&red[idx], z);
+      if (m < M && n < N) C[m * ldc + n] = apply_epilogue(ep, v, m, n, ldc);
+    }
+    cluster.sync();   // remote shared memory must stay alive until every CTA has read it
+    return;
+  }
   const bool split = gridDim.z > 1;
   float* dst = split ? partial + (int64_t)blockIdx.z * M * N : C;
   const int64_t ldd = split ? N : ldc;
@@ -208,10 +234,32 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) gemm_kernel(
         if (nb + j < N) dst[m * ldd + nb + j] = o[j];
     }
   }
+  if (!split || counters == nullptr) return;
+  // Deterministic split-K without a second launch: every CTA of an output tile publishes its partial sums, the LAST
+  // one to arrive (ticket counter) adds all slices in slice order 0..S-1 -- a fixed order, independent of which CTA
+  // happens to be last -- applies the epilogue and re-arms the counter for the next launch.
+  __shared__ int ticket_sh;
+  __threadfence();
+  __syncthreads();
+  const int tile_id = blockIdx.y * gridDim.x + blockIdx.x;
+  if (tid == 0) ticket_sh = atomicAdd(&counters[tile_id], 1);
+  __syncthreads();
+  if (ticket_sh != (int)gridDim.z - 1) return;
+  __threadfence();
+  const int splits = gridDim.z;
+  for (int idx = tid; idx < BM * BN; idx += NT) {
+    const int64_t m = m0 + idx / BN, n = n0 + idx % BN;
+    if (m >= M || n >= N) continue;
+    float v = 0.f;
+    for (int z = 0; z < splits; ++z) v += __ldcg(partial + ((int64_t)z * M + m) * N + n);
+    C[m * ldc + n] = apply_epilogue(ep, v, m, n, ldc);
+  }
+  if (tid == 0) counters[tile_id] = 0;
 }
 
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ partial, int splits, int64_t M, int64_t N,
                                                             float* __restrict__ C, int64_t ldc, Epilogue ep) {
+  CGVAE_KERNEL_PROLOGUE();
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= M * N) return;
   const int64_t m = idx / N, n = idx % N;
@@ -223,6 +271,7 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
 // column sums: out[n] = sum_m X[m][n]; one thread per column per row-chunk, two-stage, fixed order.
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X, int64_t ldx, int64_t M, int64_t N,
                                                      float* __restrict__ out) {
+  CGVAE_KERNEL_PROLOGUE();
   // blockDim = (32, 8): 32 columns x 8 row-lanes
   __shared__ float red[8][33];
   const int64_t n = (int64_t)blockIdx.x * 32 + threadIdx.x;
@@ -241,12 +290,13 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X
 
 template <int BM, int BN, int BK, int TM, int TN>
 static int launch_gemm(int form, const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t M,
-                       int64_t N, int64_t K, const Epilogue& ep, float* ws, size_t ws_bytes, cudaStream_t st) {
+                       int64_t N, int64_t K, const Epilogue& ep, float* ws, size_t ws_bytes, int* counters, int n_counters,
+                       cudaStream_t st) {
   constexpr int NT = (BM / TM) * (BN / TN);
   const int64_t tiles = ceil_div(M, BM) * ceil_div(N, BN);
   // split-K only when the output grid leaves most of the 148 SMs idle and K is deep
   int splits = 1;
-  if (ws != nullptr && tiles < kNumSM && K >= 8 * BK) {
+  if (ws != nullptr && counters != nullptr && tiles <= n_counters && tiles < kNumSM && K >= 8 * BK) {
     splits = (int)std::min<int64_t>(ceil_div(2 * kNumSM, tiles), ceil_div(K, 128));
     const int64_t cap = (int64_t)(ws_bytes / (sizeof(float) * (size_t)(M * N)));
     splits = (int)std::max<int64_t>(1, std::min<int64_t>(splits, cap));
@@ -256,17 +306,53 @@ static int launch_gemm(int form, const float* A, int64_t lda, const float* B, in
   if (splits < 1) splits = 1;
   const bool a_kc = (form != CGVAE_GEMM_TN), b_kc = (form == CGVAE_GEMM_NT);
   const bool a_vec = aligned16(A) && (lda % 4 == 0), b_vec = aligned16(B) && (ldb % 4 == 0);
+  static const bool use_cluster = [] { const char* e = getenv("CGVAE_CLUSTER_SPLITK"); return !(e && e[0] == '0'); }();
+  if (use_cluster && tiles < kNumSM && K >= 8 * BK && form != CGVAE_GEMM_TN) {
+    // cluster split-K: up to 8 K-slices per output tile (portable cluster size), reduced through DSMEM
+    int S = (int)std::min<int64_t>(std::min<int64_t>(8, ceil_div(2 * kNumSM, tiles)), ceil_div(K, 128));
+    int64_t kps = ceil_div(ceil_div(K, S), BK) * BK;
+    S = (int)ceil_div(K, kps);
+    if (S > 1) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)ceil_div(N, BN), (unsigned)ceil_div(M, BM), (unsigned)S);
+      cfg.blockDim = dim3(NT);
+      cfg.stream = st;
+      cudaLaunchAttribute attr[2];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 1;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = (unsigned)S;
+      attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[1].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = pdl_enabled() ? 2 : 1;
+      float* nopartial = nullptr;
+      int* nocounters = nullptr;
+      if (b_kc)
+        (void)cudaLaunchKernelEx(&cfg, gemm_kernel<BM, BN, BK, TM, TN, true, true, true>, A, lda, B, ldb, C, ldc, M, N, K, kps, ep,
+                                 nopartial, nocounters, a_vec, b_vec);
+      else
+        (void)cudaLaunchKernelEx(&cfg, gemm_kernel<BM, BN, BK, TM, TN, true, false, true>, A, lda, B, ldb, C, ldc, M, N, K, kps, ep,
+                                 nopartial, nocounters, a_vec, b_vec);
+      return launched("gemm_cluster");
+    }
+  }
   dim3 grid((unsigned)ceil_div(N, BN), (unsigned)ceil_div(M, BM), (unsigned)splits);
   float* partial = splits > 1 ? ws : nullptr;
+  // measured on B200 (chignolin step): the in-kernel fix-up (fence + ticket + last-CTA reduction) costs more than the extra
+  // reduce launch inside a CUDA graph (6.0 vs 5.4 ms per step), so it is opt-in
+  static const bool fixup = [] { const char* e = getenv("CGVAE_SPLITK_FIXUP"); return e && e[0] == '1'; }();
+  int* kernel_counters = fixup ? counters : nullptr;   // nullptr: partial sums are reduced by splitk_reduce_kernel
   if (a_kc && b_kc)
-    gemm_kernel<BM, BN, BK, TM, TN, true, true><<<grid, NT, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, k_per_split, ep, partial, a_vec, b_vec);
+    launch_kernel(gemm_kernel<BM, BN, BK, TM, TN, true, true, false>, dim3(grid), dim3(NT), 0, st, A, lda, B, ldb, C, ldc, M, N, K, k_per_split, ep, partial, kernel_counters, a_vec, b_vec);
   else if (a_kc && !b_kc)
-    gemm_kernel<BM, BN, BK, TM, TN, true, false><<<grid, NT, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, k_per_split, ep, partial, a_vec, b_vec);
+    launch_kernel(gemm_kernel<BM, BN, BK, TM, TN, true, false, false>, dim3(grid), dim3(NT), 0, st, A, lda, B, ldb, C, ldc, M, N, K, k_per_split, ep, partial, kernel_counters, a_vec, b_vec);
   else
-    gemm_kernel<BM, BN, BK, TM, TN, false, false><<<grid, NT, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, k_per_split, ep, partial, a_vec, b_vec);
+    launch_kernel(gemm_kernel<BM, BN, BK, TM, TN, false, false, false>, dim3(grid), dim3(NT), 0, st, A, lda, B, ldb, C, ldc, M, N, K, k_per_split, ep, partial, kernel_counters, a_vec, b_vec);
   if (int rc = launched("gemm")) return rc;
-  if (splits > 1) {
-    splitk_reduce_kernel<<<(unsigned)ceil_div(M * N, 256), 256, 0, st>>>(partial, splits, M, N, C, ldc, ep);
+  if (splits > 1 && kernel_counters == nullptr) {
+    launch_kernel(splitk_reduce_kernel, dim3((unsigned)ceil_div(M * N, 256)), dim3(256), 0, st, (const float*)partial, splits, M, N,
+                  C, ldc, ep);
     return launched("gemm_splitk_reduce");
   }
   return 0;
@@ -280,7 +366,7 @@ extern "C" {
 
 int cgvae_gemm(int form, const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t M, int64_t N,
                int64_t K, const float* bias, int act, float* z_out, const float* z_in, int dact, const float* add,
-               void* ws, size_t ws_bytes, cgvae_stream_t stream) {
+               void* ws, size_t ws_bytes, int32_t* counters, int n_counters, cgvae_stream_t stream) {
   CGVAE_REQUIRE(form >= 0 && form <= 2, "gemm: bad form %d", form);
   CGVAE_REQUIRE(M >= 0 && N >= 0 && K >= 0, "gemm: negative size");
   if (M == 0 || N == 0) return 0;
@@ -290,15 +376,17 @@ int cgvae_gemm(int form, const float* A, int64_t lda, const float* B, int64_t ld
   cudaStream_t st = (cudaStream_t)stream;
   float* wsf = reinterpret_cast<float*>(ws);
   // skinny problems (decoder graphs: 12..96 rows) stream the weight matrix: deep k-tiles keep 8-16 KB per CTA in flight
-  if (M <= 16) return launch_gemm<16, 32, 64, 1, 2>(form, A, lda, B, ldb, C, ldc, M, N, K, ep, wsf, ws_bytes, st);
-  if (M <= 32) return launch_gemm<32, 32, 64, 2, 2>(form, A, lda, B, ldb, C, ldc, M, N, K, ep, wsf, ws_bytes, st);
-  return launch_gemm<64, 64, 16, 4, 4>(form, A, lda, B, ldb, C, ldc, M, N, K, ep, wsf, ws_bytes, st);
+  if (M <= 16) return launch_gemm<16, 32, 64, 1, 2>(form, A, lda, B, ldb, C, ldc, M, N, K, ep, wsf, ws_bytes, counters, n_counters, st);
+  if (M <= 32) return launch_gemm<32, 32, 64, 2, 2>(form, A, lda, B, ldb, C, ldc, M, N, K, ep, wsf, ws_bytes, counters, n_counters, st);
+  if (M <= 48 && form != CGVAE_GEMM_TN)   // UpdateBlock mixes on 12-bead graphs: 36 rows
+    return launch_gemm<48, 32, 32, 3, 2>(form, A, lda, B, ldb, C, ldc, M, N, K, ep, wsf, ws_bytes, counters, n_counters, st);
+  return launch_gemm<64, 64, 16, 4, 4>(form, A, lda, B, ldb, C, ldc, M, N, K, ep, wsf, ws_bytes, counters, n_counters, st);
 }
 
 int cgvae_colsum(const float* X, int64_t ldx, int64_t M, int64_t N, float* out, cgvae_stream_t stream) {
   if (N == 0) return 0;
   CGVAE_REQUIRE(X && out, "colsum: null pointer");
-  colsum_kernel<<<(unsigned)ceil_div(N, 32), dim3(32, 8), 0, (cudaStream_t)stream>>>(X, ldx, M, N, out);
+  launch_kernel(colsum_kernel, dim3((unsigned)ceil_div(N, 32)), dim3(dim3(32, 8)), 0, (cudaStream_t)stream, X, ldx, M, N, out);
   return launched("colsum");
 }
 

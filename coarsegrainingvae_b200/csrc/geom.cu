@@ -19,6 +19,7 @@ __global__ void __launch_bounds__(256) edge_geometry_kernel(
     const float* __restrict__ coef, int R, int RB,
     float cutoff, const float* __restrict__ edge_wgt, const int32_t* __restrict__ eid, float* __restrict__ basis,
     float* __restrict__ unit) {
+  CGVAE_KERNEL_PROLOGUE();
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= E) return;
   if (e >= rowptr[n_recv]) {
@@ -77,6 +78,7 @@ __global__ void __launch_bounds__(256) edge_geometry_kernel(
 
 // reference layout v[N][F][3] <-> planar v[N][3][F]
 __global__ void vec_to_planar_kernel(const float* __restrict__ in, int64_t N, int F, float* __restrict__ out) {
+  CGVAE_KERNEL_PROLOGUE();
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // over N*3*F outputs
   if (idx >= N * 3 * (int64_t)F) return;
   const int f = (int)(idx % F);
@@ -85,6 +87,7 @@ __global__ void vec_to_planar_kernel(const float* __restrict__ in, int64_t N, in
   out[idx] = in[(n * F + f) * 3 + c];
 }
 __global__ void vec_from_planar_kernel(const float* __restrict__ in, int64_t N, int F, float* __restrict__ out) {
+  CGVAE_KERNEL_PROLOGUE();
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // over N*F*3 outputs
   if (idx >= N * 3 * (int64_t)F) return;
   const int c = (int)(idx % 3);
@@ -106,19 +109,19 @@ int cgvae_edge_geometry(const float* xyz_send, const float* xyz_recv, const floa
   CGVAE_REQUIRE(((xyz_send && xyz_recv) || r_edge) && rowptr && col && coef && basis && unit, "edge_geometry: null pointer");
   CGVAE_REQUIRE(R >= 1 && RB >= R + 1 && (RB % 4) == 0, "edge_geometry: need RB %% 4 == 0 and RB >= R+1 (R=%d RB=%d)", R, RB);
   CGVAE_REQUIRE(aligned16(unit) && aligned16(basis), "edge_geometry: outputs must be 16-byte aligned");
-  edge_geometry_kernel<<<(unsigned)ceil_div(n_edges, 256), 256, 0, (cudaStream_t)stream>>>(
+  launch_kernel(edge_geometry_kernel, dim3((unsigned)ceil_div(n_edges, 256)), dim3(256), 0, (cudaStream_t)stream, 
       xyz_send, xyz_recv, r_edge, rowptr, col, n_recv, n_edges, coef, R, RB, cutoff, edge_wgt, eid, basis, unit);
   return launched("edge_geometry");
 }
 
 int cgvae_vec_to_planar(const float* v_nf3, int64_t N, int F, float* v_n3f, cgvae_stream_t stream) {
   if (N == 0) return 0;
-  vec_to_planar_kernel<<<(unsigned)ceil_div(N * 3 * (int64_t)F, 256), 256, 0, (cudaStream_t)stream>>>(v_nf3, N, F, v_n3f);
+  launch_kernel(vec_to_planar_kernel, dim3((unsigned)ceil_div(N * 3 * (int64_t)F, 256)), dim3(256), 0, (cudaStream_t)stream, v_nf3, N, F, v_n3f);
   return launched("vec_to_planar");
 }
 int cgvae_vec_from_planar(const float* v_n3f, int64_t N, int F, float* v_nf3, cgvae_stream_t stream) {
   if (N == 0) return 0;
-  vec_from_planar_kernel<<<(unsigned)ceil_div(N * 3 * (int64_t)F, 256), 256, 0, (cudaStream_t)stream>>>(v_n3f, N, F, v_nf3);
+  launch_kernel(vec_from_planar_kernel, dim3((unsigned)ceil_div(N * 3 * (int64_t)F, 256)), dim3(256), 0, (cudaStream_t)stream, v_n3f, N, F, v_nf3);
   return launched("vec_from_planar");
 }
 

@@ -8,11 +8,20 @@ namespace cgvae {
 thread_local char g_err[512] = {0};
 std::atomic<unsigned long long> g_launches{0};
 
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("CGVAE_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
 // ------------------------------------------------------------------------------------------
 // scans (single CTA, 1024 threads x 8 items per sweep; inputs here are <= a few 1e5 long)
 // ------------------------------------------------------------------------------------------
 template <typename TOut>
 __global__ void __launch_bounds__(1024) scan_kernel(const int32_t* __restrict__ in, int64_t n, TOut* __restrict__ out) {
+  CGVAE_KERNEL_PROLOGUE();
   constexpr int ITEMS = 8;
   __shared__ long long warp_tot[32];
   __shared__ long long carry_sh;
@@ -89,6 +98,7 @@ constexpr int kSortWarps = 4;      // warps per CTA in the sorting kernels
 // odd-even transposition sort in global memory (correct, slow, not expected in practice).
 __global__ void __launch_bounds__(kSortWarps * 32) sort_rows_kernel(const int32_t* __restrict__ rowptr, int64_t n_rows,
                                                                     int32_t* __restrict__ data) {
+  CGVAE_KERNEL_PROLOGUE();
   __shared__ int buf[kSortWarps][kSortCap];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t row = (int64_t)blockIdx.x * kSortWarps + warp;
@@ -178,6 +188,7 @@ static size_t radius_ws_layout(int64_t n, int64_t n_frames, char* base, RadiusWs
 // one CTA per frame: bounding box -> cell grid (edge >= cutoff, total cells <= 8 n_f + 64)
 __global__ void __launch_bounds__(256) frame_bounds_kernel(const float* __restrict__ xyz, const int64_t* __restrict__ frame_ptr,
                                                            float cutoff, FrameInfo* __restrict__ frames) {
+  CGVAE_KERNEL_PROLOGUE();
   const int f = blockIdx.x;
   const int64_t beg = frame_ptr[f], end = frame_ptr[f + 1];
   float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
@@ -230,6 +241,7 @@ __global__ void __launch_bounds__(256) frame_bounds_kernel(const float* __restri
 }
 
 __global__ void frame_offsets_kernel(FrameInfo* frames, int64_t n_frames) {
+  CGVAE_KERNEL_PROLOGUE();
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     int run = 0;
     for (int64_t f = 0; f < n_frames; ++f) {
@@ -249,6 +261,7 @@ __device__ __forceinline__ void cell_coords(const FrameInfo& fi, float x, float 
 __global__ void assign_cells_kernel(const float* __restrict__ xyz, int64_t n, const int64_t* __restrict__ frame_ptr,
                                     int64_t n_frames, const FrameInfo* __restrict__ frames, int32_t* __restrict__ frame_of_atom,
                                     int32_t* __restrict__ cell_of_atom, int32_t* __restrict__ cell_count) {
+  CGVAE_KERNEL_PROLOGUE();
   const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= n) return;
   const int f = frame_of(frame_ptr, n_frames, a);
@@ -263,6 +276,7 @@ __global__ void assign_cells_kernel(const float* __restrict__ xyz, int64_t n, co
 
 __global__ void fill_cells_kernel(int64_t n, const int32_t* __restrict__ cell_of_atom, const int32_t* __restrict__ cell_start,
                                   int32_t* __restrict__ cursor, int32_t* __restrict__ cell_atoms) {
+  CGVAE_KERNEL_PROLOGUE();
   const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= n) return;
   const int c = cell_of_atom[a];
@@ -276,6 +290,7 @@ template <bool FILL, bool CELLS>
 __global__ void __launch_bounds__(kRadWarps * 32) radius_query_kernel(
     const float* __restrict__ xyz, int64_t n, const int64_t* __restrict__ frame_ptr, int64_t n_frames, float cutoff,
     int undirected, RadiusWs ws, int32_t* __restrict__ deg, const int64_t* __restrict__ rowptr, int64_t* __restrict__ out_pairs) {
+  CGVAE_KERNEL_PROLOGUE();
   __shared__ int buf[FILL ? kRadWarps : 1][FILL ? kSortCap : 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t i = (int64_t)blockIdx.x * kRadWarps + warp;
@@ -353,6 +368,7 @@ __global__ void __launch_bounds__(kRadWarps * 32) radius_query_kernel(
 // CSR
 // ------------------------------------------------------------------------------------------
 __global__ void edge_orientation_kernel(const int64_t* __restrict__ pairs, int64_t E, int32_t* __restrict__ flags) {
+  CGVAE_KERNEL_PROLOGUE();
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   bool up = false, down = false;
   if (e < E) {
@@ -377,6 +393,7 @@ __device__ __forceinline__ bool directed_edge(const int64_t* __restrict__ pairs,
 
 __global__ void csr_count_kernel(const int64_t* __restrict__ pairs, int64_t E, const int64_t* __restrict__ n_dev, int symmetrize,
                                  int32_t* __restrict__ deg_r, int32_t* __restrict__ deg_s) {
+  CGVAE_KERNEL_PROLOGUE();
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t i, j;
   if (!directed_edge(pairs, e, E, n_dev, symmetrize, i, j)) return;
@@ -389,6 +406,7 @@ __global__ void csr_place_kernel(const int64_t* __restrict__ pairs, int64_t E, c
                                  const int32_t* __restrict__ rowptr_r, const int32_t* __restrict__ rowptr_s,
                                  int32_t* __restrict__ cursor_r, int32_t* __restrict__ cursor_s,
                                  int32_t* __restrict__ eid_r, int32_t* __restrict__ eid_s) {
+  CGVAE_KERNEL_PROLOGUE();
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t i, j;
   if (!directed_edge(pairs, e, E, n_dev, symmetrize, i, j)) return;
@@ -400,6 +418,7 @@ __global__ void csr_place_kernel(const int64_t* __restrict__ pairs, int64_t E, c
 __global__ void csr_finish_r_kernel(const int64_t* __restrict__ pairs, int64_t E, const int64_t* __restrict__ n_dev, int symmetrize,
                                     int64_t cap, const int32_t* __restrict__ total, const int32_t* __restrict__ eid_r,
                                     int32_t* __restrict__ col, int32_t* __restrict__ slot_of_edge) {
+  CGVAE_KERNEL_PROLOGUE();
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= cap) return;
   if (t >= *total) { col[t] = 0; return; }
@@ -412,6 +431,7 @@ __global__ void csr_finish_r_kernel(const int64_t* __restrict__ pairs, int64_t E
 __global__ void csr_finish_s_kernel(const int64_t* __restrict__ pairs, int64_t E, const int64_t* __restrict__ n_dev, int symmetrize,
                                     int64_t cap, const int32_t* __restrict__ total, const int32_t* __restrict__ eid_s,
                                     const int32_t* __restrict__ slot_of_edge, int32_t* __restrict__ col_t, int32_t* __restrict__ perm_t) {
+  CGVAE_KERNEL_PROLOGUE();
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= cap) return;
   if (t >= *total) { col_t[t] = 0; perm_t[t] = 0; return; }
@@ -426,11 +446,13 @@ __global__ void csr_finish_s_kernel(const int64_t* __restrict__ pairs, int64_t E
 // segment ranks (CG2ChannelIdx)
 // ------------------------------------------------------------------------------------------
 __global__ void segment_count_kernel(const int64_t* __restrict__ mapping, int64_t n, int32_t* __restrict__ deg) {
+  CGVAE_KERNEL_PROLOGUE();
   const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (a < n) atomicAdd(&deg[mapping[a]], 1);
 }
 __global__ void segment_place_kernel(const int64_t* __restrict__ mapping, int64_t n, const int32_t* __restrict__ rowptr_b,
                                      int32_t* __restrict__ cursor, int32_t* __restrict__ atoms) {
+  CGVAE_KERNEL_PROLOGUE();
   const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= n) return;
   const int64_t b = mapping[a];
@@ -438,6 +460,7 @@ __global__ void segment_place_kernel(const int64_t* __restrict__ mapping, int64_
 }
 __global__ void segment_rank_kernel(const int64_t* __restrict__ mapping, int64_t n, const int32_t* __restrict__ rowptr_b,
                                     const int32_t* __restrict__ atoms, int32_t* __restrict__ slot_of_atom, int64_t* __restrict__ rank) {
+  CGVAE_KERNEL_PROLOGUE();
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
   const int a = atoms[t];
@@ -464,17 +487,17 @@ static int radius_prepare_cells(const float* xyz, int64_t n, const int64_t* fram
   CGVAE_REQUIRE(ws && ws_bytes >= cgvae_radius_graph_ws_bytes(n, n_frames), "radius_graph: workspace too small");
   radius_ws_layout(n, n_frames, reinterpret_cast<char*>(ws), w);
   CGVAE_CUDA(cudaMemsetAsync(w->cell_count, 0, sizeof(int32_t) * (size_t)w->max_cells, st));
-  frame_bounds_kernel<<<(unsigned)n_frames, 256, 0, st>>>(xyz, frame_ptr, cutoff, w->frames);
+  launch_kernel(frame_bounds_kernel, dim3((unsigned)n_frames), dim3(256), 0, st, xyz, frame_ptr, cutoff, w->frames);
   if (int rc = launched("frame_bounds")) return rc;
-  frame_offsets_kernel<<<1, 32, 0, st>>>(w->frames, n_frames);
+  launch_kernel(frame_offsets_kernel, dim3(1), dim3(32), 0, st, w->frames, n_frames);
   if (int rc = launched("frame_offsets")) return rc;
   const unsigned gb = (unsigned)ceil_div(n, 256);
-  assign_cells_kernel<<<gb, 256, 0, st>>>(xyz, n, frame_ptr, n_frames, w->frames, w->frame_of_atom, w->cell_of_atom, w->cell_count);
+  launch_kernel(assign_cells_kernel, dim3(gb), dim3(256), 0, st, xyz, n, frame_ptr, n_frames, w->frames, w->frame_of_atom, w->cell_of_atom, w->cell_count);
   if (int rc = launched("assign_cells")) return rc;
-  scan_kernel<int32_t><<<1, 1024, 0, st>>>(w->cell_count, w->max_cells, w->cell_start);
+  launch_kernel(scan_kernel<int32_t>, dim3(1), dim3(1024), 0, st, w->cell_count, w->max_cells, w->cell_start);
   if (int rc = launched("cell_scan")) return rc;
   CGVAE_CUDA(cudaMemsetAsync(w->cell_count, 0, sizeof(int32_t) * (size_t)w->max_cells, st));
-  fill_cells_kernel<<<gb, 256, 0, st>>>(n, w->cell_of_atom, w->cell_start, w->cell_count, w->cell_atoms);
+  launch_kernel(fill_cells_kernel, dim3(gb), dim3(256), 0, st, n, w->cell_of_atom, w->cell_start, w->cell_count, w->cell_atoms);
   return launched("fill_cells");
 }
 
@@ -487,10 +510,10 @@ int cgvae_radius_graph_count(const float* xyz, int64_t n, const int64_t* frame_p
   RadiusWs w{};
   if (use_cells) {
     if (int rc = radius_prepare_cells(xyz, n, frame_ptr, n_frames, cutoff, ws, ws_bytes, &w, st)) return rc;
-    radius_query_kernel<false, true><<<(unsigned)ceil_div(n, kRadWarps), kRadWarps * 32, 0, st>>>(
+    launch_kernel(radius_query_kernel<false, true>, dim3((unsigned)ceil_div(n, kRadWarps)), dim3(kRadWarps * 32), 0, st, 
         xyz, n, frame_ptr, n_frames, cutoff, undirected, w, deg, nullptr, nullptr);
   } else {
-    radius_query_kernel<false, false><<<(unsigned)ceil_div(n, kRadWarps), kRadWarps * 32, 0, st>>>(
+    launch_kernel(radius_query_kernel<false, false>, dim3((unsigned)ceil_div(n, kRadWarps)), dim3(kRadWarps * 32), 0, st, 
         xyz, n, frame_ptr, n_frames, cutoff, undirected, w, deg, nullptr, nullptr);
   }
   return launched("radius_count");
@@ -507,10 +530,10 @@ int cgvae_radius_graph_fill(const float* xyz, int64_t n, const int64_t* frame_pt
     // the cell structure written by cgvae_radius_graph_count into `ws` is reused as is
     CGVAE_REQUIRE(ws && ws_bytes >= cgvae_radius_graph_ws_bytes(n, n_frames), "radius_graph_fill: workspace too small");
     radius_ws_layout(n, n_frames, reinterpret_cast<char*>(ws), &w);
-    radius_query_kernel<true, true><<<(unsigned)ceil_div(n, kRadWarps), kRadWarps * 32, 0, st>>>(
+    launch_kernel(radius_query_kernel<true, true>, dim3((unsigned)ceil_div(n, kRadWarps)), dim3(kRadWarps * 32), 0, st, 
         xyz, n, frame_ptr, n_frames, cutoff, undirected, w, nullptr, rowptr, out_pairs);
   } else {
-    radius_query_kernel<true, false><<<(unsigned)ceil_div(n, kRadWarps), kRadWarps * 32, 0, st>>>(
+    launch_kernel(radius_query_kernel<true, false>, dim3((unsigned)ceil_div(n, kRadWarps)), dim3(kRadWarps * 32), 0, st, 
         xyz, n, frame_ptr, n_frames, cutoff, undirected, w, nullptr, rowptr, out_pairs);
   }
   return launched("radius_fill");
@@ -518,12 +541,12 @@ int cgvae_radius_graph_fill(const float* xyz, int64_t n, const int64_t* frame_pt
 
 int cgvae_exclusive_scan(const int32_t* counts, int64_t n, int64_t* out, cgvae_stream_t stream) {
   CGVAE_REQUIRE(n >= 0 && out, "exclusive_scan: bad arguments");
-  scan_kernel<int64_t><<<1, 1024, 0, (cudaStream_t)stream>>>(counts, n, out);
+  launch_kernel(scan_kernel<int64_t>, dim3(1), dim3(1024), 0, (cudaStream_t)stream, counts, n, out);
   return launched("scan_i64");
 }
 int cgvae_scan_i32(const int32_t* counts, int64_t n, int32_t* out, cgvae_stream_t stream) {
   CGVAE_REQUIRE(n >= 0 && out, "scan_i32: bad arguments");
-  scan_kernel<int32_t><<<1, 1024, 0, (cudaStream_t)stream>>>(counts, n, out);
+  launch_kernel(scan_kernel<int32_t>, dim3(1), dim3(1024), 0, (cudaStream_t)stream, counts, n, out);
   return launched("scan_i32");
 }
 
@@ -532,7 +555,7 @@ int cgvae_edge_orientation(const int64_t* pairs, int64_t n_edges, int32_t* flags
   CGVAE_REQUIRE(flags, "edge_orientation: null flags");
   CGVAE_CUDA(cudaMemsetAsync(flags, 0, 2 * sizeof(int32_t), st));
   if (n_edges == 0) return 0;
-  edge_orientation_kernel<<<(unsigned)ceil_div(n_edges, 256), 256, 0, st>>>(pairs, n_edges, flags);
+  launch_kernel(edge_orientation_kernel, dim3((unsigned)ceil_div(n_edges, 256)), dim3(256), 0, st, pairs, n_edges, flags);
   return launched("edge_orientation");
 }
 
@@ -544,7 +567,7 @@ int cgvae_csr_count(const int64_t* pairs, int64_t n_edges, const int64_t* n_edge
   CGVAE_CUDA(cudaMemsetAsync(deg_r, 0, sizeof(int32_t) * (size_t)n_recv, st));
   CGVAE_CUDA(cudaMemsetAsync(deg_s, 0, sizeof(int32_t) * (size_t)n_send, st));
   if (cap == 0) return 0;
-  csr_count_kernel<<<(unsigned)ceil_div(cap, 256), 256, 0, st>>>(pairs, n_edges, n_edges_dev, symmetrize, deg_r, deg_s);
+  launch_kernel(csr_count_kernel, dim3((unsigned)ceil_div(cap, 256)), dim3(256), 0, st, pairs, n_edges, n_edges_dev, symmetrize, deg_r, deg_s);
   return launched("csr_count");
 }
 
@@ -562,18 +585,18 @@ int cgvae_csr_fill(const int64_t* pairs, int64_t n_edges_in, const int64_t* n_ed
   int32_t* slot_of_edge = eid_s + n_edges;
   CGVAE_CUDA(cudaMemsetAsync(cursor_r, 0, sizeof(int32_t) * (size_t)(n_recv + n_send), st));
   const unsigned gb = (unsigned)ceil_div(n_edges, 256);
-  csr_place_kernel<<<gb, 256, 0, st>>>(pairs, n_edges_in, n_edges_dev, symmetrize, rowptr_r, rowptr_s, cursor_r, cursor_s, eid, eid_s);
+  launch_kernel(csr_place_kernel, dim3(gb), dim3(256), 0, st, pairs, n_edges_in, n_edges_dev, symmetrize, rowptr_r, rowptr_s, cursor_r, cursor_s, eid, eid_s);
   if (int rc = launched("csr_place")) return rc;
   // rows were filled in atomic (arbitrary) order: sorting by edge id makes the layout deterministic and
   // keeps the reference's edge-list order inside every row
-  sort_rows_kernel<<<(unsigned)ceil_div(n_recv, kSortWarps), kSortWarps * 32, 0, st>>>(rowptr_r, n_recv, eid);
+  launch_kernel(sort_rows_kernel, dim3((unsigned)ceil_div(n_recv, kSortWarps)), dim3(kSortWarps * 32), 0, st, rowptr_r, n_recv, eid);
   if (int rc = launched("csr_sort_r")) return rc;
-  sort_rows_kernel<<<(unsigned)ceil_div(n_send, kSortWarps), kSortWarps * 32, 0, st>>>(rowptr_s, n_send, eid_s);
+  launch_kernel(sort_rows_kernel, dim3((unsigned)ceil_div(n_send, kSortWarps)), dim3(kSortWarps * 32), 0, st, rowptr_s, n_send, eid_s);
   if (int rc = launched("csr_sort_s")) return rc;
-  csr_finish_r_kernel<<<gb, 256, 0, st>>>(pairs, n_edges_in, n_edges_dev, symmetrize, n_edges, rowptr_r + n_recv, eid, col,
+  launch_kernel(csr_finish_r_kernel, dim3(gb), dim3(256), 0, st, pairs, n_edges_in, n_edges_dev, symmetrize, n_edges, rowptr_r + n_recv, eid, col,
                                           slot_of_edge);
   if (int rc = launched("csr_finish_r")) return rc;
-  csr_finish_s_kernel<<<gb, 256, 0, st>>>(pairs, n_edges_in, n_edges_dev, symmetrize, n_edges, rowptr_s + n_send, eid_s,
+  launch_kernel(csr_finish_s_kernel, dim3(gb), dim3(256), 0, st, pairs, n_edges_in, n_edges_dev, symmetrize, n_edges, rowptr_s + n_send, eid_s,
                                           slot_of_edge, col_t, perm_t);
   return launched("csr_finish_s");
 }
@@ -583,7 +606,7 @@ int cgvae_segment_count(const int64_t* mapping, int64_t n, int64_t n_beads, int3
   CGVAE_REQUIRE(deg && n >= 0 && n < INT_MAX, "segment_count: bad arguments");
   CGVAE_CUDA(cudaMemsetAsync(deg, 0, sizeof(int32_t) * (size_t)n_beads, st));
   if (n == 0) return 0;
-  segment_count_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(mapping, n, deg);
+  launch_kernel(segment_count_kernel, dim3((unsigned)ceil_div(n, 256)), dim3(256), 0, st, mapping, n, deg);
   return launched("segment_count");
 }
 
@@ -594,11 +617,11 @@ int cgvae_segment_rank(const int64_t* mapping, int64_t n, int64_t n_beads, const
   CGVAE_REQUIRE(mapping && rowptr_b && scratch && atoms && slot_of_atom && rank, "segment_rank: null pointer");
   CGVAE_CUDA(cudaMemsetAsync(scratch, 0, sizeof(int32_t) * (size_t)n_beads, st));
   const unsigned gb = (unsigned)ceil_div(n, 256);
-  segment_place_kernel<<<gb, 256, 0, st>>>(mapping, n, rowptr_b, scratch, atoms);
+  launch_kernel(segment_place_kernel, dim3(gb), dim3(256), 0, st, mapping, n, rowptr_b, scratch, atoms);
   if (int rc = launched("segment_place")) return rc;
-  sort_rows_kernel<<<(unsigned)ceil_div(n_beads, kSortWarps), kSortWarps * 32, 0, st>>>(rowptr_b, n_beads, atoms);
+  launch_kernel(sort_rows_kernel, dim3((unsigned)ceil_div(n_beads, kSortWarps)), dim3(kSortWarps * 32), 0, st, rowptr_b, n_beads, atoms);
   if (int rc = launched("segment_sort")) return rc;
-  segment_rank_kernel<<<gb, 256, 0, st>>>(mapping, n, rowptr_b, atoms, slot_of_atom, rank);
+  launch_kernel(segment_rank_kernel, dim3(gb), dim3(256), 0, st, mapping, n, rowptr_b, atoms, slot_of_atom, rank);
   return launched("segment_rank");
 }
 

@@ -40,6 +40,7 @@ __global__ void __launch_bounds__(kMsgWarps * 32) message_fwd_kernel(
     const float* __restrict__ unit, const float* __restrict__ Wf, const float* __restrict__ bf, int64_t n_recv, int F, int R,
     const float* __restrict__ res_s, const float* __restrict__ res_v, int v_is_zero, float* __restrict__ out_s,
     float* __restrict__ out_v, float* __restrict__ q_out) {
+  CGVAE_KERNEL_PROLOGUE();
   constexpr int RB = 4 * RBQ;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t i = (int64_t)blockIdx.x * kMsgWarps + warp;
@@ -56,7 +57,7 @@ __global__ void __launch_bounds__(kMsgWarps * 32) message_fwd_kernel(
 
   float acc_s = 0.f, acc_v[3] = {0.f, 0.f, 0.f}, acc_q[3] = {0.f, 0.f, 0.f};
   const int beg = rowptr[i], end = rowptr[i + 1];
-#pragma unroll 2
+#pragma unroll 4
   for (int e = beg; e < end; ++e) {
     const int j = __ldg(col + e);
     float b[RB];
@@ -123,6 +124,7 @@ __global__ void __launch_bounds__(kMsgWarps * 32) message_bwd_kernel(
     const float* __restrict__ Wf, const float* __restrict__ bf, int64_t n_send, int F, int R,
     const float* __restrict__ g_out_s, const float* __restrict__ g_out_v, int residual, int v_is_zero,
     float* __restrict__ g_phi, float* __restrict__ g_v_send, float* __restrict__ partial, int senders_per_cta) {
+  CGVAE_KERNEL_PROLOGUE();
   constexpr int RB = 4 * RBQ;
   __shared__ float Wsm[KS][RB][32];
   __shared__ float dWsm[kMsgWarps][KS][RB][32];
@@ -255,6 +257,7 @@ __global__ void __launch_bounds__(kMsgWarps * 32) message_bwd_kernel(
 // dWf[(k*F+f)][r] = sum_chunks partial[chunk][k][r][f] (r < R); dbf[k*F+f] = same at r == R
 __global__ void __launch_bounds__(256) filter_grad_finalize_kernel(const float* __restrict__ partial, int n_chunks, int KS, int RB,
                                                                    int F, int R, float* __restrict__ dWf, float* __restrict__ dbf) {
+  CGVAE_KERNEL_PROLOGUE();
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // over KS*(R+1)*F, f fastest
   if (idx >= (int64_t)KS * (R + 1) * F) return;
   const int f = (int)(idx % F);
@@ -283,19 +286,39 @@ __device__ __forceinline__ void load3(const float* __restrict__ base, int64_t no
 constexpr int kMaxRB9 = 16;
 
 // The slice of split k is the contiguous chunk Wf[(k*F+f0)*R ... +nch*R): read it coalesced and transpose into
-// Wsm[k][r][lane] (the strided per-element gather this replaces dominated the 9-split kernels on tiny graphs).
+// Wsm[k][r][lane].  All global loads are issued before the first shared store (fully unrolled, predicated), otherwise
+// the ~36 dependent-latency round trips dominate these tiny-graph kernels.  blockDim.x == kMsgWarps*32.
 __device__ __forceinline__ void stage_filter9(float (*Wsm)[kMaxRB9][32], const float* __restrict__ Wf,
                                               const float* __restrict__ bf, int F, int R, int RB, int f0) {
+  constexpr int NTH = kMsgWarps * 32;
+  constexpr int ITERS = (32 * (kMaxRB9 - 1) + NTH - 1) / NTH;   // R <= 15
   const int nch = min(32, F - f0);
+  const int tid = threadIdx.x;
+  int ls[ITERS], rs[ITERS];
+  bool ok[ITERS];
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it) {
+    const int idx = tid + it * NTH;
+    ls[it] = idx / R;
+    rs[it] = idx - ls[it] * R;
+    ok[it] = idx < 32 * R && ls[it] < nch;
+  }
+  float tmp[9][ITERS], bias[9];
+#pragma unroll
   for (int k = 0; k < 9; ++k) {
     const float* src = Wf + ((int64_t)k * F + f0) * R;
-    for (int idx = threadIdx.x; idx < 32 * R; idx += blockDim.x) {
-      const int l = idx / R, r = idx - l * R;
-      Wsm[k][r][l] = (l < nch) ? src[idx] : 0.f;
-    }
-    for (int idx = threadIdx.x; idx < 32 * (RB - R); idx += blockDim.x) {
-      const int l = idx & 31, r = R + (idx >> 5);
-      Wsm[k][r][l] = (r == R && l < nch) ? bf[(int64_t)k * F + f0 + l] : 0.f;
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) tmp[k][it] = ok[it] ? __ldg(src + tid + it * NTH) : 0.f;
+    bias[k] = (tid < nch) ? __ldg(bf + (int64_t)k * F + f0 + tid) : 0.f;
+  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it)
+      if (tid + it * NTH < 32 * R) Wsm[k][rs[it]][ls[it]] = tmp[k][it];
+    if (tid < 32) {
+      Wsm[k][R][tid] = bias[k];
+      for (int r = R + 1; r < RB; ++r) Wsm[k][r][tid] = 0.f;
     }
   }
 }
@@ -306,6 +329,7 @@ __global__ void __launch_bounds__(kMsgWarps * 32) message9_fwd_kernel(
     const float* __restrict__ basis, const float* __restrict__ unit, const float* __restrict__ Wf, const float* __restrict__ bf,
     int64_t n, int F, int R, int RB, int residual, float* __restrict__ out_s, float* __restrict__ out_sbar,
     float* __restrict__ out_v, float* __restrict__ out_vbar) {
+  CGVAE_KERNEL_PROLOGUE();
   __shared__ float Wsm[9][kMaxRB9][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   stage_filter9(Wsm, Wf, bf, F, R, RB, blockIdx.y * 32);
@@ -318,6 +342,7 @@ __global__ void __launch_bounds__(kMsgWarps * 32) message9_fwd_kernel(
   load3(v, i, F, f, v_i);
   load3(vbar, i, F, f, vb_i);
   float a_s = 0.f, a_sb = 0.f, a_v[3] = {0.f, 0.f, 0.f}, a_vb[3] = {0.f, 0.f, 0.f};
+#pragma unroll 2
   for (int e = rowptr[i]; e < rowptr[i + 1]; ++e) {
     const int j = col[e];
     const float* b = basis + (int64_t)e * RB;
@@ -362,6 +387,7 @@ __global__ void __launch_bounds__(kMsgWarps * 32) message9_bwd_kernel(
     int64_t n, int F, int R, int RB, int residual, const float* __restrict__ g_s, const float* __restrict__ g_sbar,
     const float* __restrict__ g_v, const float* __restrict__ g_vbar, float* __restrict__ gi_s, float* __restrict__ gi_sbar,
     float* __restrict__ gi_v, float* __restrict__ gi_vbar, float* __restrict__ g_phi, float* __restrict__ gw) {
+  CGVAE_KERNEL_PROLOGUE();
   __shared__ float Wsm[9][kMaxRB9][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   stage_filter9(Wsm, Wf, bf, F, R, RB, blockIdx.y * 32);
@@ -508,7 +534,7 @@ int cgvae_message_fwd(int n_split, const float* phi, const float* v_send, const 
   dim3 grid((unsigned)ceil_div(n_recv, kMsgWarps), (unsigned)ceil_div(F, 32));
   cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH_FWD(KS, RBQ)                                                                                            \
-  message_fwd_kernel<KS, RBQ><<<grid, kMsgWarps * 32, 0, st>>>(phi, v_send, v_recv, rowptr, col, basis, unit, Wf, bf, \
+  launch_kernel(message_fwd_kernel<KS, RBQ>, dim3(grid), dim3(kMsgWarps * 32), 0, st, phi, v_send, v_recv, rowptr, col, basis, unit, Wf, bf, \
                                                                n_recv, F, R, res_s, res_v, v_is_zero, out_s, out_v, q)
   if (n_split == 3) {
     if (RB == 8) LAUNCH_FWD(3, 2); else if (RB == 12) LAUNCH_FWD(3, 3); else LAUNCH_FWD(3, 4);
@@ -547,7 +573,7 @@ int cgvae_message_bwd(int n_split, const float* phi, const float* v_send, const 
   } else {
     dim3 grid((unsigned)chunks, (unsigned)ceil_div(F, 32));
 #define LAUNCH_BWD(KS, RBQ)                                                                                               \
-  message_bwd_kernel<KS, RBQ><<<grid, kMsgWarps * 32, 0, st>>>(phi, v_send, v_recv, q, rowptr_t, col_t, perm_t, basis, unit, \
+  launch_kernel(message_bwd_kernel<KS, RBQ>, dim3(grid), dim3(kMsgWarps * 32), 0, st, phi, v_send, v_recv, q, rowptr_t, col_t, perm_t, basis, unit, \
                                                                Wf, bf, n_send, F, R, g_out_s, g_out_v, residual, v_is_zero,  \
                                                                g_phi, g_v_send, partial, per)
     if (n_split == 3) {
@@ -559,7 +585,7 @@ int cgvae_message_bwd(int n_split, const float* phi, const float* v_send, const 
     if (int rc = launched("message_bwd")) return rc;
   }
   const int64_t total = (int64_t)n_split * (R + 1) * F;
-  filter_grad_finalize_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(partial, n_send == 0 ? 1 : chunks, n_split, RB, F, R,
+  launch_kernel(filter_grad_finalize_kernel, dim3((unsigned)ceil_div(total, 256)), dim3(256), 0, st, partial, n_send == 0 ? 1 : chunks, n_split, RB, F, R,
                                                                                dWf, dbf);
   return launched("filter_grad_finalize");
 }
@@ -573,7 +599,7 @@ int cgvae_message9_fwd(const float* phi, const float* s, const float* sbar, cons
   CGVAE_REQUIRE(phi && s && sbar && v && vbar && rowptr && col && basis && unit && Wf && bf && out_s && out_sbar && out_v && out_vbar,
                 "message9_fwd: null pointer");
   dim3 grid((unsigned)ceil_div(n, kMsgWarps), (unsigned)ceil_div(F, 32));
-  message9_fwd_kernel<<<grid, kMsgWarps * 32, 0, (cudaStream_t)stream>>>(phi, s, sbar, v, vbar, rowptr, col, basis, unit, Wf, bf, n,
+  launch_kernel(message9_fwd_kernel, dim3(grid), dim3(kMsgWarps * 32), 0, (cudaStream_t)stream, phi, s, sbar, v, vbar, rowptr, col, basis, unit, Wf, bf, n,
                                                                          F, R, RB, residual, out_s, out_sbar, out_v, out_vbar);
   return launched("message9_fwd");
 }
@@ -591,7 +617,7 @@ int cgvae_message9_bwd(const float* phi, const float* s, const float* sbar, cons
   dim3 grid((unsigned)ceil_div(n, kMsgWarps), (unsigned)ceil_div(F, 32));
   // gw rows of unused (padded) edge slots must read as zero in the dWf = gw^T basis contraction
   CGVAE_CUDA(cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)n_edge_slots * 9 * (size_t)F, (cudaStream_t)stream));
-  message9_bwd_kernel<<<grid, kMsgWarps * 32, 0, (cudaStream_t)stream>>>(phi, s, sbar, v, vbar, rowptr, col, rowptr_t, col_t, perm_t,
+  launch_kernel(message9_bwd_kernel, dim3(grid), dim3(kMsgWarps * 32), 0, (cudaStream_t)stream, phi, s, sbar, v, vbar, rowptr, col, rowptr_t, col_t, perm_t,
                                                                          basis, unit, Wf, bf, n, F, R, RB, residual, g_s, g_sbar,
                                                                          g_v, g_vbar, gi_s, gi_sbar, gi_v, gi_vbar, g_phi, gw);
   return launched("message9_bwd");

@@ -8,6 +8,7 @@ namespace cgvae {
 // x[n] = [ s[n] | sqrt(sum_c (Vv[n][c]^2 + 1e-10)) ]
 __global__ void __launch_bounds__(256) update_norm_fwd_kernel(const float* __restrict__ s, const float* __restrict__ Vv, int64_t N,
                                                               int F, float* __restrict__ x) {
+  CGVAE_KERNEL_PROLOGUE();
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= N * F) return;
   const int64_t n = idx / F;
@@ -24,6 +25,7 @@ __global__ void __launch_bounds__(256) update_combine_fwd_kernel(const float* __
                                                                  const float* __restrict__ Uv, const float* __restrict__ Vv,
                                                                  const float* __restrict__ q, int64_t N, int F, int residual,
                                                                  float* __restrict__ s_out, float* __restrict__ v_out) {
+  CGVAE_KERNEL_PROLOGUE();
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= N * F) return;
   const int64_t n = idx / F;
@@ -45,6 +47,7 @@ __global__ void __launch_bounds__(256) update_combine_bwd_kernel(const float* __
                                                                  const float* __restrict__ g_v, int64_t N, int F,
                                                                  float* __restrict__ gq, float* __restrict__ gUv,
                                                                  float* __restrict__ gVv) {
+  CGVAE_KERNEL_PROLOGUE();
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= N * F) return;
   const int64_t n = idx / F;
@@ -71,6 +74,7 @@ __global__ void __launch_bounds__(256) update_norm_bwd_kernel(const float* __res
                                                               const float* __restrict__ gx, const float* __restrict__ g_s,
                                                               int64_t N, int F, int residual, float* __restrict__ gs_in,
                                                               float* __restrict__ gVv) {
+  CGVAE_KERNEL_PROLOGUE();
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= N * F) return;
   const int64_t n = idx / F;
@@ -86,6 +90,7 @@ __global__ void __launch_bounds__(256) update_norm_bwd_kernel(const float* __res
 __global__ void __launch_bounds__(256) segment_reduce_fwd_kernel(const float* __restrict__ X, const int32_t* __restrict__ rowptr_b,
                                                                  const int32_t* __restrict__ atoms, int64_t W, int mean,
                                                                  float* __restrict__ out) {
+  CGVAE_KERNEL_PROLOGUE();
   const int64_t b = blockIdx.x;
   const int64_t w = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
   if (w >= W) return;
@@ -98,6 +103,7 @@ __global__ void __launch_bounds__(256) segment_reduce_fwd_kernel(const float* __
 __global__ void __launch_bounds__(256) segment_reduce_bwd_kernel(const float* __restrict__ g_out, const int64_t* __restrict__ mapping,
                                                                  const int32_t* __restrict__ rowptr_b, int64_t W, int mean,
                                                                  float* __restrict__ g_X) {
+  CGVAE_KERNEL_PROLOGUE();
   const int64_t a = blockIdx.x;
   const int64_t w = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
   if (w >= W) return;
@@ -109,6 +115,7 @@ __global__ void __launch_bounds__(256) segment_reduce_bwd_kernel(const float* __
 
 __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ table, const int64_t* __restrict__ idx, int64_t W,
                                                           float* __restrict__ out) {
+  CGVAE_KERNEL_PROLOGUE();
   const int64_t n = blockIdx.x;
   const int64_t w = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
   if (w >= W) return;
@@ -120,6 +127,7 @@ __global__ void __launch_bounds__(128) lift_fwd_kernel(const float* __restrict__
                                                        const int64_t* __restrict__ rank, const int32_t* __restrict__ rowptr_b,
                                                        const int32_t* __restrict__ atoms, const uint8_t* __restrict__ pin,
                                                        int64_t n_beads, int F, int mode, float* __restrict__ xyz_out) {
+  CGVAE_KERNEL_PROLOGUE();
   const int lane = threadIdx.x & 31;
   const int64_t b = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
   if (b >= n_beads) return;
@@ -151,6 +159,7 @@ __global__ void __launch_bounds__(128) lift_bwd_kernel(const float* __restrict__
                                                        const int32_t* __restrict__ rowptr_b, const int32_t* __restrict__ atoms,
                                                        const uint8_t* __restrict__ pin, int64_t n_beads, int F, int mode,
                                                        float* __restrict__ g_V) {
+  CGVAE_KERNEL_PROLOGUE();
   const int lane = threadIdx.x & 31;
   const int64_t b = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
   if (b >= n_beads) return;
@@ -185,14 +194,14 @@ extern "C" {
 int cgvae_update_norm_fwd(const float* s, const float* Vv, int64_t N, int F, float* x, cgvae_stream_t stream) {
   if (N == 0) return 0;
   CGVAE_REQUIRE(s && Vv && x, "update_norm_fwd: null pointer");
-  update_norm_fwd_kernel<<<(unsigned)ceil_div(N * F, 256), 256, 0, (cudaStream_t)stream>>>(s, Vv, N, F, x);
+  launch_kernel(update_norm_fwd_kernel, dim3((unsigned)ceil_div(N * F, 256)), dim3(256), 0, (cudaStream_t)stream, s, Vv, N, F, x);
   return launched("update_norm_fwd");
 }
 int cgvae_update_combine_fwd(const float* s, const float* v, const float* Uv, const float* Vv, const float* q, int64_t N, int F,
                              int residual, float* s_out, float* v_out, cgvae_stream_t stream) {
   if (N == 0) return 0;
   CGVAE_REQUIRE(Uv && Vv && q && s_out && v_out && (!residual || (s && v)), "update_combine_fwd: null pointer");
-  update_combine_fwd_kernel<<<(unsigned)ceil_div(N * F, 256), 256, 0, (cudaStream_t)stream>>>(s, v, Uv, Vv, q, N, F, residual, s_out,
+  launch_kernel(update_combine_fwd_kernel, dim3((unsigned)ceil_div(N * F, 256)), dim3(256), 0, (cudaStream_t)stream, s, v, Uv, Vv, q, N, F, residual, s_out,
                                                                                              v_out);
   return launched("update_combine_fwd");
 }
@@ -200,14 +209,14 @@ int cgvae_update_combine_bwd(const float* Uv, const float* Vv, const float* q, c
                              float* gq, float* gUv, float* gVv, cgvae_stream_t stream) {
   if (N == 0) return 0;
   CGVAE_REQUIRE(Uv && Vv && q && g_s && g_v && gq && gUv && gVv, "update_combine_bwd: null pointer");
-  update_combine_bwd_kernel<<<(unsigned)ceil_div(N * F, 256), 256, 0, (cudaStream_t)stream>>>(Uv, Vv, q, g_s, g_v, N, F, gq, gUv, gVv);
+  launch_kernel(update_combine_bwd_kernel, dim3((unsigned)ceil_div(N * F, 256)), dim3(256), 0, (cudaStream_t)stream, Uv, Vv, q, g_s, g_v, N, F, gq, gUv, gVv);
   return launched("update_combine_bwd");
 }
 int cgvae_update_norm_bwd(const float* x, const float* Vv, const float* gx, const float* g_s, int64_t N, int F, int residual,
                           float* gs_in, float* gVv, cgvae_stream_t stream) {
   if (N == 0) return 0;
   CGVAE_REQUIRE(x && Vv && gx && gs_in && gVv && (!residual || g_s), "update_norm_bwd: null pointer");
-  update_norm_bwd_kernel<<<(unsigned)ceil_div(N * F, 256), 256, 0, (cudaStream_t)stream>>>(x, Vv, gx, g_s, N, F, residual, gs_in, gVv);
+  launch_kernel(update_norm_bwd_kernel, dim3((unsigned)ceil_div(N * F, 256)), dim3(256), 0, (cudaStream_t)stream, x, Vv, gx, g_s, N, F, residual, gs_in, gVv);
   return launched("update_norm_bwd");
 }
 
@@ -216,7 +225,7 @@ int cgvae_segment_reduce_fwd(const float* X, const int32_t* rowptr_b, const int3
   if (n_beads == 0 || W == 0) return 0;
   CGVAE_REQUIRE(X && rowptr_b && atoms && out, "segment_reduce_fwd: null pointer");
   dim3 grid((unsigned)n_beads, (unsigned)ceil_div(W, 256));
-  segment_reduce_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(X, rowptr_b, atoms, W, mean, out);
+  launch_kernel(segment_reduce_fwd_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, X, rowptr_b, atoms, W, mean, out);
   return launched("segment_reduce_fwd");
 }
 int cgvae_segment_reduce_bwd(const float* g_out, const int64_t* mapping, const int32_t* rowptr_b, int64_t N, int64_t W, int mean,
@@ -224,14 +233,14 @@ int cgvae_segment_reduce_bwd(const float* g_out, const int64_t* mapping, const i
   if (N == 0 || W == 0) return 0;
   CGVAE_REQUIRE(g_out && mapping && rowptr_b && g_X, "segment_reduce_bwd: null pointer");
   dim3 grid((unsigned)N, (unsigned)ceil_div(W, 256));
-  segment_reduce_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g_out, mapping, rowptr_b, W, mean, g_X);
+  launch_kernel(segment_reduce_bwd_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, g_out, mapping, rowptr_b, W, mean, g_X);
   return launched("segment_reduce_bwd");
 }
 int cgvae_gather_rows(const float* table, const int64_t* idx, int64_t N, int64_t W, float* out, cgvae_stream_t stream) {
   if (N == 0 || W == 0) return 0;
   CGVAE_REQUIRE(table && idx && out, "gather_rows: null pointer");
   dim3 grid((unsigned)N, (unsigned)ceil_div(W, 256));
-  gather_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(table, idx, W, out);
+  launch_kernel(gather_rows_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, table, idx, W, out);
   return launched("gather_rows");
 }
 
@@ -242,7 +251,7 @@ int cgvae_lift_fwd(const float* V, const float* cg_xyz, const int64_t* mapping, 
   if (N == 0 || n_beads == 0) return 0;
   CGVAE_REQUIRE(V && cg_xyz && rank && rowptr_b && atoms && xyz_out, "lift_fwd: null pointer");
   CGVAE_REQUIRE(mode >= 0 && mode <= 2, "lift_fwd: bad mode %d", mode);
-  lift_fwd_kernel<<<(unsigned)ceil_div(n_beads, 4), 128, 0, (cudaStream_t)stream>>>(V, cg_xyz, rank, rowptr_b, atoms, pin, n_beads, F,
+  launch_kernel(lift_fwd_kernel, dim3((unsigned)ceil_div(n_beads, 4)), dim3(128), 0, (cudaStream_t)stream, V, cg_xyz, rank, rowptr_b, atoms, pin, n_beads, F,
                                                                                    mode, xyz_out);
   return launched("lift_fwd");
 }
@@ -254,7 +263,7 @@ int cgvae_lift_bwd(const float* g_xyz, const int64_t* mapping, const int64_t* ra
   CGVAE_REQUIRE(g_xyz && rank && rowptr_b && atoms && g_V, "lift_bwd: null pointer");
   CGVAE_CUDA(cudaMemsetAsync(g_V, 0, sizeof(float) * (size_t)n_beads * 3 * (size_t)F, st));
   if (N == 0) return 0;
-  lift_bwd_kernel<<<(unsigned)ceil_div(n_beads, 4), 128, 0, st>>>(g_xyz, rank, rowptr_b, atoms, pin, n_beads, F, mode, g_V);
+  launch_kernel(lift_bwd_kernel, dim3((unsigned)ceil_div(n_beads, 4)), dim3(128), 0, st, g_xyz, rank, rowptr_b, atoms, pin, n_beads, F, mode, g_V);
   return launched("lift_bwd");
 }
 

@@ -347,6 +347,19 @@ def edge_geometry(graph, xyz_send, xyz_recv, n_rbf, cutoff, edge_wgt=None, r_edg
 # --------------------------------------------------------------------------------------------------
 
 _SPLITK_WS_BYTES = 32 << 20
+_N_TICKETS = 1024
+_TICKETS = {}
+
+
+def _tickets(dev, stream):
+    """zero-initialised split-K ticket counters, one array per (device, stream): launches on different streams may run
+    concurrently and must not share tickets; every kernel leaves its tickets at zero."""
+    key = (dev.index, stream)
+    t = _TICKETS.get(key)
+    if t is None:
+        t = torch.zeros(_N_TICKETS, dtype=torch.int32, device=dev)
+        _TICKETS[key] = t
+    return t
 
 
 def gemm(form, A, B, M, N, K, bias=None, act=0, z_out=False, z_in=None, dact=0, add=None, out=None):
@@ -357,9 +370,14 @@ def gemm(form, A, B, M, N, K, bias=None, act=0, z_out=False, z_in=None, dact=0, 
     C = out if out is not None else torch.empty((M, N), dtype=torch.float32, device=dev)
     Z = torch.empty((M, N), dtype=torch.float32, device=dev) if z_out else None
     tiles = ((M + 63) // 64) * ((N + 63) // 64) if M > 32 else ((N + 31) // 32)
-    ws = torch.empty(_SPLITK_WS_BYTES, dtype=torch.uint8, device=dev) if (tiles < 148 and K >= 512) else None
+    st = _stream()
+    ws = tk = None
+    if tiles < 148 and K >= 512:
+        ws = torch.empty(_SPLITK_WS_BYTES, dtype=torch.uint8, device=dev)
+        tk = _tickets(dev, st)
     _lib.check(lib.cgvae_gemm(form, _p(A), A.stride(0), _p(B), B.stride(0), _p(C), C.stride(0), M, N, K, _p(bias), act, _p(Z),
-                              _p(z_in), dact, _p(add), _p(ws), _SPLITK_WS_BYTES if ws is not None else 0, _stream()), "gemm")
+                              _p(z_in), dact, _p(add), _p(ws), _SPLITK_WS_BYTES if ws is not None else 0, _p(tk),
+                              _N_TICKETS if tk is not None else 0, st), "gemm")
     return (C, Z) if z_out else C
 
 

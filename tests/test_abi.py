@@ -59,7 +59,7 @@ def test_ctypes_prototypes_match_header():
 
 def test_argument_errors_are_reported_without_a_gpu():
     lib = _lib.load()
-    rc = lib.cgvae_gemm(7, None, 0, None, 0, None, 0, 1, 1, 1, None, 0, None, None, 0, None, None, 0, None)
+    rc = lib.cgvae_gemm(7, None, 0, None, 0, None, 0, 1, 1, 1, None, 0, None, None, 0, None, None, 0, None, 0, None)
     assert rc < 0 and "bad form" in _lib.last_error()
     rc = lib.cgvae_message_fwd(5, None, None, None, None, None, None, None, None, None, 1, 1, 8, 4, 8, None, None, 0,
                                None, None, None, None)
