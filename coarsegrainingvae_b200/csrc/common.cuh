@@ -49,8 +49,8 @@ inline int launched(const char* what) {
 // not the work, dominates.  Every kernel of this library starts with pdl_wait() (griddepcontrol.wait: blocks until the
 // preceding grid has completed and flushed its writes -- all global-memory accesses come after it, so ordering is exactly
 // that of a plain stream) and pdl_trigger() (griddepcontrol.launch_dependents: lets the NEXT kernel's launch and prologue
-// overlap with this kernel's execution).  Launches carry cudaLaunchAttributeProgrammaticStreamSerialization; set
-// CGVAE_PDL=0 to fall back to fully serialised launches.
+// overlap with this kernel's execution).  Launches carry cudaLaunchAttributeProgrammaticStreamSerialization when
+// CGVAE_PDL=1 (opt-in: it did not pay on B200 for this workload, see graph.cu::pdl_enabled).
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 #define CGVAE_KERNEL_PROLOGUE() \

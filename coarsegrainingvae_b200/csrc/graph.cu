@@ -10,8 +10,10 @@ std::atomic<unsigned long long> g_launches{0};
 
 bool pdl_enabled() {
   static const bool on = [] {
+    // opt-in: measured on B200 inside the captured step, dependent-node gaps are already ~0.35 us (median) and PDL
+    // changed the step time by < 1 %, while it inflates per-kernel durations in profiles
     const char* e = getenv("CGVAE_PDL");
-    return !(e && e[0] == '0');
+    return e && e[0] == '1';
   }();
   return on;
 }
