@@ -360,6 +360,12 @@ static int launch_gemm(int form, const float* A, int64_t lda, const float* B, in
 
 }  // namespace cgvae
 
+namespace cgvae {
+int launch_gemm_tcgen05(int form, const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t M,
+                        int64_t N, int64_t K, const float* bias, int act, float* z_out, const float* z_in, int dact,
+                        const float* add, cudaStream_t st);
+}
+
 using namespace cgvae;
 
 extern "C" {
@@ -374,6 +380,9 @@ int cgvae_gemm(int form, const float* A, int64_t lda, const float* B, int64_t ld
   CGVAE_REQUIRE(ldc >= N, "gemm: ldc < N");
   Epilogue ep{bias, act, z_out, z_in, dact, add};
   cudaStream_t st = (cudaStream_t)stream;
+  // large node GEMMs: 3xTF32 on the tcgen05 tensor cores (gemm_tc.cu); everything else: fp32 SIMT tiles below
+  if (launch_gemm_tcgen05(form, A, lda, B, ldb, C, ldc, M, N, K, bias, act, z_out, z_in, dact, add, st))
+    return launched("gemm_tcgen05");
   float* wsf = reinterpret_cast<float*>(ws);
   // skinny problems (decoder graphs: 12..96 rows) stream the weight matrix: deep k-tiles keep 8-16 KB per CTA in flight
   if (M <= 16) return launch_gemm<16, 32, 64, 1, 2>(form, A, lda, B, ldb, C, ldc, M, N, K, ep, wsf, ws_bytes, counters, n_counters, st);

@@ -139,7 +139,8 @@ def test_edge_geometry_vs_oracle():
 
 
 @pytest.mark.parametrize("M,N,K", [(12, 600, 600), (12, 5400, 600), (36, 600, 600), (350, 1800, 600), (97, 130, 77),
-                                    (12, 600, 5400), (1000, 64, 20000), (5, 7, 3)])
+                                    (12, 600, 5400), (1000, 64, 20000), (5, 7, 3),
+                                    (4000, 2048, 512), (2500, 600, 1200)])   # large: tcgen05 3xTF32 path (gemm_tc.cu)
 def test_gemm_forms_and_epilogues(M, N, K):
     g = torch.Generator().manual_seed(M * 7 + N)
     A = torch.randn(M, K, generator=g)
@@ -150,8 +151,11 @@ def test_gemm_forms_and_epilogues(M, N, K):
     y, zpre = ops.gemm(ops.GEMM_NT, _dev(A), _dev(W), M, N, K, bias=_dev(b), act=1, z_out=True)
     assert rel_err(zpre, ref) < GEMM_TOL
     assert rel_err(y, ref * torch.sigmoid(ref)) < GEMM_TOL
+    # activation epilogues: the error budget is set by the pre-activation scale (|z| up to ~5 here), while tanh / relu
+    # outputs are O(1): allow GEMM_TOL * max|z| / max|act(z)|
     for act, f in ((2, torch.relu), (3, torch.tanh)):
-        assert rel_err(ops.gemm(ops.GEMM_NT, _dev(A), _dev(W), M, N, K, bias=_dev(b), act=act), f(ref)) < GEMM_TOL
+        tol = GEMM_TOL * max(1.0, float(ref.abs().max() / f(ref).abs().max()))
+        assert rel_err(ops.gemm(ops.GEMM_NT, _dev(A), _dev(W), M, N, K, bias=_dev(b), act=act), f(ref)) < tol
     gy = torch.randn(M, N, generator=g)
     zin = torch.randn(M, K, generator=g)
     sig = torch.sigmoid(zin.double())
