@@ -1,0 +1,113 @@
+// Fused gradient clipping + Adam on flat buffers: torch.nn.utils.clip_grad_norm_(params, max_norm) followed by
+// torch.optim.Adam.step() (scripts/utils.py:151-157 of the reference) in two launches over one contiguous parameter /
+// gradient / moment layout -- one read of the gradient for the norm, one streaming pass for the update.
+#include "common.cuh"
+
+namespace cgvae {
+
+constexpr int kNormBlocks = 1024;
+
+// partial[b] = sum of squares of a fixed, contiguous slice; also advances the step counter (block 0)
+__global__ void __launch_bounds__(256) sumsq_partial_kernel(const float* __restrict__ g, int64_t n, float* __restrict__ partial,
+                                                            float* __restrict__ step) {
+  CGVAE_KERNEL_PROLOGUE();
+  __shared__ float red[8];
+  const int64_t per = (n + kNormBlocks - 1) / kNormBlocks;
+  const int64_t beg = (int64_t)blockIdx.x * per, end = min(n, beg + per);
+  float s = 0.f;
+  for (int64_t i = beg + threadIdx.x; i < end; i += 256) {
+    const float x = g[i];
+    s = fmaf(x, x, s);
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w];
+    partial[blockIdx.x] = t;
+    if (blockIdx.x == 0) step[0] += 1.0f;
+  }
+}
+
+__global__ void __launch_bounds__(256) adam_clip_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                        float* __restrict__ v, int64_t n, const float* __restrict__ partial,
+                                                        float max_norm, float lr, float beta1, float beta2, float eps,
+                                                        const float* __restrict__ step, float* __restrict__ norm_out) {
+  CGVAE_KERNEL_PROLOGUE();
+  // every block re-reduces the 1024 partial sums in the same fixed order: identical clip coefficient everywhere
+  __shared__ float red[8];
+  __shared__ float coef_sh;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < kNormBlocks; i += 256) s += partial[i];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w];
+    const float norm = sqrtf(t);
+    coef_sh = fminf(max_norm / (norm + 1e-6f), 1.0f);        // clip_grad_norm_: coef = max_norm / (norm + 1e-6), clamped to 1
+    if (blockIdx.x == 0 && norm_out) norm_out[0] = norm;
+  }
+  __syncthreads();
+  const float coef = coef_sh;
+  const float t = step[0];
+  const float bc1 = 1.0f - powf(beta1, t), bc2 = 1.0f - powf(beta2, t);
+  const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+    if (i + 3 < n) {
+      float4 gp = *reinterpret_cast<const float4*>(g + i);
+      float4 mp = *reinterpret_cast<const float4*>(m + i);
+      float4 vp = *reinterpret_cast<const float4*>(v + i);
+      float4 pp = *reinterpret_cast<const float4*>(p + i);
+      float* ga = &gp.x; float* ma = &mp.x; float* va = &vp.x; float* pa = &pp.x;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float gg = ga[k] * coef;
+        ma[k] = beta1 * ma[k] + (1.0f - beta1) * gg;
+        va[k] = beta2 * va[k] + (1.0f - beta2) * gg * gg;
+        pa[k] -= step_size * ma[k] / (sqrtf(va[k]) * inv_sqrt_bc2 + eps);
+      }
+      *reinterpret_cast<float4*>(m + i) = mp;
+      *reinterpret_cast<float4*>(v + i) = vp;
+      *reinterpret_cast<float4*>(p + i) = pp;
+    } else {
+      for (int64_t j = i; j < n; ++j) {
+        const float gg = g[j] * coef;
+        const float mm = beta1 * m[j] + (1.0f - beta1) * gg;
+        const float vv = beta2 * v[j] + (1.0f - beta2) * gg * gg;
+        m[j] = mm; v[j] = vv;
+        p[j] -= step_size * mm / (sqrtf(vv) * inv_sqrt_bc2 + eps);
+      }
+    }
+  }
+}
+
+}  // namespace cgvae
+
+using namespace cgvae;
+
+extern "C" {
+
+size_t cgvae_adam_ws_bytes(void) { return sizeof(float) * kNormBlocks; }
+
+int cgvae_adam_clip_step(float* p, const float* g, float* m, float* v, int64_t n, float max_norm, float lr, float beta1, float beta2,
+                         float eps, float* step, float* norm_out, void* ws, size_t ws_bytes, cgvae_stream_t stream) {
+  if (n == 0) return 0;
+  CGVAE_REQUIRE(p && g && m && v && step && ws && ws_bytes >= cgvae_adam_ws_bytes(), "adam_clip_step: bad arguments");
+  CGVAE_REQUIRE(aligned16(p) && aligned16(g) && aligned16(m) && aligned16(v), "adam_clip_step: buffers must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* partial = reinterpret_cast<float*>(ws);
+  launch_kernel(sumsq_partial_kernel, dim3(kNormBlocks), dim3(256), 0, st, g, n, partial, step);
+  if (int rc = launched("sumsq_partial")) return rc;
+  const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(n, 256 * 4), 148 * 8);
+  launch_kernel(adam_clip_kernel, dim3(blocks), dim3(256), 0, st, p, g, m, v, n, (const float*)partial, max_norm, lr, beta1, beta2, eps,
+                (const float*)step, norm_out);
+  return launched("adam_clip");
+}
+
+}  // extern "C"

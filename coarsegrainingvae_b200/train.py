@@ -119,13 +119,18 @@ class TrainStep(object):
     """one optimisation step of scripts/utils.py::loop (train=True branch): forward, loss, backward, [all-reduce],
     clip_grad_norm_(0.01), Adam."""
 
-    def __init__(self, model, beta, gamma, lr=1e-4, max_norm=0.01, group=None, capturable=False):
+    def __init__(self, model, beta, gamma, lr=1e-4, max_norm=0.01, group=None, capturable=False, optimizer="fused"):
+        """optimizer: "fused" = cgvae_adam_clip_step on flat parameter / gradient / moment buffers (CUDA only; the used
+        parameters are re-pointed at views of one contiguous buffer), "torch" = clip on the flat gradients +
+        torch.optim.Adam (always used for CPU tensors)."""
         self.model, self.beta, self.gamma = model, beta, gamma
         self.max_norm, self.group = max_norm, group
         self.lr = lr
         self.capturable = capturable
+        self.optimizer = optimizer
         self.flat = None
         self.opt = None
+        self.flat_p = self.exp_avg = self.exp_avg_sq = self.step_count = None
 
     def _loss(self, batch, eps):
         out = self.model(batch, eps=eps) if eps is not None else self.model(batch)
@@ -135,9 +140,26 @@ class TrainStep(object):
     def prepare(self, batch, eps=None):
         """discover the used parameters with one dry backward and lay their gradients out in one flat buffer."""
         used = used_parameters(self.model, lambda: self._loss(batch, eps).backward())
-        self.flat = FlatGrads([p for _, p in used])
+        params = [p for _, p in used]
+        on_cuda = bool(params) and params[0].is_cuda
+        if on_cuda and self.optimizer == "fused":
+            # parameters of the used set become views of ONE buffer (same order as the gradient buffer): the optimiser
+            # is then a single streaming pass.  Must happen before FlatGrads registers the sinks (keyed by data_ptr).
+            n = sum(p.numel() for p in params)
+            self.flat_p = torch.empty(n, dtype=torch.float32, device=params[0].device)
+            off = 0
+            for p in params:
+                view = self.flat_p[off:off + p.numel()].view_as(p)
+                view.copy_(p.data)
+                p.data = view
+                off += p.numel()
+            self.exp_avg = torch.zeros_like(self.flat_p)
+            self.exp_avg_sq = torch.zeros_like(self.flat_p)
+            self.step_count = torch.zeros(1, dtype=torch.float32, device=params[0].device)
+        self.flat = FlatGrads(params)
         fused = self.flat.flat.is_cuda
-        self.opt = torch.optim.Adam(self.flat.params, lr=self.lr, fused=fused, capturable=bool(self.capturable and fused))
+        if self.flat_p is None:
+            self.opt = torch.optim.Adam(self.flat.params, lr=self.lr, fused=fused, capturable=bool(self.capturable and fused))
         if self.flat.sink:                 # verify once that autograd adopts the sink views (else fall back to copies)
             self.forward_backward(batch, eps)
             if not self.flat.check_adopted():
@@ -151,8 +173,12 @@ class TrainStep(object):
         return loss
 
     def apply_gradients(self):
-        self.flat.clip_(self.max_norm)
-        self.opt.step()
+        if self.flat_p is not None:
+            from . import ops
+            ops.adam_clip_step(self.flat_p, self.flat.flat, self.exp_avg, self.exp_avg_sq, self.step_count, self.max_norm, self.lr)
+        else:
+            self.flat.clip_(self.max_norm)
+            self.opt.step()
 
     def step(self, batch, eps=None):
         loss = self.forward_backward(batch, eps)

@@ -345,11 +345,35 @@ def test_train_step_gradient_sink_matches_plain_autograd():
     for k, p in model.named_parameters():
         if k in plain:
             assert torch.equal(p.grad, plain[k]), k
-    before = step.flat.flat.clone()
     loss = step.step(batch, eps)
-    assert torch.isfinite(loss) and not torch.equal(before, step.flat.flat)   # clipped in place
+    assert torch.isfinite(loss)
     step.flat.release()
     assert not ops.GRAD_SINK
+
+
+def test_fused_clip_adam_matches_torch():
+    """cgvae_adam_clip_step == torch.nn.utils.clip_grad_norm_ + torch.optim.Adam over several steps (same gradients)."""
+    g = torch.Generator().manual_seed(3)
+    shapes = [(600, 600), (600,), (1800, 10), (5, 7), (3,)]
+    params_a = [torch.randn(*s, generator=g).to(DEV).requires_grad_() for s in shapes]
+    n = sum(p.numel() for p in params_a)
+    flat_p = torch.cat([p.detach().reshape(-1) for p in params_a]).clone()
+    m, v = torch.zeros_like(flat_p), torch.zeros_like(flat_p)
+    step = torch.zeros(1, device=DEV)
+    norm_out = torch.zeros(1, device=DEV)
+    opt = torch.optim.Adam(params_a, lr=1e-3)
+    for it in range(4):
+        grads = [torch.randn(*s, generator=g).to(DEV) * (10.0 if it % 2 else 1e-3) for s in shapes]   # clipped / not clipped
+        for p, gr in zip(params_a, grads):
+            p.grad = gr.clone()
+        flat_g = torch.cat([gr.reshape(-1) for gr in grads])
+        want_norm = torch.nn.utils.clip_grad_norm_(params_a, 0.01 if it % 2 else 1e3)
+        opt.step()
+        ops.adam_clip_step(flat_p, flat_g, m, v, step, 0.01 if it % 2 else 1e3, 1e-3, norm_out=norm_out)
+        assert rel_err(norm_out, want_norm.reshape(1)) < 1e-6
+        want = torch.cat([p.detach().reshape(-1) for p in params_a])
+        assert rel_err(flat_p, want) < 1e-6, it
+    assert float(step) == 4.0 and n == flat_p.numel()
 
 
 def test_graphed_train_step_matches_eager():
