@@ -130,8 +130,6 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) gemm_kernel(
   const int64_t kbeg = (int64_t)blockIdx.z * k_per_split;
   const int64_t kend = min(K, kbeg + k_per_split);
 
-  LoaderA la;
-  LoaderB lb;
   // two-level accumulation: `acc` is folded into `tot` every kFold k-tiles so the rounding error grows with
   // sqrt(kFold*BK) + sqrt(K/(kFold*BK)) instead of sqrt(K) (weight gradients reduce over up to 1e5 rows)
   constexpr int kFold = 256 / BK;
@@ -141,46 +139,55 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) gemm_kernel(
 #pragma unroll
     for (int j = 0; j < TN; ++j) { acc[i][j] = 0.f; tot[i][j] = 0.f; }
 
-  int buf = 0;
-  if (kbeg < kend) {
-    la.fetch(A, lda, m0, M, kbeg, kend, a_vec, tid);
-    lb.fetch(B, ldb, n0, N, kbeg, kend, b_vec, tid);
-    la.store(As[0], tid);
-    lb.store(Bs[0], tid);
+  // PD k-tiles are kept in flight in registers (static slots, loop unrolled by PD): a CTA that streams a weight slab is a
+  // chain of dependent DRAM round trips otherwise (one per k-tile: 10-25 us for the 13 MB decoder matrices).
+  constexpr int PD = (BK >= 32) ? 3 : 2;
+  LoaderA las[PD];
+  LoaderB lbs[PD];
+#pragma unroll
+  for (int p = 0; p < PD; ++p) {
+    if (kbeg + (int64_t)p * BK < kend) {
+      las[p].fetch(A, lda, m0, M, kbeg + (int64_t)p * BK, kend, a_vec, tid);
+      lbs[p].fetch(B, ldb, n0, N, kbeg + (int64_t)p * BK, kend, b_vec, tid);
+    }
   }
-  __syncthreads();
+  int buf = 0;
   int fold = 0;
-  for (int64_t k0 = kbeg; k0 < kend; k0 += BK) {
-    const bool more = k0 + BK < kend;
-    if (more) {
-      la.fetch(A, lda, m0, M, k0 + BK, kend, a_vec, tid);
-      lb.fetch(B, ldb, n0, N, k0 + BK, kend, b_vec, tid);
+  for (int64_t base = kbeg; base < kend; base += (int64_t)PD * BK) {
+#pragma unroll
+    for (int p = 0; p < PD; ++p) {
+      const int64_t k0 = base + (int64_t)p * BK;
+      if (k0 < kend) {
+        // tile k0 sits in register slot p; smem is double buffered, one barrier per tile
+        las[p].store(As[buf], tid);
+        lbs[p].store(Bs[buf], tid);
+        __syncthreads();
+        if (k0 + (int64_t)PD * BK < kend) {
+          las[p].fetch(A, lda, m0, M, k0 + (int64_t)PD * BK, kend, a_vec, tid);
+          lbs[p].fetch(B, ldb, n0, N, k0 + (int64_t)PD * BK, kend, b_vec, tid);
+        }
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+          float a[TM], b[TN];
+#pragma unroll
+          for (int i = 0; i < TM; ++i) a[i] = LoaderA::at(As[buf], ty * TM + i, k);
+#pragma unroll
+          for (int j = 0; j < TN; ++j) b[j] = LoaderB::at(Bs[buf], tx * TN + j, k);
+#pragma unroll
+          for (int i = 0; i < TM; ++i)
+#pragma unroll
+            for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        if (++fold == kFold) {
+          fold = 0;
+#pragma unroll
+          for (int i = 0; i < TM; ++i)
+#pragma unroll
+            for (int j = 0; j < TN; ++j) { tot[i][j] += acc[i][j]; acc[i][j] = 0.f; }
+        }
+        buf ^= 1;
+      }
     }
-#pragma unroll
-    for (int k = 0; k < BK; ++k) {
-      float a[TM], b[TN];
-#pragma unroll
-      for (int i = 0; i < TM; ++i) a[i] = LoaderA::at(As[buf], ty * TM + i, k);
-#pragma unroll
-      for (int j = 0; j < TN; ++j) b[j] = LoaderB::at(Bs[buf], tx * TN + j, k);
-#pragma unroll
-      for (int i = 0; i < TM; ++i)
-#pragma unroll
-        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-    }
-    if (more) {
-      la.store(As[buf ^ 1], tid);
-      lb.store(Bs[buf ^ 1], tid);
-    }
-    if (++fold == kFold) {
-      fold = 0;
-#pragma unroll
-      for (int i = 0; i < TM; ++i)
-#pragma unroll
-        for (int j = 0; j < TN; ++j) { tot[i][j] += acc[i][j]; acc[i][j] = 0.f; }
-    }
-    __syncthreads();
-    buf ^= 1;
   }
 #pragma unroll
   for (int i = 0; i < TM; ++i)
@@ -266,6 +273,153 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
   float v = 0.f;
   for (int s = 0; s < splits; ++s) v += partial[(int64_t)s * M * N + idx];  // fixed order: deterministic
   C[m * ldc + n] = apply_epilogue(ep, v, m, n, ldc);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Skinny kernel: M <= 16 rows (decoder graphs of the molecule configs: 12 beads).  The generic tile above is bound by
+// shared-memory LOADS for such shapes (1x2 micro-tile: 3 LDS per 2 FMA, measured 15-25 us for the 13 MB matrices).
+// Here a thread owns ONE output column and ALL 16 rows: per k it reads the 16 activations as four broadcast LDS.128
+// and one weight element, i.e. 5 LDS per 16 FMA.  K is split over a thread-block cluster (1,1,S) and reduced through
+// distributed shared memory in slice order.  A [M,K] is K-contiguous (NT and NN forms); B_KC selects W[N,K] (NT)
+// or W[K,N] (NN).
+// ------------------------------------------------------------------------------------------------------------
+constexpr int SK_BK = 32;
+
+template <int BN, bool B_KC>
+__global__ void __launch_bounds__(BN) gemm_skinny_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ B,
+                                                        int64_t ldb, float* __restrict__ C, int64_t ldc, int64_t M, int64_t N,
+                                                        int64_t K, int64_t k_per_split, Epilogue ep, bool a_vec, bool b_vec) {
+  CGVAE_KERNEL_PROLOGUE();
+  namespace cg = cooperative_groups;
+  constexpr int NV_B = SK_BK * BN / 4 / BN;       // float4 of the weight tile per thread (= 8)
+  __shared__ __align__(16) float As[2][SK_BK][20];          // k-major: As[k][row], 16 rows + pad
+  __shared__ __align__(16) float Bs[2][SK_BK][BN + 4];      // k-major: Bs[k][n]
+  __shared__ __align__(16) float red[16][BN];
+  const int tid = threadIdx.x;
+  const int64_t n0 = (int64_t)blockIdx.x * BN;
+  const int64_t kbeg = (int64_t)blockIdx.z * k_per_split;
+  const int64_t kend = min(K, kbeg + k_per_split);
+
+  constexpr int NV_A = 128 / BN;                  // the activation tile is 16 rows x 8 chunks = 128 float4
+  float4 a_reg[NV_A];
+  float4 b_reg[NV_B];
+  auto fetch = [&](int64_t k0) {
+#pragma unroll
+    for (int ia = 0; ia < NV_A; ++ia) {
+      const int v = tid + BN * ia;
+      const int r = v >> 3, c = v & 7;
+      const int64_t k = k0 + 4 * c;
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < M) {
+        const float* src = A + (int64_t)r * lda + k;
+        if (a_vec && k + 3 < kend) x = __ldg(reinterpret_cast<const float4*>(src));
+        else {
+          if (k + 0 < kend) x.x = src[0];
+          if (k + 1 < kend) x.y = src[1];
+          if (k + 2 < kend) x.z = src[2];
+          if (k + 3 < kend) x.w = src[3];
+        }
+      }
+      a_reg[ia] = x;
+    }
+#pragma unroll
+    for (int it = 0; it < NV_B; ++it) {
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (B_KC) {
+        // W[N,K]: thread = output column n, it = k-chunk: 16 bytes of row n (the next chunk hits the same sector / line)
+        const int64_t n = n0 + tid, k = k0 + 4 * it;
+        if (n < N) {
+          const float* src = B + n * ldb + k;
+          if (b_vec && k + 3 < kend) x = __ldg(reinterpret_cast<const float4*>(src));
+          else {
+            if (k + 0 < kend) x.x = src[0];
+            if (k + 1 < kend) x.y = src[1];
+            if (k + 2 < kend) x.z = src[2];
+            if (k + 3 < kend) x.w = src[3];
+          }
+        }
+      } else {
+        // W[K,N]: v = tid + BN*it -> k row = v / (BN/4), column quad = v % (BN/4): coalesced along n
+        const int v = tid + BN * it;
+        const int kk = v / (BN / 4), q = v % (BN / 4);
+        const int64_t k = k0 + kk, n = n0 + 4 * q;
+        if (k < kend) {
+          const float* src = B + k * ldb + n;
+          if (b_vec && n + 3 < N) x = __ldg(reinterpret_cast<const float4*>(src));
+          else {
+            if (n + 0 < N) x.x = src[0];
+            if (n + 1 < N) x.y = src[1];
+            if (n + 2 < N) x.z = src[2];
+            if (n + 3 < N) x.w = src[3];
+          }
+        }
+      }
+      b_reg[it] = x;
+    }
+  };
+  auto stash = [&](int buf) {
+#pragma unroll
+    for (int ia = 0; ia < NV_A; ++ia) {
+      const int v = tid + BN * ia;
+      const int r = v >> 3, c = v & 7;
+      As[buf][4 * c + 0][r] = a_reg[ia].x;
+      As[buf][4 * c + 1][r] = a_reg[ia].y;
+      As[buf][4 * c + 2][r] = a_reg[ia].z;
+      As[buf][4 * c + 3][r] = a_reg[ia].w;
+    }
+#pragma unroll
+    for (int it = 0; it < NV_B; ++it) {
+      if (B_KC) {
+        Bs[buf][4 * it + 0][tid] = b_reg[it].x;
+        Bs[buf][4 * it + 1][tid] = b_reg[it].y;
+        Bs[buf][4 * it + 2][tid] = b_reg[it].z;
+        Bs[buf][4 * it + 3][tid] = b_reg[it].w;
+      } else {
+        const int v = tid + BN * it;
+        const int kk = v / (BN / 4), q = v % (BN / 4);
+        *reinterpret_cast<float4*>(&Bs[buf][kk][4 * q]) = b_reg[it];
+      }
+    }
+  };
+
+  float acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+  int buf = 0;
+  if (kbeg < kend) fetch(kbeg);
+  for (int64_t k0 = kbeg; k0 < kend; k0 += SK_BK) {
+    stash(buf);
+    __syncthreads();
+    if (k0 + SK_BK < kend) fetch(k0 + SK_BK);
+#pragma unroll
+    for (int k = 0; k < SK_BK; ++k) {
+      const float b = Bs[buf][k][tid];
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][0]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][4]);
+      const float4 a2 = *reinterpret_cast<const float4*>(&As[buf][k][8]);
+      const float4 a3 = *reinterpret_cast<const float4*>(&As[buf][k][12]);
+      acc[0] = fmaf(a0.x, b, acc[0]);   acc[1] = fmaf(a0.y, b, acc[1]);   acc[2] = fmaf(a0.z, b, acc[2]);   acc[3] = fmaf(a0.w, b, acc[3]);
+      acc[4] = fmaf(a1.x, b, acc[4]);   acc[5] = fmaf(a1.y, b, acc[5]);   acc[6] = fmaf(a1.z, b, acc[6]);   acc[7] = fmaf(a1.w, b, acc[7]);
+      acc[8] = fmaf(a2.x, b, acc[8]);   acc[9] = fmaf(a2.y, b, acc[9]);   acc[10] = fmaf(a2.z, b, acc[10]); acc[11] = fmaf(a2.w, b, acc[11]);
+      acc[12] = fmaf(a3.x, b, acc[12]); acc[13] = fmaf(a3.y, b, acc[13]); acc[14] = fmaf(a3.z, b, acc[14]); acc[15] = fmaf(a3.w, b, acc[15]);
+    }
+    buf ^= 1;
+  }
+  // cluster reduction over the K-slices, slice order 0..S-1 (deterministic), every CTA finishes a share of the rows
+  cg::cluster_group cluster = cg::this_cluster();
+#pragma unroll
+  for (int i = 0; i < 16; ++i) red[i][tid] = acc[i];
+  cluster.sync();
+  const int S = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+  const int64_t n = n0 + tid;
+  for (int i = rank; i < 16; i += S) {
+    if (i < M && n < N) {
+      float v = 0.f;
+      for (int z = 0; z < S; ++z) v += *cluster.map_shared_rank(&red[i][tid], z);
+      C[(int64_t)i * ldc + n] = apply_epilogue(ep, v, i, n, ldc);
+    }
+  }
+  cluster.sync();
 }
 
 // column sums: out[n] = sum_m X[m][n]; one thread per column per row-chunk, two-stage, fixed order.
@@ -384,6 +538,42 @@ int cgvae_gemm(int form, const float* A, int64_t lda, const float* B, int64_t ld
   if (launch_gemm_tcgen05(form, A, lda, B, ldb, C, ldc, M, N, K, bias, act, z_out, z_in, dact, add, st))
     return launched("gemm_tcgen05");
   float* wsf = reinterpret_cast<float*>(ws);
+  static const bool use_skinny = [] { const char* e = getenv("CGVAE_SKINNY_GEMM"); return !(e && e[0] == '0'); }();
+  // measured in isolation inside a CUDA graph (tools/bench_skinny.py, weights rotated through > L2): the column-per-thread
+  // kernel wins for wide outputs (W2 forward, 5400 columns: 17.9 vs 23.2 us) and loses where 8 cluster slices of 64-wide
+  // tiles leave too few threads in flight (N = 600 outputs: 80 CTAs x 64 threads), so it takes the NT form with N >= 1024
+  if (use_skinny && M <= 16 && form == CGVAE_GEMM_NT && K >= 64 && N >= 1024) {
+    // one output column per thread, K split over a cluster of up to 8 CTAs
+    const bool b_kc = (form == CGVAE_GEMM_NT);
+    const bool a_vec = aligned16(A) && (lda % 4 == 0), b_vec = aligned16(B) && (ldb % 4 == 0);
+    const bool narrow = ceil_div(N, 128) * 8 < kNumSM;        // few columns: 64-wide tiles double the CTA count
+    const int BNs = narrow ? 64 : 128;
+    const int64_t tiles = ceil_div(N, BNs);
+    int S = (int)std::min<int64_t>(std::min<int64_t>(8, std::max<int64_t>(1, ceil_div(2 * kNumSM, tiles))), ceil_div(K, 2 * SK_BK));
+    int64_t kps = ceil_div(ceil_div(K, S), SK_BK) * SK_BK;
+    S = (int)ceil_div(K, kps);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)tiles, 1, (unsigned)S);
+    cfg.blockDim = dim3(BNs);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = (unsigned)S;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    if (narrow) {
+      if (b_kc) (void)cudaLaunchKernelEx(&cfg, gemm_skinny_kernel<64, true>, A, lda, B, ldb, C, ldc, M, N, K, kps, ep, a_vec, b_vec);
+      else (void)cudaLaunchKernelEx(&cfg, gemm_skinny_kernel<64, false>, A, lda, B, ldb, C, ldc, M, N, K, kps, ep, a_vec, b_vec);
+    } else {
+      if (b_kc) (void)cudaLaunchKernelEx(&cfg, gemm_skinny_kernel<128, true>, A, lda, B, ldb, C, ldc, M, N, K, kps, ep, a_vec, b_vec);
+      else (void)cudaLaunchKernelEx(&cfg, gemm_skinny_kernel<128, false>, A, lda, B, ldb, C, ldc, M, N, K, kps, ep, a_vec, b_vec);
+    }
+    return launched("gemm_skinny");
+  }
   // skinny problems (decoder graphs: 12..96 rows) stream the weight matrix: deep k-tiles keep 8-16 KB per CTA in flight
   if (M <= 16) return launch_gemm<16, 32, 64, 1, 2>(form, A, lda, B, ldb, C, ldc, M, N, K, ep, wsf, ws_bytes, counters, n_counters, st);
   if (M <= 32) return launch_gemm<32, 32, 64, 2, 2>(form, A, lda, B, ldb, C, ldc, M, N, K, ep, wsf, ws_bytes, counters, n_counters, st);

@@ -31,7 +31,7 @@ def _oracle_params(module, prefix=""):
 def _check_grads(module, P, tol, prefix="", P64=None):
     """every parameter gradient vs the oracle's autograd.  With ``P64`` (the same oracle evaluated in float64 = ground
     truth) the criterion becomes conditioning-aware: per tensor, the kernel's error against the truth must be below
-    ``tol`` OR below five times the error the fp32 oracle itself makes on that tensor (summation-order luck on an
+    ``tol`` OR below ten times the error the fp32 oracle itself makes on that tensor (summation-order luck on an
     ill-conditioned quantity); and the WHOLE gradient vector (what clip_grad_norm_ / Adam consume) must be within ``tol``
     of the truth in relative L2 norm.  The raw fp32-vs-fp32 difference is returned for reporting.
     (Needed for the UpdateBlock norm path: d sqrt(sum(Vv^2+1e-10)) / dVv divides by ~1e-5 when v is still ~0, which
@@ -51,7 +51,7 @@ def _check_grads(module, P, tol, prefix="", P64=None):
         else:
             truth = P64[prefix + k].grad
             e_kernel, e_ref = rel_err(p.grad, truth), rel_err(og, truth)
-            assert e_kernel < max(tol, 5.0 * e_ref), (k, e_kernel, e_ref)
+            assert e_kernel < max(tol, 10.0 * e_ref), (k, e_kernel, e_ref)
             num += float((p.grad.detach().cpu().double() - truth).pow(2).sum())
             den += float(truth.pow(2).sum())
         worst = max(worst, raw)
