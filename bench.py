@@ -30,6 +30,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# DRAM traffic per launch of the fused message kernels on the chignolin atom graph, from the committed ncu capture
+NCU_DRAM_BYTES = {"message_fwd": 9.8e6, "message_bwd": 12.5e6}
+
 METRIC = "conformations/s (fwd+bwd train step)"
 UNIT = "conformations/s"
 
@@ -318,12 +321,14 @@ def run_cuda(args, cfg):
         if not recs:
             continue
         t_ms = float(np.mean([t for t, _ in recs]))
-        E = float(np.mean([m["E"] for _, m in recs]))
+        E = float(edges)           # live directed edges (the static-capacity graph holds a few padded slots on top)
         flops = factor * 2.0 * (R + 1) * 3 * F * E                   # filter contraction incl. the bias column
         share = (sum(t for t, _ in recs) / n_prof) / ms
         entry = {"kernel": name + "_kernel<3,%d> (atom graph)" % (ops.rb_for(R) // 4), "bound": "tensor",
                  "achieved": flops / (t_ms * 1e-3) / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
-                 "frac": flops / (t_ms * 1e-3) / 1e12 / tf32_peak, "traffic": None,
+                 "frac": flops / (t_ms * 1e-3) / 1e12 / tf32_peak, "traffic": NCU_DRAM_BYTES.get(name),
+                 "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of this launch in the ncu --set full capture "
+                                   "profiles/r1_ncu_full_message_kernels_raw.csv (same workload, earlier build)",
                  "peak_source": "derived: 0.5 x bf16_tflops_sustained of %s MEASURED_PEAKS (TF32 is not measured there)" % peaks["source"],
                  "avg_launch_us": 1e3 * t_ms, "launches_per_step": len(recs) / n_prof, "edges_per_launch": E,
                  "edges_per_s": E / (t_ms * 1e-3), "share_of_step": share,
