@@ -518,6 +518,9 @@ namespace cgvae {
 int launch_gemm_tcgen05(int form, const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t M,
                         int64_t N, int64_t K, const float* bias, int act, float* z_out, const float* z_in, int dact,
                         const float* add, cudaStream_t st);
+int launch_gemm_stream(int form, const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t M,
+                       int64_t N, int64_t K, const float* bias, int act, float* z_out, const float* z_in, int dact,
+                       const float* add, cudaStream_t st);
 }
 
 using namespace cgvae;
@@ -537,6 +540,9 @@ int cgvae_gemm(int form, const float* A, int64_t lda, const float* B, int64_t ld
   // large node GEMMs: 3xTF32 on the tcgen05 tensor cores (gemm_tc.cu); everything else: fp32 SIMT tiles below
   if (launch_gemm_tcgen05(form, A, lda, B, ldb, C, ldc, M, N, K, bias, act, z_out, z_in, dact, add, st))
     return launched("gemm_tcgen05");
+  // M <= 48 rows (decoder graphs): weight-streaming kernels (gemm_stream.cu)
+  if (launch_gemm_stream(form, A, lda, B, ldb, C, ldc, M, N, K, bias, act, z_out, z_in, dact, add, st))
+    return launched("gemm_stream");
   float* wsf = reinterpret_cast<float*>(ws);
   static const bool use_skinny = [] { const char* e = getenv("CGVAE_SKINNY_GEMM"); return !(e && e[0] == '0'); }();
   // measured in isolation inside a CUDA graph (tools/bench_skinny.py, weights rotated through > L2): the column-per-thread

@@ -330,13 +330,18 @@ __device__ __forceinline__ void stage_filter9(float (*Wsm)[kMaxRB9][32], const f
   }
 }
 
+// RB is a template parameter (RBQ float4 per basis row): the per-edge basis row sits in registers and the 9 x RB filter
+// contraction is fully unrolled.  With a run-time RB the loop was a chain of dependent L1 loads (~50 cycles per term,
+// 108 terms per edge): 23 us per launch on the 12-bead decoder graphs, almost all of it latency.
+template <int RBQ>
 __global__ void __launch_bounds__(kMsgWarps * 32) message9_fwd_kernel(
     const float* __restrict__ phi, const float* __restrict__ s, const float* __restrict__ sbar, const float* __restrict__ v,
     const float* __restrict__ vbar, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
     const float* __restrict__ basis, const float* __restrict__ unit, const float* __restrict__ Wf, const float* __restrict__ bf,
-    int64_t n, int F, int R, int RB, int residual, float* __restrict__ out_s, float* __restrict__ out_sbar,
+    int64_t n, int F, int R, int residual, float* __restrict__ out_s, float* __restrict__ out_sbar,
     float* __restrict__ out_v, float* __restrict__ out_vbar) {
   CGVAE_KERNEL_PROLOGUE();
+  constexpr int RB = 4 * RBQ;
   __shared__ float Wsm[9][kMaxRB9][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   stage_filter9(Wsm, Wf, bf, F, R, RB, blockIdx.y * 32);
@@ -349,22 +354,25 @@ __global__ void __launch_bounds__(kMsgWarps * 32) message9_fwd_kernel(
   load3(v, i, F, f, v_i);
   load3(vbar, i, F, f, vb_i);
   float a_s = 0.f, a_sb = 0.f, a_v[3] = {0.f, 0.f, 0.f}, a_vb[3] = {0.f, 0.f, 0.f};
-#pragma unroll 2
+#pragma unroll 1
   for (int e = rowptr[i]; e < rowptr[i + 1]; ++e) {
     const int j = col[e];
-    const float* b = basis + (int64_t)e * RB;
+    float b[RB];
+    load_basis<RBQ>(basis, e, b);
     const float4 u4 = reinterpret_cast<const float4*>(unit)[e];
     const float u[3] = {u4.x, u4.y, u4.z};
-    float m[9];
+    float m[9], v_j[3], vb_j[3], c1[3], c2[3], c3[3];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) m[k] = __ldg(phi + ((int64_t)j * 9 + k) * F + f);   // all gathers in flight before the math
+    load3(v, j, F, f, v_j);
+    load3(vbar, j, F, f, vb_j);
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
       float w = 0.f;
+#pragma unroll
       for (int r = 0; r < RB; ++r) w = fmaf(b[r], Wsm[k][r][lane], w);
-      m[k] = phi[((int64_t)j * 9 + k) * F + f] * w;
+      m[k] *= w;
     }
-    float v_j[3], vb_j[3], c1[3], c2[3], c3[3];
-    load3(v, j, F, f, v_j);
-    load3(vbar, j, F, f, vb_j);
     cross3(v_i, vb_j, c1);
     cross3(v_i, v_j, c2);
     cross3(vb_i, vb_j, c3);
@@ -386,15 +394,17 @@ __global__ void __launch_bounds__(kMsgWarps * 32) message9_fwd_kernel(
   }
 }
 
+template <int RBQ>
 __global__ void __launch_bounds__(kMsgWarps * 32) message9_bwd_kernel(
     const float* __restrict__ phi, const float* __restrict__ s, const float* __restrict__ sbar, const float* __restrict__ v,
     const float* __restrict__ vbar, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
     const int32_t* __restrict__ rowptr_t, const int32_t* __restrict__ col_t, const int32_t* __restrict__ perm_t,
     const float* __restrict__ basis, const float* __restrict__ unit, const float* __restrict__ Wf, const float* __restrict__ bf,
-    int64_t n, int F, int R, int RB, int residual, const float* __restrict__ g_s, const float* __restrict__ g_sbar,
+    int64_t n, int F, int R, int residual, const float* __restrict__ g_s, const float* __restrict__ g_sbar,
     const float* __restrict__ g_v, const float* __restrict__ g_vbar, float* __restrict__ gi_s, float* __restrict__ gi_sbar,
     float* __restrict__ gi_v, float* __restrict__ gi_vbar, float* __restrict__ g_phi, float* __restrict__ gw) {
   CGVAE_KERNEL_PROLOGUE();
+  constexpr int RB = 4 * RBQ;
   __shared__ float Wsm[9][kMaxRB9][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   stage_filter9(Wsm, Wf, bf, F, R, RB, blockIdx.y * 32);
@@ -420,16 +430,10 @@ __global__ void __launch_bounds__(kMsgWarps * 32) message9_bwd_kernel(
   for (int k = 0; k < 9; ++k) { ph[k] = phi[((int64_t)nd * 9 + k) * F + f]; gph[k] = 0.f; }
   for (int t = rowptr_t[nd]; t < rowptr_t[nd + 1]; ++t) {
     const int i = col_t[t], e = perm_t[t];
-    const float* b = basis + (int64_t)e * RB;
+    float b[RB];
+    load_basis<RBQ>(basis, e, b);
     const float4 u4 = reinterpret_cast<const float4*>(unit)[e];
     const float u[3] = {u4.x, u4.y, u4.z};
-    float w[9];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) {
-      float a = 0.f;
-      for (int r = 0; r < RB; ++r) a = fmaf(b[r], Wsm[k][r][lane], a);
-      w[k] = a;
-    }
     const float s_i = s[(int64_t)i * F + f], sb_i = sbar[(int64_t)i * F + f];
     const float gs_i = g_s[(int64_t)i * F + f], gsb_i = g_sbar[(int64_t)i * F + f];
     float v_i[3], vb_i[3], gv_i[3], gvb_i[3], c1[3], c2[3], c3[3];
@@ -437,6 +441,14 @@ __global__ void __launch_bounds__(kMsgWarps * 32) message9_bwd_kernel(
     load3(vbar, i, F, f, vb_i);
     load3(g_v, i, F, f, gv_i);
     load3(g_vbar, i, F, f, gvb_i);
+    float w[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      float a = 0.f;
+#pragma unroll
+      for (int r = 0; r < RB; ++r) a = fmaf(b[r], Wsm[k][r][lane], a);
+      w[k] = a;
+    }
     cross3(v_i, vb_n, c1);     // v_i x vbar_j
     cross3(v_i, v_n, c2);      // v_i x v_j
     cross3(vb_i, vb_n, c3);    // vbar_i x vbar_j
@@ -474,18 +486,21 @@ __global__ void __launch_bounds__(kMsgWarps * 32) message9_bwd_kernel(
   // ---- node as RECEIVER i = nd: edges (nd <- j)
   for (int e = rowptr[nd]; e < rowptr[nd + 1]; ++e) {
     const int j = col[e];
-    const float* b = basis + (int64_t)e * RB;
-    float m[9];
+    float b[RB];
+    load_basis<RBQ>(basis, e, b);
+    float m[9], v_j[3], vb_j[3], y1[3], y2[3], y3[3];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) {
-      if (k == 1 || k == 2 || k == 5) { m[k] = 0.f; continue; }
-      float a = 0.f;
-      for (int r = 0; r < RB; ++r) a = fmaf(b[r], Wsm[k][r][lane], a);
-      m[k] = a * phi[((int64_t)j * 9 + k) * F + f];
-    }
-    float v_j[3], vb_j[3], y1[3], y2[3], y3[3];
+    for (int k = 0; k < 9; ++k) m[k] = (k == 1 || k == 2 || k == 5) ? 0.f : __ldg(phi + ((int64_t)j * 9 + k) * F + f);
     load3(v, j, F, f, v_j);
     load3(vbar, j, F, f, vb_j);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      if (k == 1 || k == 2 || k == 5) continue;
+      float a = 0.f;
+#pragma unroll
+      for (int r = 0; r < RB; ++r) a = fmaf(b[r], Wsm[k][r][lane], a);
+      m[k] *= a;
+    }
     d_s += gs_n * m[0];
     d_sb += m[4] * dot3(gv_n, vb_j) + m[6] * dot3(gvb_n, v_j);
     cross3(vb_j, gv_n, y1);    // d/dv_i of m3 (v_i x vbar_j)
@@ -606,13 +621,17 @@ int cgvae_message9_fwd(const float* phi, const float* s, const float* sbar, cons
                        const int32_t* rowptr, const int32_t* col, const float* basis, const float* unit, const float* Wf,
                        const float* bf, int64_t n, int F, int R, int RB, int residual, float* out_s, float* out_sbar,
                        float* out_v, float* out_vbar, cgvae_stream_t stream) {
-  CGVAE_REQUIRE(RB <= kMaxRB9 && R + 1 <= RB && RB % 4 == 0, "message9_fwd: bad RB=%d R=%d", RB, R);
+  CGVAE_REQUIRE((RB == 8 || RB == 12 || RB == 16) && R + 1 <= RB, "message9_fwd: bad RB=%d R=%d", RB, R);
   if (n == 0) return 0;
   CGVAE_REQUIRE(phi && s && sbar && v && vbar && rowptr && col && basis && unit && Wf && bf && out_s && out_sbar && out_v && out_vbar,
                 "message9_fwd: null pointer");
   dim3 grid((unsigned)ceil_div(n, kMsgWarps), (unsigned)ceil_div(F, 32));
-  launch_kernel(message9_fwd_kernel, dim3(grid), dim3(kMsgWarps * 32), 0, (cudaStream_t)stream, phi, s, sbar, v, vbar, rowptr, col, basis, unit, Wf, bf, n,
-                                                                         F, R, RB, residual, out_s, out_sbar, out_v, out_vbar);
+  CGVAE_REQUIRE(aligned16(basis) && aligned16(unit), "message9_fwd: edge data must be 16-byte aligned");
+#define LAUNCH_FWD9(RBQ)                                                                                                        \
+  launch_kernel(message9_fwd_kernel<RBQ>, dim3(grid), dim3(kMsgWarps * 32), 0, (cudaStream_t)stream, phi, s, sbar, v, vbar, rowptr, col, \
+                basis, unit, Wf, bf, n, F, R, residual, out_s, out_sbar, out_v, out_vbar)
+  if (RB == 8) LAUNCH_FWD9(2); else if (RB == 12) LAUNCH_FWD9(3); else LAUNCH_FWD9(4);
+#undef LAUNCH_FWD9
   return launched("message9_fwd");
 }
 
@@ -622,16 +641,20 @@ int cgvae_message9_bwd(const float* phi, const float* s, const float* sbar, cons
                        int64_t n_edge_slots, int F, int R, int RB, int residual, const float* g_s, const float* g_sbar, const float* g_v,
                        const float* g_vbar, float* gi_s, float* gi_sbar, float* gi_v, float* gi_vbar, float* g_phi, float* gw,
                        cgvae_stream_t stream) {
-  CGVAE_REQUIRE(RB <= kMaxRB9 && R + 1 <= RB && RB % 4 == 0, "message9_bwd: bad RB=%d R=%d", RB, R);
+  CGVAE_REQUIRE((RB == 8 || RB == 12 || RB == 16) && R + 1 <= RB, "message9_bwd: bad RB=%d R=%d", RB, R);
   if (n == 0) return 0;
   CGVAE_REQUIRE(phi && s && sbar && v && vbar && rowptr && col && rowptr_t && col_t && perm_t && basis && unit && Wf && bf && g_s &&
                     g_sbar && g_v && g_vbar && gi_s && gi_sbar && gi_v && gi_vbar && g_phi && gw, "message9_bwd: null pointer");
   dim3 grid((unsigned)ceil_div(n, kMsgWarps), (unsigned)ceil_div(F, 32));
   // gw rows of unused (padded) edge slots must read as zero in the dWf = gw^T basis contraction
   CGVAE_CUDA(cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)n_edge_slots * 9 * (size_t)F, (cudaStream_t)stream));
-  launch_kernel(message9_bwd_kernel, dim3(grid), dim3(kMsgWarps * 32), 0, (cudaStream_t)stream, phi, s, sbar, v, vbar, rowptr, col, rowptr_t, col_t, perm_t,
-                                                                         basis, unit, Wf, bf, n, F, R, RB, residual, g_s, g_sbar,
-                                                                         g_v, g_vbar, gi_s, gi_sbar, gi_v, gi_vbar, g_phi, gw);
+  CGVAE_REQUIRE(aligned16(basis) && aligned16(unit), "message9_bwd: edge data must be 16-byte aligned");
+#define LAUNCH_BWD9(RBQ)                                                                                                        \
+  launch_kernel(message9_bwd_kernel<RBQ>, dim3(grid), dim3(kMsgWarps * 32), 0, (cudaStream_t)stream, phi, s, sbar, v, vbar, rowptr, col, \
+                rowptr_t, col_t, perm_t, basis, unit, Wf, bf, n, F, R, residual, g_s, g_sbar, g_v, g_vbar, gi_s, gi_sbar, gi_v,  \
+                gi_vbar, g_phi, gw)
+  if (RB == 8) LAUNCH_BWD9(2); else if (RB == 12) LAUNCH_BWD9(3); else LAUNCH_BWD9(4);
+#undef LAUNCH_BWD9
   return launched("message9_bwd");
 }
 

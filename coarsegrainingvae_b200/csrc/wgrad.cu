@@ -1,0 +1,162 @@
+// Grouped parameter-gradient contraction for small node counts (decoder graphs of the molecule configs: 12 beads).
+//
+// dW[n_out][n_in] = gy[rows][n_out]^T x[rows][n_in] with rows = 12..96 is an outer-product accumulation whose cost is
+// WRITING dW: at the chignolin config 55 M weight gradients (222 MB) per step.  As one launch per Dense layer (92 TN
+// GEMMs of 1.4..13 MB each + 56 bias column sums) the step spent 1.2 ms on them -- every launch is a single wave of
+// CTAs whose life is one load -> 12 FMA -> store latency chain (180 GB/s of stores).  The weight gradients do not feed
+// the rest of the backward pass, so the host defers them (ops.py: deferred list) and this kernel produces ALL of them
+// in one launch per 64 problems: the grid is the concatenation of the 64x64 output tiles of every problem, thousands
+// of CTAs are in flight and the stores stream at HBM rate.  The problem table travels in the kernel parameters
+// (__grid_constant__, 3.9 KB): no table memory, no copies, CUDA-graph capturable.
+//
+// Summation over rows is sequential in row order: deterministic, independent of the grouping.
+#include "common.cuh"
+
+namespace cgvae {
+
+constexpr int WG_MAXP = 64;   // problems per launch
+constexpr int WG_ROWS = 32;   // rows staged per pass
+constexpr int WG_T = 64;      // output tile edge
+
+struct WgradBatch {
+  cgvae_wgrad_problem p[WG_MAXP];
+  int tile_begin[WG_MAXP + 1];
+  int n;
+};
+static_assert(sizeof(WgradBatch) <= 4000, "problem table must fit the 4 KB kernel parameter space");
+
+__device__ __forceinline__ void stage_rows(float (*dst)[WG_T], const float* __restrict__ src, int ld, int r0, int rows,
+                                           int c0, int ncols, bool vec, int tid) {
+  // dst[r][c] = src[(r0+r)*ld + c0 + c] for r0 + r < rows (at most WG_ROWS of them), c < 64; zero for c0 + c >= ncols
+  const int rn = min(WG_ROWS, rows - r0);
+  for (int idx = tid; idx < rn * (WG_T / 4); idx += 256) {
+    const int r = idx / (WG_T / 4), c = 4 * (idx % (WG_T / 4));
+    float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+    {
+      const float* q = src + (int64_t)(r0 + r) * ld + c0 + c;
+      if (vec && c0 + c + 3 < ncols) {
+        val = __ldg(reinterpret_cast<const float4*>(q));
+      } else {
+        if (c0 + c + 0 < ncols) val.x = __ldg(q + 0);
+        if (c0 + c + 1 < ncols) val.y = __ldg(q + 1);
+        if (c0 + c + 2 < ncols) val.z = __ldg(q + 2);
+        if (c0 + c + 3 < ncols) val.w = __ldg(q + 3);
+      }
+    }
+    *reinterpret_cast<float4*>(&dst[r][c]) = val;
+  }
+}
+
+__global__ void __launch_bounds__(256) wgrad_grouped_kernel(const __grid_constant__ WgradBatch batch) {
+  CGVAE_KERNEL_PROLOGUE();
+  __shared__ __align__(16) float gs[WG_ROWS][WG_T];
+  __shared__ __align__(16) float xs[WG_ROWS][WG_T];
+  const int tid = threadIdx.x, bid = blockIdx.x;
+  int lo = 0, hi = batch.n;                     // tile_begin[lo] <= bid < tile_begin[hi]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (batch.tile_begin[mid] <= bid) lo = mid; else hi = mid;
+  }
+  const cgvae_wgrad_problem& P = batch.p[lo];
+  const float* __restrict__ gy = P.gy;
+  const float* __restrict__ x = P.x;
+  float* __restrict__ dW = P.dW;
+  float* __restrict__ db = P.db;
+  const int rows = P.rows, n_out = P.n_out, n_in = P.n_in, ldg = P.ldg, ldx = P.ldx;
+  const bool has_w = (dW != nullptr);
+  const int tiles_k = has_w ? (n_in + WG_T - 1) / WG_T : 1;
+  const int t = bid - batch.tile_begin[lo];
+  const int n0 = (t / tiles_k) * WG_T, k0 = (t % tiles_k) * WG_T;
+  const bool g_vec = ((reinterpret_cast<uintptr_t>(gy) & 15) == 0) && (ldg % 4 == 0);
+  const bool x_vec = has_w && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && (ldx % 4 == 0);
+  const int ty = tid >> 4, tx = tid & 15;       // outputs n0 + 4*ty + a, k0 + 4*tx + b
+
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+  float bsum = 0.f;
+  const bool do_bias = (db != nullptr) && k0 == 0;
+
+  for (int r0 = 0; r0 < rows; r0 += WG_ROWS) {
+    if (r0 > 0) __syncthreads();
+    stage_rows(gs, gy, ldg, r0, rows, n0, n_out, g_vec, tid);
+    if (has_w) stage_rows(xs, x, ldx, r0, rows, k0, n_in, x_vec, tid);
+    __syncthreads();
+    const int rn = min(WG_ROWS, rows - r0);
+    if (has_w) {
+#pragma unroll 4
+      for (int r = 0; r < rn; ++r) {
+        const float4 g4 = *reinterpret_cast<const float4*>(&gs[r][4 * ty]);
+        const float4 x4 = *reinterpret_cast<const float4*>(&xs[r][4 * tx]);
+        const float g[4] = {g4.x, g4.y, g4.z, g4.w}, xv[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(g[a], xv[b], acc[a][b]);
+      }
+    }
+    if (do_bias && tid < WG_T) {
+#pragma unroll 4
+      for (int r = 0; r < rn; ++r) bsum += gs[r][tid];
+    }
+  }
+  if (has_w) {
+    const bool w_vec = ((reinterpret_cast<uintptr_t>(dW) & 15) == 0) && (n_in % 4 == 0);
+    const int k = k0 + 4 * tx;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int n = n0 + 4 * ty + a;
+      if (n >= n_out) continue;
+      float* dst = dW + (int64_t)n * n_in + k;
+      if (w_vec && k + 3 < n_in) {
+        *reinterpret_cast<float4*>(dst) = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
+      } else {
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+          if (k + b < n_in) dst[b] = acc[a][b];
+      }
+    }
+  }
+  if (do_bias && tid < WG_T && n0 + tid < n_out) db[n0 + tid] = bsum;
+}
+
+}  // namespace cgvae
+
+using namespace cgvae;
+
+extern "C" {
+
+int cgvae_wgrad_grouped(const cgvae_wgrad_problem* problems, int n_problems, cgvae_stream_t stream) {
+  CGVAE_REQUIRE(n_problems >= 0, "wgrad_grouped: negative problem count");
+  if (n_problems == 0) return 0;
+  CGVAE_REQUIRE(problems != nullptr, "wgrad_grouped: null problem table");
+  for (int i = 0; i < n_problems; ++i) {
+    const cgvae_wgrad_problem& q = problems[i];
+    CGVAE_REQUIRE(q.gy && (q.dW || q.db), "wgrad_grouped: problem %d has no operand / no output", i);
+    CGVAE_REQUIRE(!q.dW || q.x, "wgrad_grouped: problem %d: dW without x", i);
+    CGVAE_REQUIRE(q.rows >= 0 && q.n_out >= 1 && q.ldg >= q.n_out, "wgrad_grouped: problem %d: bad gy shape", i);
+    CGVAE_REQUIRE(!q.dW || (q.n_in >= 1 && q.ldx >= q.n_in), "wgrad_grouped: problem %d: bad x shape", i);
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int base = 0; base < n_problems; base += WG_MAXP) {
+    WgradBatch batch;
+    batch.n = std::min(WG_MAXP, n_problems - base);
+    int64_t tiles = 0;
+    for (int i = 0; i < batch.n; ++i) {
+      batch.p[i] = problems[base + i];
+      batch.tile_begin[i] = (int)tiles;
+      const cgvae_wgrad_problem& q = batch.p[i];
+      tiles += ceil_div(q.n_out, WG_T) * (q.dW ? ceil_div(q.n_in, WG_T) : 1);
+      CGVAE_REQUIRE(tiles < (int64_t)1 << 30, "wgrad_grouped: too many output tiles");
+    }
+    for (int i = batch.n; i <= WG_MAXP; ++i) batch.tile_begin[i] = (int)tiles;
+    for (int i = batch.n; i < WG_MAXP; ++i) batch.p[i] = cgvae_wgrad_problem{};
+    launch_kernel(wgrad_grouped_kernel, dim3((unsigned)tiles), dim3(256), 0, st, batch);
+    if (int rc = launched("wgrad_grouped")) return rc;
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -21,7 +21,7 @@ def _phi_forward(s, W1, b1, W2, b2, act=SWISH):
 
 def _phi_backward(g_phi2d, s, a1, z1, W1, b1, W2, b2, add_to_gs, act=SWISH):
     """backward of phi = Dense2(act(Dense1(s))) given g_phi [N, K*F]; returns gs (+add), gW1, gb1, gW2, gb2."""
-    fork = ops.Fork(g_phi2d.device)
+    fork = ops.Fork(g_phi2d.device, enabled=not ops.deferring(g_phi2d.shape[0]))   # deferred: nothing to overlap
     gz1 = ops.linear_bwd_input(g_phi2d, W2, z_in=z1, dact=act)            # (g_phi W2) * act'(z1)
     with fork.branch():                                                   # parameter gradients: off the critical path
         gW2 = ops.linear_bwd_weight(g_phi2d, a1, W2)
@@ -158,7 +158,7 @@ class UpdateBlockFn(Function):
         gq2 = gq.view(N, 3 * F)
         v2 = v.view(3 * N, F)
         gUv2, gVv2 = gUv.view(3 * N, F), gVv.view(3 * N, F)
-        fork = ops.Fork(g_s.device)
+        fork = ops.Fork(g_s.device, enabled=not ops.deferring(3 * N))
         gz = ops.linear_bwd_input(gq2, A1, z_in=z, dact=SWISH)
         with fork.branch():                                                 # parameter gradients: off the critical path
             gA1 = ops.linear_bwd_weight(gq2, h, A1)

@@ -86,8 +86,8 @@ class Fork(object):
     graph capture this becomes a parallel branch of the graph).  Every branch is joined before the node returns, so all
     tensors it touches are still referenced -- no cross-stream allocator hazards."""
 
-    def __init__(self, device):
-        self.enabled = FORK_ENABLED and device.type == "cuda"
+    def __init__(self, device, enabled=True):
+        self.enabled = enabled and FORK_ENABLED and device.type == "cuda"
         if not self.enabled:
             return
         idx = device.index if device.index is not None else torch.cuda.current_device()
@@ -395,11 +395,99 @@ def linear_bwd_input(gy, W, z_in=None, dact=0, add=None):
     return gemm(GEMM_NN, gy, W, M, K, N, z_in=z_in, dact=dact, add=add)
 
 
+# Deferred parameter gradients.  Weight / bias gradients of Dense layers on small node sets (decoder graphs: 12..96
+# rows) cost as much as writing them; one launch per layer cannot keep enough stores in flight (1.2 ms per chignolin
+# step in 92 + 56 launches).  Nothing in the backward pass reads them, so while a DeferredGrads scope is open
+# (train.TrainStep opens one around loss.backward() when gradient sinks are registered) they are only RECORDED, and
+# flush() produces all of them with cgvae_wgrad_grouped: one launch per 64 problems.  The recorded operands stay
+# referenced until the flush, which is enqueued on the stream the backward ran on.
+DEFER_MAX_ROWS = 128
+_DEFERRED = None
+
+
+def deferring(rows):
+    return _DEFERRED is not None and rows <= DEFER_MAX_ROWS
+
+
+class DeferredGrads(object):
+    def __enter__(self):
+        global _DEFERRED
+        if _DEFERRED is not None:
+            raise RuntimeError("DeferredGrads scopes do not nest")
+        _DEFERRED = []
+        return self
+
+    def __exit__(self, exc_type, exc, tb):
+        global _DEFERRED
+        pending, _DEFERRED = _DEFERRED, None
+        if exc_type is None:
+            flush_deferred(pending)
+        return False
+
+
+_WGRAD_DTYPE = None
+
+
+def _wgrad_dtype():
+    global _WGRAD_DTYPE
+    if _WGRAD_DTYPE is None:
+        import numpy as np
+        _WGRAD_DTYPE = np.dtype([("gy", np.uint64), ("x", np.uint64), ("dW", np.uint64), ("db", np.uint64),
+                                 ("rows", np.int32), ("n_out", np.int32), ("n_in", np.int32), ("ldg", np.int32),
+                                 ("ldx", np.int32), ("reserved", np.int32)], align=True)
+        assert _WGRAD_DTYPE.itemsize == 56
+    return _WGRAD_DTYPE
+
+
+def wgrad_grouped(problems):
+    """problems: list of (gy [rows,n_out], x [rows,n_in] or None, dW [n_out,n_in] or None, db [n_out] or None);
+    cgvae_wgrad_grouped: every dW = gy^T x and db = colsum(gy) in one launch per 64 problems."""
+    if not problems:
+        return
+    import numpy as np
+    lib = _lib.load()
+    table = np.zeros(len(problems), dtype=_wgrad_dtype())
+    for i, (gy, x, dW, db) in enumerate(problems):
+        _need_cuda(gy)
+        if gy.stride(1) != 1 or (x is not None and x.stride(1) != 1):
+            raise ValueError("wgrad_grouped: operands must have unit column stride")
+        if dW is not None and not dW.is_contiguous():
+            raise ValueError("wgrad_grouped: dW must be contiguous")
+        table[i] = (gy.data_ptr(), x.data_ptr() if x is not None else 0, dW.data_ptr() if dW is not None else 0,
+                    db.data_ptr() if db is not None else 0, gy.shape[0], gy.shape[1], x.shape[1] if x is not None else 0,
+                    gy.stride(0), x.stride(0) if x is not None else 0, 0)
+    _lib.check(lib.cgvae_wgrad_grouped(table.ctypes.data, len(problems), _stream()), "wgrad_grouped")
+
+
+def flush_deferred(pending):
+    """merge the bias problem of a layer into its weight problem (same gy) and launch."""
+    merged, by_gy = [], {}
+    for gy, x, dW, db in pending:
+        key = (gy.data_ptr(), gy.shape[0], gy.shape[1], gy.stride(0))
+        hit = by_gy.get(key)
+        if hit is not None and ((db is not None and merged[hit][3] is None and dW is None)
+                                or (dW is not None and merged[hit][2] is None and db is None)):
+            g0, x0, w0, b0 = merged[hit]
+            merged[hit] = (g0, x if x0 is None else x0, dW if w0 is None else w0, db if b0 is None else b0)
+            continue
+        by_gy[key] = len(merged)
+        merged.append((gy, x, dW, db))
+    wgrad_grouped(merged)
+
+
 def linear_bwd_weight(gy, x, param=None):
     """gW[out,in] = gy^T x (written into the parameter's gradient sink when one is registered)"""
     rows, n_out = gy.shape
     n_in = x.shape[1]
     out = _grad_out(param, (n_out, n_in)) if param is not None else None
+    if deferring(rows) and gy.is_cuda and gy.stride(1) == 1 and x.stride(1) == 1:
+        if out is None:
+            out = torch.empty((n_out, n_in), dtype=torch.float32, device=gy.device)
+        # record an ALIAS of the output: autograd only adopts a returned gradient without copying when nothing else
+        # references the tensor object (AccumulateGrad's use_count test); gy / x are recorded as they are so that
+        # nobody accumulates into them in place before the flush
+        _DEFERRED.append((gy, x, out.detach(), None))
+        return out
     return gemm(GEMM_TN, gy, x, n_out, n_in, rows, out=out)
 
 
@@ -408,6 +496,9 @@ def colsum(X, param=None):
     lib = _lib.load()
     M, N = X.shape
     out = _grad_out(param, (N,)) if param is not None else torch.empty(N, dtype=torch.float32, device=X.device)
+    if deferring(M) and X.stride(1) == 1:
+        _DEFERRED.append((X, None, None, out.detach()))
+        return out
     _lib.check(lib.cgvae_colsum(_p(X), X.stride(0), M, N, _p(out), _stream()), "colsum")
     return out
 
@@ -489,13 +580,18 @@ def message9_bwd(phi, s, sbar, v, vbar, geom, Wf, bf, residual, g_s, g_sbar, g_v
     # dWf[9F,R] = gw^T basis[:, :R] ; dbf[9F] = gw^T basis[:, R]   (DistanceEmbed weight / bias gradients)
     R = geom.n_rbf
     E = g.n_edges
-    if E > 0:
+    if E > 0 and deferring(E):
+        dWf = linear_bwd_weight(gw, geom.basis[:, :R], Wf)
+        dbf = linear_bwd_weight(gw, geom.basis[:, R:R + 1], bf).reshape(9 * F)
+    elif E > 0:
         # forked branch; it is joined by the caller's next Fork.join() on the same side stream
         # (functions.Message9Block.backward -> _phi_backward), i.e. before the autograd node returns
         fork = Fork(dev)
         with fork.branch():
             dWf = gemm(GEMM_TN, gw, geom.basis, 9 * F, R, E, out=_grad_out(Wf, (9 * F, R)))
             dbf = gemm(GEMM_TN, gw, geom.basis[:, R:], 9 * F, 1, E, out=_grad_out(bf, (9 * F,)).view(9 * F, 1)).reshape(9 * F)
+        if deferring(n):          # the caller's forks are disabled when its own parameter gradients are deferred
+            fork.join()
     else:
         dWf = torch.zeros((9 * F, R), dtype=torch.float32, device=dev)
         dbf = torch.zeros((9 * F,), dtype=torch.float32, device=dev)

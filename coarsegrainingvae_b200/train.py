@@ -131,6 +131,8 @@ class TrainStep(object):
         self.flat = None
         self.opt = None
         self.flat_p = self.exp_avg = self.exp_avg_sq = self.step_count = None
+        import os
+        self.defer_grads = os.environ.get("CGVAE_DEFER_WGRAD", "1") != "0"
 
     def _loss(self, batch, eps):
         out = self.model(batch, eps=eps) if eps is not None else self.model(batch)
@@ -169,7 +171,12 @@ class TrainStep(object):
     def forward_backward(self, batch, eps=None):
         self.flat.zero_()
         loss = self._loss(batch, eps)
-        loss.backward()
+        if self.flat.sink and self.defer_grads:
+            from . import ops
+            with ops.DeferredGrads():      # small-graph weight / bias gradients: recorded, then ONE grouped launch
+                loss.backward()
+        else:
+            loss.backward()
         return loss
 
     def apply_gradients(self):

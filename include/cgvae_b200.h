@@ -136,6 +136,23 @@ int cgvae_gemm(int form, const float* A, int64_t lda, const float* B, int64_t ld
 /* out[N] = sum over rows of X[M][N] (bias gradients); deterministic. */
 int cgvae_colsum(const float* X, int64_t ldx, int64_t M, int64_t N, float* out, cgvae_stream_t stream);
 
+/* Grouped parameter gradients of Dense layers on small node sets (autograd of modules.py:99-112 /
+ * nn.Linear for the 12..96-row decoder graphs): for every problem
+ *   dW[n_out][n_in] = gy[rows][n_out]^T x[rows][n_in]   (dW contiguous; skipped when dW == NULL)
+ *   db[n_out]       = column sums of gy                 (skipped when db == NULL)
+ * All problems of the table are produced by ONE launch per 64 problems (the cost is writing dW, and one
+ * launch per layer cannot keep enough stores in flight).  `problems` is a HOST array (the table is
+ * passed to the device in the kernel parameters; it may be freed when the call returns); the pointers
+ * inside are device pointers.  Row sums run in row order: deterministic. */
+typedef struct cgvae_wgrad_problem {
+  const float* gy;   /* [rows][n_out], row stride ldg */
+  const float* x;    /* [rows][n_in], row stride ldx; may be NULL when dW is NULL */
+  float* dW;         /* [n_out][n_in] contiguous, or NULL */
+  float* db;         /* [n_out], or NULL */
+  int32_t rows, n_out, n_in, ldg, ldx, reserved;
+} cgvae_wgrad_problem;
+int cgvae_wgrad_grouped(const cgvae_wgrad_problem* problems, int n_problems, cgvae_stream_t stream);
+
 /* ------------------------------------------------------------------ message blocks */
 
 /* One fused message layer = gather phi/v at the sender, filter w = basis*[Wf;bf], channel mixing and

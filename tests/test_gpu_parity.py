@@ -140,7 +140,11 @@ def test_edge_geometry_vs_oracle():
 
 @pytest.mark.parametrize("M,N,K", [(12, 600, 600), (12, 5400, 600), (36, 600, 600), (350, 1800, 600), (97, 130, 77),
                                     (12, 600, 5400), (1000, 64, 20000), (5, 7, 3),
-                                    (4000, 2048, 512), (2500, 600, 1200)])   # large: tcgen05 3xTF32 path (gemm_tc.cu)
+                                    (4000, 2048, 512), (2500, 600, 1200),    # large: tcgen05 3xTF32 path (gemm_tc.cu)
+                                    # weight-streaming kernels (gemm_stream.cu): every row-count variant, ragged tails,
+                                    # several K blocks, column counts that are not a multiple of the vector width
+                                    (16, 1800, 1200), (13, 1030, 260), (40, 1030, 644), (48, 200, 1028), (1, 4096, 128),
+                                    (33, 77, 64), (12, 1200, 600), (36, 1800, 600)])
 def test_gemm_forms_and_epilogues(M, N, K):
     g = torch.Generator().manual_seed(M * 7 + N)
     A = torch.randn(M, K, generator=g)
@@ -338,6 +342,7 @@ def test_train_step_gradient_sink_matches_plain_autograd():
     training_loss(out, out[4], batch["bond_edge_list"], cfg["beta"], cfg["gamma"])[0].backward()
     plain = {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
     step = TrainStep(model, cfg["beta"], cfg["gamma"])
+    step.defer_grads = False
     used = step.prepare(batch, eps)
     assert sorted(used) == sorted(plain)
     step.forward_backward(batch, eps)
@@ -345,10 +350,55 @@ def test_train_step_gradient_sink_matches_plain_autograd():
     for k, p in model.named_parameters():
         if k in plain:
             assert torch.equal(p.grad, plain[k]), k
+    # deferred mode: the small-graph weight / bias gradients come from ONE grouped launch after the backward pass
+    # (different summation order than the per-layer contraction: compare to rounding)
+    step.defer_grads = True
+    before = ops.launch_count()
+    step.forward_backward(batch, eps)
+    deferred_launches = ops.launch_count() - before
+    assert step.flat.check_adopted()
+    for k, p in model.named_parameters():
+        if k in plain:
+            assert rel_err(p.grad, plain[k]) < 2e-6, k
+    step.defer_grads = False
+    before = ops.launch_count()
+    step.forward_backward(batch, eps)
+    assert deferred_launches < ops.launch_count() - before
+    step.defer_grads = True
     loss = step.step(batch, eps)
     assert torch.isfinite(loss)
     step.flat.release()
     assert not ops.GRAD_SINK
+
+
+def test_wgrad_grouped_vs_float64():
+    """cgvae_wgrad_grouped: every dW = gy^T x and db = colsum(gy) of a table of ragged problems (odd sizes, strided
+    operands, bias-only and weight-only entries, more than one 64-problem launch) against float64."""
+    g = torch.Generator().manual_seed(11)
+    shapes = [(12, 600, 600), (12, 5400, 600), (36, 600, 600), (1, 7, 5), (60, 5400, 10), (97, 130, 77), (33, 64, 64),
+              (128, 200, 36), (12, 1800, 1200)] + [(5 + i % 9, 17 + 3 * i, 9 + 5 * i) for i in range(70)]
+    problems, want = [], []
+    for idx, (rows, n_out, n_in) in enumerate(shapes):
+        gy_full = torch.randn(rows, n_out + 3, generator=g).to(DEV)
+        x_full = torch.randn(rows, n_in + 2, generator=g).to(DEV)
+        gy = gy_full[:, :n_out] if idx % 3 == 0 else gy_full[:, :n_out].contiguous()
+        x = x_full[:, 1:n_in + 1] if idx % 4 == 0 else x_full[:, :n_in].contiguous()
+        dW = torch.full((n_out, n_in), float("nan"), device=DEV) if idx % 5 != 1 else None
+        db = torch.full((n_out,), float("nan"), device=DEV) if idx % 5 != 2 else None
+        problems.append((gy, x if dW is not None else None, dW, db))
+        want.append((gy.double().t() @ x.double(), gy.double().sum(0)))
+    before = ops.launch_count()
+    ops.wgrad_grouped(problems)
+    assert ops.launch_count() - before == (len(problems) + 63) // 64
+    for (gy, x, dW, db), (w_ref, b_ref) in zip(problems, want):
+        if dW is not None:
+            assert rel_err(dW, w_ref) < GEMM_TOL, (tuple(gy.shape), tuple(dW.shape))
+        if db is not None:
+            assert rel_err(db, b_ref) < GEMM_TOL, tuple(gy.shape)
+    first = [t.clone() for pr in problems for t in pr[2:] if t is not None]
+    ops.wgrad_grouped(problems)
+    again = [t for pr in problems for t in pr[2:] if t is not None]
+    assert all(torch.equal(a, b) for a, b in zip(first, again))
 
 
 def test_fused_clip_adam_matches_torch():

@@ -81,3 +81,25 @@ def test_collate_matches_reference_layout():
     batch = cg.CG_collate(samples)
     for key in ("nxyz", "CG_nxyz", "CG_mapping", "nbr_list", "CG_nbr_list", "bond_edge_list", "num_atoms", "num_CGs"):
         assert torch.equal(batch[key], sec["batch/" + key]), key
+
+
+def test_deferred_gradients_merge_bias_into_weight_problem(monkeypatch):
+    """ops.flush_deferred: the bias problem of a Dense layer joins the weight problem on the same gy; a second weight
+    problem on the same gy (filter weight + filter bias of the 9-split block) stays separate."""
+    import torch
+    from coarsegrainingvae_b200 import ops
+    seen = []
+    monkeypatch.setattr(ops, "wgrad_grouped", lambda problems: seen.append(list(problems)))
+    gy, gy2, x = torch.randn(12, 8), torch.randn(12, 8), torch.randn(12, 5)
+    dW, db, dW2, db2, dW3 = torch.empty(8, 5), torch.empty(8), torch.empty(8, 5), torch.empty(8), torch.empty(8, 1)
+    ops.flush_deferred([(gy, x, dW, None), (gy, None, None, db), (gy2, None, None, db2), (gy2, x, dW2, None),
+                        (gy, x[:, :1], dW3, None)])
+    (merged,) = seen
+    assert len(merged) == 3
+    assert merged[0][0] is gy and merged[0][2] is dW and merged[0][3] is db
+    assert merged[1][0] is gy2 and merged[1][1] is x and merged[1][2] is dW2 and merged[1][3] is db2
+    assert merged[2][2] is dW3 and merged[2][3] is None
+    assert not ops.deferring(12)
+    with ops.DeferredGrads():
+        assert ops.deferring(12) and not ops.deferring(ops.DEFER_MAX_ROWS + 1)
+    assert len(seen) == 2 and seen[1] == []

@@ -36,3 +36,18 @@ for M in (12, 36):
         mb = n_out * n_in * 4 / 1e6
         print("M=%2d %s [%4dx%4d] %5.1f MB | NT %6.1f us (%5.2f TB/s)  NN %6.1f us (%5.2f TB/s)  TN %6.1f us (%5.2f TB/s write)" %
               (M, name, n_out, n_in, mb, t_nt, mb / t_nt, t_nn, mb / t_nn, t_tn, mb / t_tn), flush=True)
+
+# all decoder-layer parameter gradients of one chignolin step in one grouped launch (cgvae_wgrad_grouped)
+for M in (12,):
+    probs = []
+    for layer in range(9):
+        for name, n_out, n_in in shapes:
+            rows = 3 * M if name == "U" else M
+            probs.append((torch.randn(rows, n_out, device=dev), torch.randn(rows, n_in, device=dev),
+                          torch.empty(n_out, n_in, device=dev), torch.empty(n_out, device=dev)))
+        for _ in range(2):      # u_mat / v_mat: 36 rows
+            probs.append((torch.randn(3 * M, 600, device=dev), torch.randn(3 * M, 600, device=dev),
+                          torch.empty(600, 600, device=dev), None))
+    mb = sum(p[2].numel() for p in probs) * 4 / 1e6
+    t = bench([lambda: ops.wgrad_grouped(probs)], iters=10)
+    print("grouped wgrad: %d problems, %.0f MB written, %.1f us (%.2f TB/s)" % (len(probs), mb, t, mb / t), flush=True)
