@@ -30,8 +30,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-# DRAM traffic per launch of the fused message kernels on the chignolin atom graph, from the committed ncu capture
-NCU_DRAM_BYTES = {"message_fwd": 9.8e6, "message_bwd": 12.5e6}
+# DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) at the chignolin shapes, from the committed
+# ncu --set full capture profiles/r1b_ncu_full_hot_kernels_raw.csv (tools/profile_kernels.py)
+NCU_DRAM_BYTES = {"message_fwd": 12.3e6, "message_bwd": 12.5e6}
+NCU_SOURCE = "profiles/r1b_ncu_full_hot_kernels_raw.csv (tools/profile_kernels.py: same shapes, same build)"
 
 METRIC = "conformations/s (fwd+bwd train step)"
 UNIT = "conformations/s"
@@ -305,7 +307,7 @@ def run_cuda(args, cfg):
     # ---- roofline of the dominant kernel (fused message layer on the ATOM graph): CUDA events around the individual
     # launches.  Kernel boundaries are not host-visible inside a graph replay, so these launches are timed in eager
     # steps of the same workload, same process, right after the timed region.
-    ops.TIMER = ops.KernelTimer(["message_fwd", "message_bwd"])
+    ops.TIMER = ops.KernelTimer(["message_fwd", "message_bwd", "gemm", "wgrad_grouped", "adam_clip"])
     n_prof = min(args.steps, 10)
     for i in range(n_prof):
         trainer.step(dev_batches[i % args.pool], eps)
@@ -327,8 +329,11 @@ def run_cuda(args, cfg):
         entry = {"kernel": name + "_kernel<3,%d> (atom graph)" % (ops.rb_for(R) // 4), "bound": "tensor",
                  "achieved": flops / (t_ms * 1e-3) / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
                  "frac": flops / (t_ms * 1e-3) / 1e12 / tf32_peak, "traffic": NCU_DRAM_BYTES.get(name),
-                 "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of this launch in the ncu --set full capture "
-                                   "profiles/r1_ncu_full_message_kernels_raw.csv (same workload, earlier build)",
+                 "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of this launch in " + NCU_SOURCE,
+                 "fp32_simt": {"achieved_tflops": 2.0 * (46.0 if factor == 1.0 else 61.0) * E * F / (t_ms * 1e-3) / 1e12,
+                               "peak_tflops": 2.0 * 148 * 128 * 1.965e-3,
+                               "note": "all fp32 FMAs of the kernel (filter + channel mixing, 46 / 61 per edge and channel "
+                                       "forward / backward) against the SIMT FMA peak: the bound this implementation runs on"},
                  "peak_source": "derived: 0.5 x bf16_tflops_sustained of %s MEASURED_PEAKS (TF32 is not measured there)" % peaks["source"],
                  "avg_launch_us": 1e3 * t_ms, "launches_per_step": len(recs) / n_prof, "edges_per_launch": E,
                  "edges_per_s": E / (t_ms * 1e-3), "share_of_step": share,
@@ -337,6 +342,31 @@ def run_cuda(args, cfg):
         other[name] = entry
     if other:
         roof = max(other.values(), key=lambda e: e["share_of_step"])
+    # HBM-bound streaming kernels of the step: algorithmic bytes / measured time against the measured copy bandwidth
+    hbm_peak = peaks["hbm_gbs"]
+
+    def hbm_entry(kernel, recs, bytes_of, note):
+        if not recs:
+            return None
+        tot_ms = sum(t for t, _ in recs)
+        tot_b = float(sum(bytes_of(m) for _, m in recs))
+        return {"kernel": kernel, "bound": "hbm", "achieved": tot_b / (tot_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": tot_b / (tot_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None, "launches_per_step": len(recs) / n_prof,
+                "avg_launch_us": 1e3 * tot_ms / len(recs), "algorithmic_bytes_per_step": tot_b / n_prof,
+                "share_of_step": (tot_ms / n_prof) / ms, "peak_source": "hbm_gbs of %s MEASURED_PEAKS" % peaks["source"], "note": note}
+
+    skinny = [(t_, m) for t_, m in summ.get("gemm", []) if m["M"] <= 16 and m["form"] != ops.GEMM_TN and m["N"] * m["K"] >= 4096]
+    for key, ent in (
+            ("gemm_stream", hbm_entry("gemm_nt_stream / gemm_nn_stream (12-bead Dense layers, TMA weight streaming)", skinny,
+                                      lambda m: 4.0 * m["N"] * m["K"], "bytes = the weight matrix once per launch")),
+            ("wgrad_grouped", hbm_entry("wgrad_grouped_kernel (all small-graph weight / bias gradients of the step)",
+                                        summ.get("wgrad_grouped", []), lambda m: 4.0 * m["out_floats"],
+                                        "bytes = gradients written once")),
+            ("adam_clip", hbm_entry("sumsq_partial + adam_clip_kernel (clip_grad_norm_ + Adam on flat buffers)",
+                                    summ.get("adam_clip", []), lambda m: 32.0 * m["n"],
+                                    "bytes = 4 (norm pass) + 28 (p, g, m, v read; p, m, v written) per parameter"))):
+        if ent is not None:
+            other[key] = ent
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",

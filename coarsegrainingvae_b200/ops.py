@@ -375,9 +375,12 @@ def gemm(form, A, B, M, N, K, bias=None, act=0, z_out=False, z_in=None, dact=0, 
     if tiles < 148 and K >= 512:
         ws = torch.empty(_SPLITK_WS_BYTES, dtype=torch.uint8, device=dev)
         tk = _tickets(dev, st)
+    t0 = TIMER.begin("gemm") if TIMER is not None else None
     _lib.check(lib.cgvae_gemm(form, _p(A), A.stride(0), _p(B), B.stride(0), _p(C), C.stride(0), M, N, K, _p(bias), act, _p(Z),
                               _p(z_in), dact, _p(add), _p(ws), _SPLITK_WS_BYTES if ws is not None else 0, _p(tk),
                               _N_TICKETS if tk is not None else 0, st), "gemm")
+    if t0 is not None:
+        TIMER.end("gemm", t0, dict(form=form, M=M, N=N, K=K))
     return (C, Z) if z_out else C
 
 
@@ -456,7 +459,12 @@ def wgrad_grouped(problems):
         table[i] = (gy.data_ptr(), x.data_ptr() if x is not None else 0, dW.data_ptr() if dW is not None else 0,
                     db.data_ptr() if db is not None else 0, gy.shape[0], gy.shape[1], x.shape[1] if x is not None else 0,
                     gy.stride(0), x.stride(0) if x is not None else 0, 0)
+    t0 = TIMER.begin("wgrad_grouped") if TIMER is not None else None
     _lib.check(lib.cgvae_wgrad_grouped(table.ctypes.data, len(problems), _stream()), "wgrad_grouped")
+    if t0 is not None:
+        TIMER.end("wgrad_grouped", t0, dict(problems=len(problems),
+                                           out_floats=sum((p[2].numel() if p[2] is not None else 0) +
+                                                          (p[3].numel() if p[3] is not None else 0) for p in problems)))
 
 
 def flush_deferred(pending):
@@ -723,6 +731,9 @@ def adam_clip_step(p, g, m, v, step, max_norm, lr, betas=(0.9, 0.999), eps=1e-8,
     lib = _lib.load()
     ws_bytes = int(lib.cgvae_adam_ws_bytes())
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=p.device)
+    t0 = TIMER.begin("adam_clip") if TIMER is not None else None
     _lib.check(lib.cgvae_adam_clip_step(_p(p), _p(g), _p(m), _p(v), p.numel(), float(max_norm), float(lr), float(betas[0]),
                                         float(betas[1]), float(eps), _p(step), _p(norm_out), _p(ws), ws_bytes, _stream()),
                "adam_clip_step")
+    if t0 is not None:
+        TIMER.end("adam_clip", t0, dict(n=p.numel()))

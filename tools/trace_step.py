@@ -80,13 +80,20 @@ for e in s:
     by_stream[e.get("args", {}).get("stream", "?")] += e["dur"]
 P("sum of durations per stream: %s" % dict(by_stream))
 # gaps on the union timeline
-gaps = []
+gaps, where = [], []
 end = s[0]["ts"] + s[0]["dur"]
+prev = s[0]
 for e in s[1:]:
     if e["ts"] > end:
         gaps.append(e["ts"] - end)
+        where.append((e["ts"] - end, prev["name"].split("(")[0].replace("void ", "")[:60], e["name"].split("(")[0].replace("void ", "")[:60]))
+    if e["ts"] + e["dur"] >= end:
+        prev = e
     end = max(end, e["ts"] + e["dur"])
 gaps = np.array(gaps) if gaps else np.zeros(1)
+P("largest idle gaps (us, after kernel -> before kernel):")
+for g_, a_, b_ in sorted(where, key=lambda w: -w[0])[:24]:
+    P("  %6.2f  %-60s -> %s" % (g_, a_, b_))
 P("idle gaps in last step: n=%d total=%.1f us median=%.2f us p90=%.2f us max=%.1f us" % (len(gaps), gaps.sum(), np.median(gaps), np.percentile(gaps, 90), gaps.max()))
 os.makedirs(os.path.dirname(args.out), exist_ok=True)
 open(args.out, "w").write("\n".join(lines) + "\n")
