@@ -488,7 +488,7 @@ static int radius_prepare_cells(const float* xyz, int64_t n, const int64_t* fram
                                 void* ws, size_t ws_bytes, RadiusWs* w, cudaStream_t st) {
   CGVAE_REQUIRE(ws && ws_bytes >= cgvae_radius_graph_ws_bytes(n, n_frames), "radius_graph: workspace too small");
   radius_ws_layout(n, n_frames, reinterpret_cast<char*>(ws), w);
-  CGVAE_CUDA(cudaMemsetAsync(w->cell_count, 0, sizeof(int32_t) * (size_t)w->max_cells, st));
+  CGVAE_ZERO(w->cell_count, sizeof(int32_t) * (size_t)w->max_cells, st);
   launch_kernel(frame_bounds_kernel, dim3((unsigned)n_frames), dim3(256), 0, st, xyz, frame_ptr, cutoff, w->frames);
   if (int rc = launched("frame_bounds")) return rc;
   launch_kernel(frame_offsets_kernel, dim3(1), dim3(32), 0, st, w->frames, n_frames);
@@ -498,7 +498,7 @@ static int radius_prepare_cells(const float* xyz, int64_t n, const int64_t* fram
   if (int rc = launched("assign_cells")) return rc;
   launch_kernel(scan_kernel<int32_t>, dim3(1), dim3(1024), 0, st, w->cell_count, w->max_cells, w->cell_start);
   if (int rc = launched("cell_scan")) return rc;
-  CGVAE_CUDA(cudaMemsetAsync(w->cell_count, 0, sizeof(int32_t) * (size_t)w->max_cells, st));
+  CGVAE_ZERO(w->cell_count, sizeof(int32_t) * (size_t)w->max_cells, st);
   launch_kernel(fill_cells_kernel, dim3(gb), dim3(256), 0, st, n, w->cell_of_atom, w->cell_start, w->cell_count, w->cell_atoms);
   return launched("fill_cells");
 }
@@ -555,7 +555,7 @@ int cgvae_scan_i32(const int32_t* counts, int64_t n, int32_t* out, cgvae_stream_
 int cgvae_edge_orientation(const int64_t* pairs, int64_t n_edges, int32_t* flags, cgvae_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
   CGVAE_REQUIRE(flags, "edge_orientation: null flags");
-  CGVAE_CUDA(cudaMemsetAsync(flags, 0, 2 * sizeof(int32_t), st));
+  CGVAE_ZERO(flags, 2 * sizeof(int32_t), st);
   if (n_edges == 0) return 0;
   launch_kernel(edge_orientation_kernel, dim3((unsigned)ceil_div(n_edges, 256)), dim3(256), 0, st, pairs, n_edges, flags);
   return launched("edge_orientation");
@@ -566,8 +566,8 @@ int cgvae_csr_count(const int64_t* pairs, int64_t n_edges, const int64_t* n_edge
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t cap = symmetrize ? 2 * n_edges : n_edges;
   CGVAE_REQUIRE(n_edges >= 0 && cap < INT_MAX && deg_r && deg_s, "csr_count: bad arguments");
-  CGVAE_CUDA(cudaMemsetAsync(deg_r, 0, sizeof(int32_t) * (size_t)n_recv, st));
-  CGVAE_CUDA(cudaMemsetAsync(deg_s, 0, sizeof(int32_t) * (size_t)n_send, st));
+  CGVAE_ZERO(deg_r, sizeof(int32_t) * (size_t)n_recv, st);
+  CGVAE_ZERO(deg_s, sizeof(int32_t) * (size_t)n_send, st);
   if (cap == 0) return 0;
   launch_kernel(csr_count_kernel, dim3((unsigned)ceil_div(cap, 256)), dim3(256), 0, st, pairs, n_edges, n_edges_dev, symmetrize, deg_r, deg_s);
   return launched("csr_count");
@@ -585,7 +585,7 @@ int cgvae_csr_fill(const int64_t* pairs, int64_t n_edges_in, const int64_t* n_ed
   int32_t* cursor_s = cursor_r + n_recv;
   int32_t* eid_s = cursor_s + n_send;
   int32_t* slot_of_edge = eid_s + n_edges;
-  CGVAE_CUDA(cudaMemsetAsync(cursor_r, 0, sizeof(int32_t) * (size_t)(n_recv + n_send), st));
+  CGVAE_ZERO(cursor_r, sizeof(int32_t) * (size_t)(n_recv + n_send), st);
   const unsigned gb = (unsigned)ceil_div(n_edges, 256);
   launch_kernel(csr_place_kernel, dim3(gb), dim3(256), 0, st, pairs, n_edges_in, n_edges_dev, symmetrize, rowptr_r, rowptr_s, cursor_r, cursor_s, eid, eid_s);
   if (int rc = launched("csr_place")) return rc;
@@ -606,7 +606,7 @@ int cgvae_csr_fill(const int64_t* pairs, int64_t n_edges_in, const int64_t* n_ed
 int cgvae_segment_count(const int64_t* mapping, int64_t n, int64_t n_beads, int32_t* deg, cgvae_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
   CGVAE_REQUIRE(deg && n >= 0 && n < INT_MAX, "segment_count: bad arguments");
-  CGVAE_CUDA(cudaMemsetAsync(deg, 0, sizeof(int32_t) * (size_t)n_beads, st));
+  CGVAE_ZERO(deg, sizeof(int32_t) * (size_t)n_beads, st);
   if (n == 0) return 0;
   launch_kernel(segment_count_kernel, dim3((unsigned)ceil_div(n, 256)), dim3(256), 0, st, mapping, n, deg);
   return launched("segment_count");
@@ -617,7 +617,7 @@ int cgvae_segment_rank(const int64_t* mapping, int64_t n, int64_t n_beads, const
   cudaStream_t st = (cudaStream_t)stream;
   if (n == 0) return 0;
   CGVAE_REQUIRE(mapping && rowptr_b && scratch && atoms && slot_of_atom && rank, "segment_rank: null pointer");
-  CGVAE_CUDA(cudaMemsetAsync(scratch, 0, sizeof(int32_t) * (size_t)n_beads, st));
+  CGVAE_ZERO(scratch, sizeof(int32_t) * (size_t)n_beads, st);
   const unsigned gb = (unsigned)ceil_div(n, 256);
   launch_kernel(segment_place_kernel, dim3(gb), dim3(256), 0, st, mapping, n, rowptr_b, scratch, atoms);
   if (int rc = launched("segment_place")) return rc;

@@ -665,7 +665,7 @@ int cgvae_message_bwd(int n_split, const float* phi, const float* v_send, const 
   const int chunks = bwd_chunks(n_send > 0 ? n_send : 1, F, &per);
   float* partial = reinterpret_cast<float*>(ws);
   if (n_send == 0) {
-    CGVAE_CUDA(cudaMemsetAsync(partial, 0, sizeof(float) * (size_t)n_split * RB * F, st));
+    CGVAE_ZERO(partial, sizeof(float) * (size_t)n_split * RB * F, st);
   } else {
     dim3 grid((unsigned)chunks, (unsigned)ceil_div(F, 32));
     // (forcing 5 CTAs per SM -- 96 registers, 24 bytes of spills -- measured no faster on B200: 186 vs 183 us at chignolin)
@@ -717,7 +717,7 @@ int cgvae_message9_bwd(const float* phi, const float* s, const float* sbar, cons
                     g_sbar && g_v && g_vbar && gi_s && gi_sbar && gi_v && gi_vbar && g_phi && gw, "message9_bwd: null pointer");
   dim3 grid((unsigned)ceil_div(n, kMsgWarps), (unsigned)ceil_div(F, 32));
   // gw rows of unused (padded) edge slots must read as zero in the dWf = gw^T basis contraction
-  CGVAE_CUDA(cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)n_edge_slots * 9 * (size_t)F, (cudaStream_t)stream));
+  CGVAE_ZERO(gw, sizeof(float) * (size_t)n_edge_slots * 9 * (size_t)F, (cudaStream_t)stream);
   CGVAE_REQUIRE(aligned16(basis) && aligned16(unit), "message9_bwd: edge data must be 16-byte aligned");
 #define LAUNCH_BWD9(RBQ)                                                                                                        \
   launch_kernel(message9_bwd_kernel<RBQ>, dim3(grid), dim3(kMsgWarps * 32), 0, (cudaStream_t)stream, phi, s, sbar, v, vbar, rowptr, col, \

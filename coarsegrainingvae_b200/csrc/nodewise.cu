@@ -261,7 +261,7 @@ int cgvae_lift_bwd(const float* g_xyz, const int64_t* mapping, const int64_t* ra
   cudaStream_t st = (cudaStream_t)stream;
   if (n_beads == 0) return 0;
   CGVAE_REQUIRE(g_xyz && rank && rowptr_b && atoms && g_V, "lift_bwd: null pointer");
-  CGVAE_CUDA(cudaMemsetAsync(g_V, 0, sizeof(float) * (size_t)n_beads * 3 * (size_t)F, st));
+  CGVAE_ZERO(g_V, sizeof(float) * (size_t)n_beads * 3 * (size_t)F, st);
   if (N == 0) return 0;
   launch_kernel(lift_bwd_kernel, dim3((unsigned)ceil_div(n_beads, 4)), dim3(128), 0, st, g_xyz, rank, rowptr_b, atoms, pin, n_beads, F, mode, g_V);
   return launched("lift_bwd");

@@ -51,9 +51,11 @@ class KernelTimer(object):
     """Optional CUDA-event timing of individual kernel launches on the launching stream (bench.py uses it for the
     live roofline figure).  ``records[name]`` = list of (start_event, end_event, meta)."""
 
-    def __init__(self, names):
+    def __init__(self, names, keep_operands=False):
         self.names = set(names)
         self.records = {}
+        self.keep_operands = keep_operands      # also keep the operand tensors of gemm / wgrad_grouped calls (bench.py
+                                                # replays those exact launches in isolation inside a CUDA graph)
 
     def begin(self, name):
         if name not in self.names:
@@ -380,7 +382,10 @@ def gemm(form, A, B, M, N, K, bias=None, act=0, z_out=False, z_in=None, dact=0, 
                               _p(z_in), dact, _p(add), _p(ws), _SPLITK_WS_BYTES if ws is not None else 0, _p(tk),
                               _N_TICKETS if tk is not None else 0, st), "gemm")
     if t0 is not None:
-        TIMER.end("gemm", t0, dict(form=form, M=M, N=N, K=K))
+        meta = dict(form=form, M=M, N=N, K=K)
+        if TIMER.keep_operands:
+            meta.update(A=A, B=B, bias=bias, act=act, z_in=z_in, dact=dact, add=add)
+        TIMER.end("gemm", t0, meta)
     return (C, Z) if z_out else C
 
 
@@ -462,7 +467,7 @@ def wgrad_grouped(problems):
     t0 = TIMER.begin("wgrad_grouped") if TIMER is not None else None
     _lib.check(lib.cgvae_wgrad_grouped(table.ctypes.data, len(problems), _stream()), "wgrad_grouped")
     if t0 is not None:
-        TIMER.end("wgrad_grouped", t0, dict(problems=len(problems),
+        TIMER.end("wgrad_grouped", t0, dict(problems=len(problems), table=(list(problems) if TIMER.keep_operands else None),
                                            out_floats=sum((p[2].numel() if p[2] is not None else 0) +
                                                           (p[3].numel() if p[3] is not None else 0) for p in problems)))
 

@@ -452,9 +452,11 @@ def test_graphed_train_step_matches_eager():
     graphed = GraphedTrainStep(graph_tr, static[0], eps)
     for _ in range(3):
         eager.step(_to(raw[0], DEV), eps)
-    for i in (1, 2, 0, 1):
+    for n, i in enumerate((1, 2, 0, 1)):
         la = eager.step(_to(raw[i], DEV), eps)
-        lb = graphed.step(static[i])
+        # dict of tensors (one copy per key) and the packed single-buffer form (one copy) must load the same batch
+        lb = graphed.step(static[i] if n % 2 == 0 else graphed.pack({k: (v.cpu() if torch.is_tensor(v) else v)
+                                                                     for k, v in static[i].items()}, pin=True))
         assert rel_err(lb, la) < 1e-5, (i, float(la), float(lb))
     for (k, pa), (_, pb) in zip(model_a.named_parameters(), model_b.named_parameters()):
         assert rel_err(pb, pa) < 1e-4, k
