@@ -122,8 +122,14 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) gemm_kernel(
   constexpr int NT = (BM / TM) * (BN / TN);
   using LoaderA = TileLoader<BM, BK, A_KC, NT>;
   using LoaderB = TileLoader<BN, BK, B_KC, NT>;
-  __shared__ __align__(16) float As[2][LoaderA::SMEM_FLOATS];
-  __shared__ __align__(16) float Bs[2][LoaderB::SMEM_FLOATS];
+  // one buffer: the double-buffered operand tiles during the k-loop, the CTA's partial output tile for the cluster
+  // reduction afterwards (the tiles are dead by then)
+  constexpr int SA = LoaderA::SMEM_FLOATS, SB = LoaderB::SMEM_FLOATS;
+  constexpr int TILE_FLOATS = 2 * (SA + SB);
+  constexpr int SMEM_FLOATS = (CLUSTER && BM * BN > TILE_FLOATS) ? BM * BN : TILE_FLOATS;
+  __shared__ __align__(16) float smem_all[SMEM_FLOATS];
+  float (*As)[SA] = reinterpret_cast<float (*)[SA]>(smem_all);
+  float (*Bs)[SB] = reinterpret_cast<float (*)[SB]>(smem_all + 2 * SA);
   const int tid = threadIdx.x;
   const int tx = tid % (BN / TN), ty = tid / (BN / TN);
   const int64_t m0 = (int64_t)blockIdx.y * BM, n0 = (int64_t)blockIdx.x * BN;
@@ -197,7 +203,8 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) gemm_kernel(
   if constexpr (CLUSTER) {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
-    __shared__ __align__(16) float red[BM * BN];
+    __syncthreads();                 // every warp is done reading the operand tiles
+    float* red = smem_all;
 #pragma unroll
     for (int i = 0; i < TM; ++i)
 #pragma unroll
@@ -585,6 +592,13 @@ int cgvae_gemm(int form, const float* A, int64_t lda, const float* B, int64_t ld
   if (M <= 32) return launch_gemm<32, 32, 64, 2, 2>(form, A, lda, B, ldb, C, ldc, M, N, K, ep, wsf, ws_bytes, counters, n_counters, st);
   if (M <= 48 && form != CGVAE_GEMM_TN)   // UpdateBlock mixes on 12-bead graphs: 36 rows
     return launch_gemm<48, 32, 32, 3, 2>(form, A, lda, B, ldb, C, ldc, M, N, K, ep, wsf, ws_bytes, counters, n_counters, st);
+  // 128-row tiles, 8x4 per thread (3 LDS.128 per 32 FMA instead of 2 per 16; the 64x64 tile is bound by shared-memory
+  // loads: ncu short-scoreboard stalls, 37 % issue utilisation).  Measured on B200 at the chignolin atom-level layers
+  // (350 rows): NN 35 vs 39 us, but NT 22 vs 19.5 and TN 59 vs 52 us (3 row tiles of 128 waste 9 % and halve the CTA
+  // count), 3.55 vs 3.49 ms per step -- opt-in
+  static const bool tall = [] { const char* e = getenv("CGVAE_GEMM_TALL"); return e && e[0] == '1'; }();
+  if (tall && M >= 192 && N >= 64)
+    return launch_gemm<128, 64, 16, 8, 4>(form, A, lda, B, ldb, C, ldc, M, N, K, ep, wsf, ws_bytes, counters, n_counters, st);
   return launch_gemm<64, 64, 16, 4, 4>(form, A, lda, B, ldb, C, ldc, M, N, K, ep, wsf, ws_bytes, counters, n_counters, st);
 }
 

@@ -402,7 +402,10 @@ __device__ __forceinline__ void stage_filter9(float (*Wsm)[kMaxRB9][32], const f
 // RB is a template parameter (RBQ float4 per basis row): the per-edge basis row sits in registers and the 9 x RB filter
 // contraction is fully unrolled.  With a run-time RB the loop was a chain of dependent L1 loads (~50 cycles per term,
 // 108 terms per edge): 23 us per launch on the 12-bead decoder graphs, almost all of it latency.
-template <int RBQ>
+// UNR: edges of a node processed per unrolled group.  The decoder graphs of the molecule configs are tiny (12 beads, 5
+// edges each, 57 CTAs): the kernel is a chain of dependent round trips (edge -> sender index -> gathers), and with
+// UNR = 4 the loads of four edges are in flight together.  Large graphs (PCN: 16 000 residues) use UNR = 1: 64 registers.
+template <int RBQ, int UNR>
 __global__ void __launch_bounds__(kMsgWarps * 32) message9_fwd_kernel(
     const float* __restrict__ phi, const float* __restrict__ s, const float* __restrict__ sbar, const float* __restrict__ v,
     const float* __restrict__ vbar, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
@@ -423,7 +426,7 @@ __global__ void __launch_bounds__(kMsgWarps * 32) message9_fwd_kernel(
   load3(v, i, F, f, v_i);
   load3(vbar, i, F, f, vb_i);
   float a_s = 0.f, a_sb = 0.f, a_v[3] = {0.f, 0.f, 0.f}, a_vb[3] = {0.f, 0.f, 0.f};
-#pragma unroll 1
+#pragma unroll UNR
   for (int e = rowptr[i]; e < rowptr[i + 1]; ++e) {
     const int j = col[e];
     float b[RB];
@@ -463,7 +466,7 @@ __global__ void __launch_bounds__(kMsgWarps * 32) message9_fwd_kernel(
   }
 }
 
-template <int RBQ>
+template <int RBQ, int UNR>
 __global__ void __launch_bounds__(kMsgWarps * 32) message9_bwd_kernel(
     const float* __restrict__ phi, const float* __restrict__ s, const float* __restrict__ sbar, const float* __restrict__ v,
     const float* __restrict__ vbar, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
@@ -497,6 +500,7 @@ __global__ void __launch_bounds__(kMsgWarps * 32) message9_bwd_kernel(
   float ph[9], gph[9];
 #pragma unroll
   for (int k = 0; k < 9; ++k) { ph[k] = phi[((int64_t)nd * 9 + k) * F + f]; gph[k] = 0.f; }
+#pragma unroll UNR
   for (int t = rowptr_t[nd]; t < rowptr_t[nd + 1]; ++t) {
     const int i = col_t[t], e = perm_t[t];
     float b[RB];
@@ -553,6 +557,7 @@ __global__ void __launch_bounds__(kMsgWarps * 32) message9_bwd_kernel(
   for (int k = 0; k < 9; ++k) g_phi[((int64_t)nd * 9 + k) * F + f] = gph[k];
 
   // ---- node as RECEIVER i = nd: edges (nd <- j)
+#pragma unroll UNR
   for (int e = rowptr[nd]; e < rowptr[nd + 1]; ++e) {
     const int j = col[e];
     float b[RB];
@@ -697,9 +702,16 @@ int cgvae_message9_fwd(const float* phi, const float* s, const float* sbar, cons
                 "message9_fwd: null pointer");
   dim3 grid((unsigned)ceil_div(n, kMsgWarps), (unsigned)ceil_div(F, 32));
   CGVAE_REQUIRE(aligned16(basis) && aligned16(unit), "message9_fwd: edge data must be 16-byte aligned");
+  const bool tiny = n <= 512;
 #define LAUNCH_FWD9(RBQ)                                                                                                        \
-  launch_kernel(message9_fwd_kernel<RBQ>, dim3(grid), dim3(kMsgWarps * 32), 0, (cudaStream_t)stream, phi, s, sbar, v, vbar, rowptr, col, \
-                basis, unit, Wf, bf, n, F, R, residual, out_s, out_sbar, out_v, out_vbar)
+  do {                                                                                                                          \
+    if (tiny)                                                                                                                   \
+      launch_kernel(message9_fwd_kernel<RBQ, 4>, dim3(grid), dim3(kMsgWarps * 32), 0, (cudaStream_t)stream, phi, s, sbar, v, vbar, rowptr, \
+                    col, basis, unit, Wf, bf, n, F, R, residual, out_s, out_sbar, out_v, out_vbar);                              \
+    else                                                                                                                        \
+      launch_kernel(message9_fwd_kernel<RBQ, 1>, dim3(grid), dim3(kMsgWarps * 32), 0, (cudaStream_t)stream, phi, s, sbar, v, vbar, rowptr, \
+                    col, basis, unit, Wf, bf, n, F, R, residual, out_s, out_sbar, out_v, out_vbar);                              \
+  } while (0)
   if (RB == 8) LAUNCH_FWD9(2); else if (RB == 12) LAUNCH_FWD9(3); else LAUNCH_FWD9(4);
 #undef LAUNCH_FWD9
   return launched("message9_fwd");
@@ -719,10 +731,18 @@ int cgvae_message9_bwd(const float* phi, const float* s, const float* sbar, cons
   // gw rows of unused (padded) edge slots must read as zero in the dWf = gw^T basis contraction
   CGVAE_ZERO(gw, sizeof(float) * (size_t)n_edge_slots * 9 * (size_t)F, (cudaStream_t)stream);
   CGVAE_REQUIRE(aligned16(basis) && aligned16(unit), "message9_bwd: edge data must be 16-byte aligned");
+  const bool tiny = n <= 512;
 #define LAUNCH_BWD9(RBQ)                                                                                                        \
-  launch_kernel(message9_bwd_kernel<RBQ>, dim3(grid), dim3(kMsgWarps * 32), 0, (cudaStream_t)stream, phi, s, sbar, v, vbar, rowptr, col, \
-                rowptr_t, col_t, perm_t, basis, unit, Wf, bf, n, F, R, residual, g_s, g_sbar, g_v, g_vbar, gi_s, gi_sbar, gi_v,  \
-                gi_vbar, g_phi, gw)
+  do {                                                                                                                          \
+    if (tiny)                                                                                                                   \
+      launch_kernel(message9_bwd_kernel<RBQ, 3>, dim3(grid), dim3(kMsgWarps * 32), 0, (cudaStream_t)stream, phi, s, sbar, v, vbar, rowptr, \
+                    col, rowptr_t, col_t, perm_t, basis, unit, Wf, bf, n, F, R, residual, g_s, g_sbar, g_v, g_vbar, gi_s, gi_sbar, \
+                    gi_v, gi_vbar, g_phi, gw);                                                                                  \
+    else                                                                                                                        \
+      launch_kernel(message9_bwd_kernel<RBQ, 1>, dim3(grid), dim3(kMsgWarps * 32), 0, (cudaStream_t)stream, phi, s, sbar, v, vbar, rowptr, \
+                    col, rowptr_t, col_t, perm_t, basis, unit, Wf, bf, n, F, R, residual, g_s, g_sbar, g_v, g_vbar, gi_s, gi_sbar, \
+                    gi_v, gi_vbar, g_phi, gw);                                                                                  \
+  } while (0)
   if (RB == 8) LAUNCH_BWD9(2); else if (RB == 12) LAUNCH_BWD9(3); else LAUNCH_BWD9(4);
 #undef LAUNCH_BWD9
   return launched("message9_bwd");
