@@ -57,7 +57,7 @@ SIGNATURES = {
     "cgvae_lift_fwd": (_INT, [_P, _P, _P, _P, _P, _P, _P, _I64, _I64, _INT, _INT, _P, _P]),
     "cgvae_lift_bwd": (_INT, [_P, _P, _P, _P, _P, _P, _I64, _I64, _INT, _INT, _P, _P]),
     "cgvae_adam_ws_bytes": (_SZ, []),
-    "cgvae_adam_clip_step": (_INT, [_P, _P, _P, _P, _I64, _F32, _F32, _F32, _F32, _F32, _P, _P, _P, _SZ, _P]),
+    "cgvae_adam_clip_step": (_INT, [_P, _P, _P, _P, _I64, _F32, _F32, _F32, _F32, _F32, _F32, _P, _P, _P, _SZ, _P]),
     "cgvae_vec_to_planar": (_INT, [_P, _I64, _INT, _P, _P]),
     "cgvae_vec_from_planar": (_INT, [_P, _I64, _INT, _P, _P]),
 }

@@ -33,8 +33,8 @@ __global__ void __launch_bounds__(256) sumsq_partial_kernel(const float* __restr
 
 __global__ void __launch_bounds__(256) adam_clip_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                         float* __restrict__ v, int64_t n, const float* __restrict__ partial,
-                                                        float max_norm, float lr, float beta1, float beta2, float eps,
-                                                        const float* __restrict__ step, float* __restrict__ norm_out) {
+                                                        float max_norm, float grad_scale, float lr, float beta1, float beta2,
+                                                        float eps, const float* __restrict__ step, float* __restrict__ norm_out) {
   CGVAE_KERNEL_PROLOGUE();
   // every block re-reduces the 1024 partial sums in the same fixed order: identical clip coefficient everywhere
   __shared__ float red[8];
@@ -48,8 +48,9 @@ __global__ void __launch_bounds__(256) adam_clip_kernel(float* __restrict__ p, c
     float t = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) t += red[w];
-    const float norm = sqrtf(t);
-    coef_sh = fminf(max_norm / (norm + 1e-6f), 1.0f);        // clip_grad_norm_: coef = max_norm / (norm + 1e-6), clamped to 1
+    const float norm = grad_scale * sqrtf(t);                // g holds the SUM over ranks: the mean's norm is scale * |g|
+    // clip_grad_norm_: coef = max_norm / (norm + 1e-6), clamped to 1; the 1/world of the data-parallel mean rides along
+    coef_sh = grad_scale * fminf(max_norm / (norm + 1e-6f), 1.0f);
     if (blockIdx.x == 0 && norm_out) norm_out[0] = norm;
   }
   __syncthreads();
@@ -95,8 +96,9 @@ extern "C" {
 
 size_t cgvae_adam_ws_bytes(void) { return sizeof(float) * kNormBlocks; }
 
-int cgvae_adam_clip_step(float* p, const float* g, float* m, float* v, int64_t n, float max_norm, float lr, float beta1, float beta2,
-                         float eps, float* step, float* norm_out, void* ws, size_t ws_bytes, cgvae_stream_t stream) {
+int cgvae_adam_clip_step(float* p, const float* g, float* m, float* v, int64_t n, float max_norm, float grad_scale, float lr,
+                         float beta1, float beta2, float eps, float* step, float* norm_out, void* ws, size_t ws_bytes,
+                         cgvae_stream_t stream) {
   if (n == 0) return 0;
   CGVAE_REQUIRE(p && g && m && v && step && ws && ws_bytes >= cgvae_adam_ws_bytes(), "adam_clip_step: bad arguments");
   CGVAE_REQUIRE(aligned16(p) && aligned16(g) && aligned16(m) && aligned16(v), "adam_clip_step: buffers must be 16-byte aligned");
@@ -105,7 +107,7 @@ int cgvae_adam_clip_step(float* p, const float* g, float* m, float* v, int64_t n
   launch_kernel(sumsq_partial_kernel, dim3(kNormBlocks), dim3(256), 0, st, g, n, partial, step);
   if (int rc = launched("sumsq_partial")) return rc;
   const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(n, 256 * 4), 148 * 8);
-  launch_kernel(adam_clip_kernel, dim3(blocks), dim3(256), 0, st, p, g, m, v, n, (const float*)partial, max_norm, lr, beta1, beta2, eps,
+  launch_kernel(adam_clip_kernel, dim3(blocks), dim3(256), 0, st, p, g, m, v, n, (const float*)partial, max_norm, grad_scale, lr, beta1, beta2, eps,
                 (const float*)step, norm_out);
   return launched("adam_clip");
 }

@@ -730,14 +730,15 @@ def vec_from_planar(v_n3f):
     return out
 
 
-def adam_clip_step(p, g, m, v, step, max_norm, lr, betas=(0.9, 0.999), eps=1e-8, norm_out=None):
-    """fused clip_grad_norm_ + Adam on flat buffers (cgvae_adam_clip_step); all tensors flat fp32 CUDA, `step` float [1]."""
+def adam_clip_step(p, g, m, v, step, max_norm, lr, betas=(0.9, 0.999), eps=1e-8, norm_out=None, grad_scale=1.0):
+    """fused clip_grad_norm_ + Adam on flat buffers (cgvae_adam_clip_step); all tensors flat fp32 CUDA, `step` float [1];
+    the gradients are taken as grad_scale * g (1/world after an all-reduce(sum))."""
     _need_cuda(p, g, m, v, step)
     lib = _lib.load()
     ws_bytes = int(lib.cgvae_adam_ws_bytes())
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=p.device)
     t0 = TIMER.begin("adam_clip") if TIMER is not None else None
-    _lib.check(lib.cgvae_adam_clip_step(_p(p), _p(g), _p(m), _p(v), p.numel(), float(max_norm), float(lr), float(betas[0]),
+    _lib.check(lib.cgvae_adam_clip_step(_p(p), _p(g), _p(m), _p(v), p.numel(), float(max_norm), float(grad_scale), float(lr), float(betas[0]),
                                         float(betas[1]), float(eps), _p(step), _p(norm_out), _p(ws), ws_bytes, _stream()),
                "adam_clip_step")
     if t0 is not None:

@@ -88,8 +88,9 @@ class FlatGrads(object):
             for p in self.params:
                 ops.GRAD_SINK.pop(p.data_ptr(), None)
 
-    def allreduce_mean_(self, group=None):
-        """gradient exchange of data-parallel training: one all-reduce(sum) over NVLink, then 1/world."""
+    def allreduce_mean_(self, group=None, scale_in_optimizer=False):
+        """gradient exchange of data-parallel training: one all-reduce(sum) over NVLink, then 1/world -- applied here, or
+        (scale_in_optimizer) left to the fused optimiser kernel, which takes the factor as an argument."""
         import torch.distributed as dist
         if not (dist.is_available() and dist.is_initialized()):
             return
@@ -97,7 +98,8 @@ class FlatGrads(object):
         if world == 1:
             return
         dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
-        self.flat.mul_(1.0 / world)
+        if not scale_in_optimizer:
+            self.flat.mul_(1.0 / world)
 
     def clip_(self, max_norm):
         """torch.nn.utils.clip_grad_norm_ semantics (scripts/utils.py:156) on the flat buffer; returns the norm."""
@@ -179,17 +181,26 @@ class TrainStep(object):
             loss.backward()
         return loss
 
+    def _world(self):
+        import torch.distributed as dist
+        return dist.get_world_size(self.group) if (dist.is_available() and dist.is_initialized()) else 1
+
+    def exchange_gradients(self):
+        """data-parallel gradient mean; with the fused optimiser the 1/world factor is applied inside its kernel."""
+        self.flat.allreduce_mean_(self.group, scale_in_optimizer=self.flat_p is not None)
+
     def apply_gradients(self):
         if self.flat_p is not None:
             from . import ops
-            ops.adam_clip_step(self.flat_p, self.flat.flat, self.exp_avg, self.exp_avg_sq, self.step_count, self.max_norm, self.lr)
+            ops.adam_clip_step(self.flat_p, self.flat.flat, self.exp_avg, self.exp_avg_sq, self.step_count, self.max_norm, self.lr,
+                               grad_scale=1.0 / self._world())
         else:
             self.flat.clip_(self.max_norm)
             self.opt.step()
 
     def step(self, batch, eps=None):
         loss = self.forward_backward(batch, eps)
-        self.flat.allreduce_mean_(self.group)
+        self.exchange_gradients()
         self.apply_gradients()
         return loss
 
@@ -293,7 +304,7 @@ class GraphedTrainStep(object):
         self.load(batch)
         self.graph.replay()
         if self.opt_graph is not None:
-            self.trainer.flat.allreduce_mean_(self.trainer.group)
+            self.trainer.exchange_gradients()
             self.opt_graph.replay()
         return self.loss
 

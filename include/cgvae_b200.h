@@ -242,11 +242,13 @@ int cgvae_lift_bwd(const float* g_xyz, const int64_t* mapping, const int64_t* ra
 /* torch.nn.utils.clip_grad_norm_(params, max_norm) + torch.optim.Adam.step() (scripts/utils.py:151-157) fused over flat
  * buffers p / g / m / v of n floats (train.FlatGrads lays parameters and gradients out contiguously).  `step` is a device
  * float holding the number of steps taken so far (incremented by the call: graph-replay safe); norm_out (nullable)
- * receives the unclipped gradient norm.  The gradient buffer itself is left unscaled.  ws: cgvae_adam_ws_bytes(). */
+ * receives the unclipped gradient norm.  The gradient buffer itself is left unscaled.  grad_scale: the gradients
+ * are taken as grad_scale * g (1/world after a data-parallel all-reduce(sum): saves the separate scaling pass; 1.0f
+ * otherwise).  ws: cgvae_adam_ws_bytes(). */
 size_t cgvae_adam_ws_bytes(void);
-int cgvae_adam_clip_step(float* p, const float* g, float* m, float* v, int64_t n, float max_norm, float lr,
-                         float beta1, float beta2, float eps, float* step, float* norm_out, void* ws, size_t ws_bytes,
-                         cgvae_stream_t stream);
+int cgvae_adam_clip_step(float* p, const float* g, float* m, float* v, int64_t n, float max_norm, float grad_scale,
+                         float lr, float beta1, float beta2, float eps, float* step, float* norm_out, void* ws,
+                         size_t ws_bytes, cgvae_stream_t stream);
 
 /* layout conversion at the module boundary: reference v[N][F][3] <-> planar v[N][3][F] */
 int cgvae_vec_to_planar(const float* v_nf3, int64_t N, int F, float* v_n3f, cgvae_stream_t stream);

@@ -424,6 +424,14 @@ def test_fused_clip_adam_matches_torch():
         want = torch.cat([p.detach().reshape(-1) for p in params_a])
         assert rel_err(flat_p, want) < 1e-6, it
     assert float(step) == 4.0 and n == flat_p.numel()
+    # grad_scale: the data-parallel 1/world factor applied inside the kernel == pre-scaled gradients
+    pa, pb = flat_p.clone(), flat_p.clone()
+    ma, va, mb, vb = m.clone(), v.clone(), m.clone(), v.clone()
+    sa, sb = step.clone(), step.clone()
+    gsum = torch.randn(n, generator=g).to(DEV)
+    ops.adam_clip_step(pa, gsum * 0.25, ma, va, sa, 0.01, 1e-3)
+    ops.adam_clip_step(pb, gsum, mb, vb, sb, 0.01, 1e-3, grad_scale=0.25)
+    assert rel_err(pb, pa) < 1e-6 and rel_err(mb, ma) < 1e-6 and rel_err(vb, va) < 1e-6
 
 
 def test_graphed_train_step_matches_eager():
