@@ -470,3 +470,74 @@ def test_graphed_train_step_matches_eager():
         assert rel_err(pb, pa) < 1e-4, k
     graph_tr.flat.release()
     eager.flat.release()
+
+
+def test_torch_library_ops_match_autograd_nodes():
+    """torch.ops.cgvae_b200.* (torch.library custom ops with fake kernels and registered autograd) give the results of
+    the autograd nodes / raw kernel calls the models use, and pass opcheck's schema / fake-tensor / autograd checks."""
+    from coarsegrainingvae_b200 import functions, torch_ops  # noqa: F401  (registers the ops)
+    T = torch.ops.cgvae_b200
+    g = torch.Generator().manual_seed(21)
+    rn = lambda *sh: torch.randn(*sh, generator=g).to(DEV)
+    # dense vs float64 torch
+    x, W, b = rn(12, 600).requires_grad_(), (rn(1800, 600) * 0.05).requires_grad_(), rn(1800).requires_grad_()
+    gy = rn(12, 1800)
+    y = T.dense(x, W, b)
+    y.backward(gy)
+    xd, Wd, bd = (t.detach().double().requires_grad_() for t in (x, W, b))
+    yd = torch.nn.functional.linear(xd, Wd, bd)
+    yd.backward(gy.double())
+    for got, want in ((y, yd), (x.grad, xd.grad), (W.grad, Wd.grad), (b.grad, bd.grad)):
+        assert rel_err(got, want) < GEMM_TOL
+    # mlp2 == functions.MLP2 (same kernels, same order: bitwise)
+    ps = [rn(36, 600), rn(600, 600) * 0.05, rn(600), rn(1800, 600) * 0.05, rn(1800)]
+    a = [t.clone().requires_grad_() for t in ps]
+    c = [t.clone().requires_grad_() for t in ps]
+    gy = rn(36, 1800)
+    T.mlp2(a[0], a[1], a[2], a[3], a[4], 1)[0].backward(gy)
+    functions.MLP2.apply(1, *c).backward(gy)
+    for u, w in zip(a, c):
+        assert torch.equal(u.grad, w.grad)
+    # message layer (3 and 4 splits) == raw kernel calls
+    n, F, R = 300, 64, 8
+    xyz = rn(n, 3) * 4.0
+    pairs = ops.radius_graph(xyz, 6.0)
+    gr = ops.build_graph(pairs, n, symmetrize=True)
+    geom = ops.edge_geometry(gr, xyz, xyz, R, 6.0)
+    for K in (3, 4):
+        phi, v = rn(n, K, F).requires_grad_(), rn(n, 3, F).requires_grad_()
+        Wf, bf = (rn(K * F, R) * 0.1).requires_grad_(), (rn(K * F) * 0.1).requires_grad_()
+        rs, rv = rn(n, F).requires_grad_(), rn(n, 3, F).requires_grad_()
+        gs, gv = rn(n, F), rn(n, 3, F)
+        o_s, o_v, q = T.message_layer(K, phi, v, gr.rowptr, gr.col, gr.rowptr_t, gr.col_t, gr.perm_t, geom.basis, geom.unit,
+                                      Wf, bf, rs, rv, R)
+        torch.autograd.backward([o_s, o_v], [gs, gv])
+        w_s, w_v, w_q = ops.message_fwd(K, phi.detach(), v.detach(), v.detach() if K == 4 else None, geom, Wf.detach(),
+                                        bf.detach(), rs.detach(), rv.detach(), want_q=(K == 4))
+        assert torch.equal(o_s, w_s) and torch.equal(o_v, w_v)
+        g_phi, g_vs, dWf, dbf = ops.message_bwd(K, phi.detach(), v.detach(), v.detach() if K == 4 else None, w_q, geom,
+                                                Wf.detach(), bf.detach(), gs, gv, False, sink=False)
+        assert torch.equal(phi.grad, g_phi) and torch.equal(v.grad, g_vs)
+        assert torch.equal(Wf.grad, dWf) and torch.equal(bf.grad, dbf)
+        assert torch.equal(rs.grad, gs) and torch.equal(rv.grad, gv)
+    # bead pooling vs index_add
+    mapping = torch.sort(torch.randint(0, 40, (n,), generator=g))[0].to(DEV)
+    seg = ops.build_segments(mapping, 40)
+    X = rn(n, 3, F).requires_grad_()
+    out = T.segment_reduce(X, seg.rowptr, seg.atoms, seg.mapping, True)
+    gout = rn(40, 3, F)
+    out.backward(gout)
+    Xd = X.detach().double().requires_grad_()
+    cnt = torch.bincount(mapping, minlength=40).clamp(min=1).double().view(40, 1, 1)
+    ref = torch.zeros(40, 3, F, dtype=torch.float64, device=DEV).index_add_(0, mapping, Xd) / cnt
+    ref.backward(gout.double())
+    assert rel_err(out, ref) < TOL and rel_err(X.grad, Xd.grad) < TOL
+    # radius graph op == ops.radius_graph
+    assert torch.equal(T.radius_graph(xyz, 6.0, True), pairs)
+    # dispatcher-level checks
+    checks = ("test_schema", "test_faketensor", "test_autograd_registration")
+    torch.library.opcheck(T.dense.default, (x.detach().requires_grad_(), W.detach().requires_grad_(), b.detach().requires_grad_()),
+                          test_utils=checks)
+    torch.library.opcheck(T.segment_reduce.default, (X.detach().requires_grad_(), seg.rowptr, seg.atoms, seg.mapping, True),
+                          test_utils=checks)
+    torch.library.opcheck(T.mlp2.default, tuple(t.detach().requires_grad_() for t in ps) + (1,), test_utils=checks)

@@ -103,3 +103,21 @@ def test_deferred_gradients_merge_bias_into_weight_problem(monkeypatch):
     with ops.DeferredGrads():
         assert ops.deferring(12) and not ops.deferring(ops.DEFER_MAX_ROWS + 1)
     assert len(seen) == 2 and seen[1] == []
+
+
+def test_torch_library_ops_are_registered_and_cuda_only():
+    """torch.ops.cgvae_b200.*: schemas exist, fake kernels give the right shapes without a GPU, CPU tensors are refused
+    (there is no CPU kernel behind the ops)."""
+    import pytest
+    import torch
+    from coarsegrainingvae_b200 import torch_ops
+    for name in torch_ops.OPS:
+        assert hasattr(torch.ops.cgvae_b200, name), name
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    with FakeTensorMode():
+        x, W, b = torch.empty(12, 600, device="cuda"), torch.empty(1800, 600, device="cuda"), torch.empty(1800, device="cuda")
+        assert tuple(torch.ops.cgvae_b200.dense(x, W, b).shape) == (12, 1800)
+        y, a1, z1 = torch.ops.cgvae_b200.mlp2(x, torch.empty(600, 600, device="cuda"), torch.empty(600, device="cuda"), W, b, 1)
+        assert tuple(y.shape) == (12, 1800) and tuple(a1.shape) == (12, 600) == tuple(z1.shape)
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        torch.ops.cgvae_b200.dense(torch.zeros(2, 4), torch.zeros(3, 4), None)
