@@ -314,3 +314,55 @@ def sample_ensemble_member(model, cg_xyz, CG_nbr_list, mapping, num_CGs, H_prior
     """scripts/sampling.py:276-279: H = mu + eps*sigma, then the decoder."""
     H = H_prior_mu + eps * H_prior_sigma
     return model.decoder(cg_xyz, CG_nbr_list, H, H, mapping, num_CGs, graphs=graphs)
+
+
+class GraphedSampler(object):
+    """Ensemble sampling of scripts/sampling.py:265-284 for one conformation shape as ONE CUDA graph: the prior once,
+    then ``n_ensemble`` decoder passes H_m = mu + eps_m * sigma -> decoder.  Sampling is host-launch-bound when issued
+    eagerly (~125 launches of a few microseconds per member); a replay costs one launch per conformation.  Inputs are
+    static-capacity batches from ``to_static_batch`` (CG_nbr_list padded, live count on the device); the noise
+    ``eps [n_ensemble, n_beads, F]`` is an input, so a fixed seed reproduces the reference's geometries member by member.
+    Ensemble members of different conformations are independent: under torchrun each rank samples its own conformations
+    (or members) with no exchange step."""
+
+    def __init__(self, model, example_batch, n_ensemble):
+        self.model, self.n_ensemble = model, int(n_ensemble)
+        self.static = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in example_batch.items()}
+        n_beads = self.static["CG_nxyz"].shape[0]
+        F = model.atom_munet[0].weight.shape[1]
+        dev = self.static["CG_nxyz"].device
+        self.eps = torch.zeros((self.n_ensemble, n_beads, F), dtype=torch.float32, device=dev)
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self._run()
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, stream=side):
+            self.out = self._run()
+        cur.wait_stream(side)
+
+    @torch.no_grad()
+    def _run(self):
+        from .cgvae import BatchGraphs
+        m = self.model
+        z, cg_z, xyz, cg_xyz, nbr, cg_nbr, mapping, num = m.get_inputs(self.static)
+        cg_xyz = cg_xyz.contiguous()
+        graphs = BatchGraphs(None, self.static.get("CG_nbr_count"))
+        mu, sigma = m.prior_net(cg_z, cg_xyz, cg_nbr, graphs=graphs)
+        outs = [sample_ensemble_member(m, cg_xyz, cg_nbr, mapping, num, mu, sigma, self.eps[k], graphs=graphs)
+                for k in range(self.n_ensemble)]
+        return torch.stack(outs)
+
+    def sample(self, batch, eps):
+        """batch: static-capacity dict of one conformation batch; eps [n_ensemble, n_beads, F].  Returns the static output
+        buffer xyz [n_ensemble, n_atoms, 3] (overwritten by the next call)."""
+        for k, v in batch.items():
+            if torch.is_tensor(v):
+                self.static[k].copy_(v, non_blocking=True)
+        self.eps.copy_(eps, non_blocking=True)
+        self.graph.replay()
+        return self.out
+

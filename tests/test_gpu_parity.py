@@ -541,3 +541,31 @@ def test_torch_library_ops_match_autograd_nodes():
     torch.library.opcheck(T.segment_reduce.default, (X.detach().requires_grad_(), seg.rowptr, seg.atoms, seg.mapping, True),
                           test_utils=checks)
     torch.library.opcheck(T.mlp2.default, tuple(t.detach().requires_grad_() for t in ps) + (1,), test_utils=checks)
+
+
+def test_graphed_sampler_matches_eager_members():
+    """train.GraphedSampler (prior + n_ensemble decoder passes of scripts/sampling.py:265-284 as one CUDA graph over
+    static-capacity inputs) reproduces the eager member-by-member geometries for the same noise, for conformations
+    replayed through the SAME graph."""
+    from coarsegrainingvae_b200.factory import build_cgvae
+    from coarsegrainingvae_b200.train import GraphedSampler, sample_ensemble_member, to_static_batch
+    cfg = dict(synthetic.CONFIGS["c1_dipeptide"])
+    cfg.update(batch=2, n_basis=64, enc_nconv=2, dec_nconv=3, cg_cutoff=4.2)       # short CG cutoff: CG edge count varies
+    raw = [synthetic.cgvae_batch(cfg, i, _gpu_radius, cg.CG_collate) for i in range(4)]
+    caps = {"nbr_list": 2 * 22 * 21 // 2, "CG_nbr_list": 6, "bond_edge_list": max(b["bond_edge_list"].shape[0] for b in raw) + 8}
+    static = [_to(to_static_batch(b, caps), DEV) for b in raw]
+    torch.manual_seed(9)
+    model = build_cgvae(cfg["n_basis"], cfg["n_rbf"], 2, 3, cfg["atom_cutoff"], cfg["cg_cutoff"], 3).to(DEV)
+    n_ens = 3
+    sampler = GraphedSampler(model, static[0], n_ens)
+    for i in (1, 2, 3, 0):
+        eps = torch.randn(n_ens, 6, 64, generator=torch.Generator().manual_seed(i)).to(DEV)
+        got = sampler.sample(static[i], eps).clone()
+        b = _to(raw[i], DEV)
+        with torch.no_grad():
+            z, cg_z, xyz, cg_xyz, nbr, cg_nbr, mapping, num = model.get_inputs(b)
+            graphs = cg.BatchGraphs()
+            mu, sig = model.prior_net(cg_z, cg_xyz.contiguous(), cg_nbr, graphs=graphs)
+            want = torch.stack([sample_ensemble_member(model, cg_xyz.contiguous(), cg_nbr, mapping, num, mu, sig, eps[m], graphs=graphs)
+                                for m in range(n_ens)])
+        assert got.shape == want.shape and rel_err(got, want) < 1e-6, i

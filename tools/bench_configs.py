@@ -84,6 +84,29 @@ if "c3" in only:
     ms = timeit(step, 3, 20)
     emit(config="c3_sampling", what="1 prior + 8 decoder passes per conformation (eager launches), chignolin model", ms_per_conformation=ms,
          decoder_passes_per_s=n_ens / ms * 1e3, conformation_members_per_s=n_ens / ms * 1e3)
+    # the same as one CUDA graph per conformation (train.GraphedSampler), noise passed in
+    from coarsegrainingvae_b200.train import GraphedSampler
+    raw = [synthetic.cgvae_batch(cfg, i, rad, cg.CG_collate) for i in range(4)]
+    n, ncg = cfg["n_atoms"], cfg["n_cgs"]
+    caps = {"nbr_list": n * (n - 1) // 2, "CG_nbr_list": ncg * (ncg - 1) // 2,
+            "bond_edge_list": max(b["bond_edge_list"].shape[0] for b in raw) + 64}
+    sconfs = [{k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in to_static_batch(b, caps).items()} for b in raw]
+    sampler = GraphedSampler(model, sconfs[0], n_ens)
+    eps = torch.randn(n_ens, ncg, cfg["n_basis"], device=dev)
+    # same noise, same conformation: graph replay == eager members
+    with torch.no_grad():
+        z, cg_z, xyz, cg_xyz, nbr, cg_nbr, mapping, num = model.get_inputs(confs[1])
+        graphs = cg.BatchGraphs()
+        mu, sig = model.prior_net(cg_z, cg_xyz.contiguous(), cg_nbr, graphs=graphs)
+        want = torch.stack([model.decoder(cg_xyz.contiguous(), cg_nbr, mu + eps[m] * sig, mu + eps[m] * sig, mapping, num, graphs=graphs)
+                            for m in range(n_ens)])
+    got = sampler.sample(sconfs[1], eps).clone()
+    err = float((got - want).abs().max() / want.abs().max())
+    def gstep():
+        sampler.sample(sconfs[it[0] % 4], eps); it[0] += 1
+    ms = timeit(gstep, 3, 30)
+    emit(config="c3_sampling_graph", what="1 prior + 8 decoder passes per conformation as ONE CUDA graph replay (train.GraphedSampler)",
+         ms_per_conformation=ms, decoder_passes_per_s=n_ens / ms * 1e3, max_rel_err_vs_eager=err)
     del model
 
 if "c5" in only:
