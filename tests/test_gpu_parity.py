@@ -550,7 +550,7 @@ def test_graphed_sampler_matches_eager_members():
     from coarsegrainingvae_b200.factory import build_cgvae
     from coarsegrainingvae_b200.train import GraphedSampler, sample_ensemble_member, to_static_batch
     cfg = dict(synthetic.CONFIGS["c1_dipeptide"])
-    cfg.update(batch=2, n_basis=64, enc_nconv=2, dec_nconv=3, cg_cutoff=4.2)       # short CG cutoff: CG edge count varies
+    cfg.update(batch=2, n_basis=64, enc_nconv=2, dec_nconv=3)
     raw = [synthetic.cgvae_batch(cfg, i, _gpu_radius, cg.CG_collate) for i in range(4)]
     caps = {"nbr_list": 2 * 22 * 21 // 2, "CG_nbr_list": 6, "bond_edge_list": max(b["bond_edge_list"].shape[0] for b in raw) + 8}
     static = [_to(to_static_batch(b, caps), DEV) for b in raw]
