@@ -5,7 +5,7 @@
 // GEMMs of 1.4..13 MB each + 56 bias column sums) the step spent 1.2 ms on them -- every launch is a single wave of
 // CTAs whose life is one load -> 12 FMA -> store latency chain (180 GB/s of stores).  The weight gradients do not feed
 // the rest of the backward pass, so the host defers them (ops.py: deferred list) and this kernel produces ALL of them
-// in one launch per 64 problems: the grid is the concatenation of the 64x64 output tiles of every problem, thousands
+// in one launch per 64 problems: the grid is the concatenation of the 64x256 output strips of every problem, thousands
 // of CTAs are in flight and the stores stream at HBM rate.  The problem table travels in the kernel parameters
 // (__grid_constant__, 3.9 KB): no table memory, no copies, CUDA-graph capturable.
 //
@@ -17,6 +17,7 @@ namespace cgvae {
 constexpr int WG_MAXP = 64;   // problems per launch
 constexpr int WG_ROWS = 32;   // rows staged per pass
 constexpr int WG_T = 64;      // output tile edge
+constexpr int WG_STRIP = 4;   // output tiles along n_in per CTA
 
 struct WgradBatch {
   cgvae_wgrad_problem p[WG_MAXP];
@@ -64,28 +65,48 @@ __global__ void __launch_bounds__(256) wgrad_grouped_kernel(const __grid_constan
   float* __restrict__ db = P.db;
   const int rows = P.rows, n_out = P.n_out, n_in = P.n_in, ldg = P.ldg, ldx = P.ldx;
   const bool has_w = (dW != nullptr);
-  const int tiles_k = has_w ? (n_in + WG_T - 1) / WG_T : 1;
+  // a CTA owns a 64 x (WG_STRIP * 64) strip of dW: WG_STRIP output tiles along n_in share one staged gy tile (13 600
+  // one-tile CTAs per chignolin step were bound by CTA turnover, not by the stores)
+  const int strips_k = has_w ? (n_in + WG_STRIP * WG_T - 1) / (WG_STRIP * WG_T) : 1;
   const int t = bid - batch.tile_begin[lo];
-  const int n0 = (t / tiles_k) * WG_T, k0 = (t % tiles_k) * WG_T;
+  const int n0 = (t / strips_k) * WG_T, kstrip = (t % strips_k) * WG_STRIP * WG_T;
   const bool g_vec = ((reinterpret_cast<uintptr_t>(gy) & 15) == 0) && (ldg % 4 == 0);
   const bool x_vec = has_w && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && (ldx % 4 == 0);
+  const bool w_vec = has_w && ((reinterpret_cast<uintptr_t>(dW) & 15) == 0) && (n_in % 4 == 0);
   const int ty = tid >> 4, tx = tid & 15;       // outputs n0 + 4*ty + a, k0 + 4*tx + b
+  const bool one_chunk = rows <= WG_ROWS;       // the gy tile is staged once for the whole strip
 
-  float acc[4][4];
+  if (one_chunk) stage_rows(gs, gy, ldg, 0, rows, n0, n_out, g_vec, tid);
+  if (db != nullptr && kstrip == 0) {
+    // bias gradient: column sums of gy, rows in order
+    float bsum = 0.f;
+    for (int r0 = 0; r0 < rows; r0 += WG_ROWS) {
+      if (!one_chunk) {
+        __syncthreads();
+        stage_rows(gs, gy, ldg, r0, rows, n0, n_out, g_vec, tid);
+      }
+      __syncthreads();
+      const int rn = min(WG_ROWS, rows - r0);
+      if (tid < WG_T)
+        for (int r = 0; r < rn; ++r) bsum += gs[r][tid];
+    }
+    if (tid < WG_T && n0 + tid < n_out) db[n0 + tid] = bsum;
+  }
+  if (!has_w) return;
+  for (int kk = 0; kk < WG_STRIP; ++kk) {
+    const int k0 = kstrip + kk * WG_T;
+    if (k0 >= n_in) break;
+    float acc[4][4];
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < 4; ++a)
 #pragma unroll
-    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
-  float bsum = 0.f;
-  const bool do_bias = (db != nullptr) && k0 == 0;
-
-  for (int r0 = 0; r0 < rows; r0 += WG_ROWS) {
-    if (r0 > 0) __syncthreads();
-    stage_rows(gs, gy, ldg, r0, rows, n0, n_out, g_vec, tid);
-    if (has_w) stage_rows(xs, x, ldx, r0, rows, k0, n_in, x_vec, tid);
-    __syncthreads();
-    const int rn = min(WG_ROWS, rows - r0);
-    if (has_w) {
+      for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+    for (int r0 = 0; r0 < rows; r0 += WG_ROWS) {
+      __syncthreads();                           // previous readers of xs (and of gs when it is re-staged) are done
+      if (!one_chunk) stage_rows(gs, gy, ldg, r0, rows, n0, n_out, g_vec, tid);
+      stage_rows(xs, x, ldx, r0, rows, k0, n_in, x_vec, tid);
+      __syncthreads();
+      const int rn = min(WG_ROWS, rows - r0);
 #pragma unroll 4
       for (int r = 0; r < rn; ++r) {
         const float4 g4 = *reinterpret_cast<const float4*>(&gs[r][4 * ty]);
@@ -97,13 +118,6 @@ __global__ void __launch_bounds__(256) wgrad_grouped_kernel(const __grid_constan
           for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(g[a], xv[b], acc[a][b]);
       }
     }
-    if (do_bias && tid < WG_T) {
-#pragma unroll 4
-      for (int r = 0; r < rn; ++r) bsum += gs[r][tid];
-    }
-  }
-  if (has_w) {
-    const bool w_vec = ((reinterpret_cast<uintptr_t>(dW) & 15) == 0) && (n_in % 4 == 0);
     const int k = k0 + 4 * tx;
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
@@ -119,7 +133,6 @@ __global__ void __launch_bounds__(256) wgrad_grouped_kernel(const __grid_constan
       }
     }
   }
-  if (do_bias && tid < WG_T && n0 + tid < n_out) db[n0 + tid] = bsum;
 }
 
 }  // namespace cgvae
@@ -148,7 +161,7 @@ int cgvae_wgrad_grouped(const cgvae_wgrad_problem* problems, int n_problems, cgv
       batch.p[i] = problems[base + i];
       batch.tile_begin[i] = (int)tiles;
       const cgvae_wgrad_problem& q = batch.p[i];
-      tiles += ceil_div(q.n_out, WG_T) * (q.dW ? ceil_div(q.n_in, WG_T) : 1);
+      tiles += ceil_div(q.n_out, WG_T) * (q.dW ? ceil_div(q.n_in, WG_STRIP * WG_T) : 1);
       CGVAE_REQUIRE(tiles < (int64_t)1 << 30, "wgrad_grouped: too many output tiles");
     }
     for (int i = batch.n; i <= WG_MAXP; ++i) batch.tile_begin[i] = (int)tiles;

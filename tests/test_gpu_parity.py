@@ -569,3 +569,38 @@ def test_graphed_sampler_matches_eager_members():
             want = torch.stack([sample_ensemble_member(model, cg_xyz.contiguous(), cg_nbr, mapping, num, mu, sig, eps[m], graphs=graphs)
                                 for m in range(n_ens)])
         assert got.shape == want.shape and rel_err(got, want) < 1e-6, i
+
+
+@pytest.mark.parametrize("cls,K", [("EquiMessageBlock", 3), ("EquiMessageCross", 4)])
+def test_message_layer_ragged_degrees_vs_oracle(cls, K):
+    """Hand-built directed graph with isolated nodes, in- and out-degrees of exactly 1, 31, 32, 33, 64, 65 (the edge
+    metadata is staged 32 edges at a time per warp) and one hub of degree 150: outputs and all gradients vs the oracle."""
+    n, F, R, cutoff = 200, 64, 8, 9.0
+    g = torch.Generator().manual_seed(41 + K)
+    xyz = torch.rand(n, 3, generator=g) * 5.0
+    degs = {3: 1, 10: 31, 11: 32, 12: 33, 40: 64, 41: 65, 77: 150}            # receiver -> in-degree; the rest: 0
+    recv, send = [], []
+    for i, d in degs.items():
+        others = [j for j in range(n) if j != i]
+        perm = torch.randperm(len(others), generator=g)[:d].tolist()
+        for q in sorted(perm):
+            recv.append(i); send.append(others[q])
+    nbrs = torch.tensor([recv, send], dtype=torch.int64).t().contiguous()      # directed as given (not symmetrised)
+    nbrs = torch.cat([nbrs, nbrs.flip(1)], 0)                                  # + reversed edges: ragged out-degrees too
+    s0, v0 = torch.randn(n, F, generator=g), torch.randn(n, F, 3, generator=g)
+    torch.manual_seed(3)
+    blk = getattr(cg, cls)(feat_dim=F, activation="swish", n_rbf=R, cutoff=cutoff, dropout=0.0).to(DEV)
+    r = (xyz[nbrs[:, 1]] - xyz[nbrs[:, 0]]).to(DEV)
+    s, v = s0.to(DEV).requires_grad_(), v0.to(DEV).requires_grad_()
+    ds, dv = blk(s, v, r, nbrs.to(DEV))
+    (ds.sum() + (dv * dv).sum()).backward()
+    P = pc._oracle_params(blk, "blk.")
+    so, vo = s0.clone().requires_grad_(), v0.clone().requires_grad_()
+    fn_o = orc.equi_message if K == 3 else orc.equi_message_cross
+    ods, odv = fn_o(P, "blk", so, vo, r.cpu(), nbrs, R, cutoff)
+    (ods.sum() + (odv * odv).sum()).backward()
+    assert rel_err(ds, ods) < TOL and rel_err(dv, odv) < TOL
+    assert rel_err(s.grad, so.grad) < TOL and rel_err(v.grad, vo.grad) < TOL
+    isolated = [i for i in range(n) if i not in degs and i not in set(send)]
+    assert isolated and float(ds[isolated].abs().max()) == 0.0 and float(dv[isolated].abs().max()) == 0.0
+    pc._check_grads(blk, P, TOL, "blk.")
