@@ -408,7 +408,7 @@ def run_cuda(args, cfg):
                     graph_time_ms(replay_gemms), len(calls), float(sum(4.0 * m["N"] * m["K"] for m in calls)),
                     "bytes = the weight matrix once per launch; the %d launches of one step replayed back to back in a CUDA graph" % len(calls)))
     if tables:
-        n_launch = sum((len(tb) + 63) // 64 for tb in tables)
+        n_launch = sum((len(tb) + ops.WGRAD_PROBLEMS_PER_LAUNCH - 1) // ops.WGRAD_PROBLEMS_PER_LAUNCH for tb in tables)
         iso.append(("wgrad_grouped", "wgrad_grouped_kernel (all small-graph weight / bias gradients of the step)",
                     graph_time_ms(replay_wgrad), n_launch,
                     float(sum(4.0 * ((p[2].numel() if p[2] is not None else 0) + (p[3].numel() if p[3] is not None else 0))

@@ -14,7 +14,7 @@
 
 namespace cgvae {
 
-constexpr int WG_MAXP = 64;   // problems per launch
+constexpr int WG_MAXP = 48;   // problems per launch (72-byte entries: the table stays below the 4 KB parameter space)
 constexpr int WG_ROWS = 32;   // rows staged per pass
 constexpr int WG_T = 64;      // output tile edge
 constexpr int WG_STRIP = 4;   // output tiles along n_in per CTA
@@ -26,15 +26,25 @@ struct WgradBatch {
 };
 static_assert(sizeof(WgradBatch) <= 4000, "problem table must fit the 4 KB kernel parameter space");
 
+// Row R of an operand: one [rows x cols] matrix, or -- seg_rows > 0 -- the row-wise concatenation of several such
+// matrices that live seg_stride elements apart (the all-gathered factors of the data-parallel ranks: dW = sum over ranks
+// of gy_r^T x_r is ONE contraction over world * rows rows, in rank order).
 __device__ __forceinline__ void stage_rows(float (*dst)[WG_T], const float* __restrict__ src, int ld, int r0, int rows,
-                                           int c0, int ncols, bool vec, int tid) {
-  // dst[r][c] = src[(r0+r)*ld + c0 + c] for r0 + r < rows (at most WG_ROWS of them), c < 64; zero for c0 + c >= ncols
+                                           int c0, int ncols, bool vec, int tid, int seg_rows, int64_t seg_stride) {
+  // dst[r][c] = row (r0+r), column c0 + c for r0 + r < rows (at most WG_ROWS of them), c < 64; zero for c0 + c >= ncols
   const int rn = min(WG_ROWS, rows - r0);
   for (int idx = tid; idx < rn * (WG_T / 4); idx += 256) {
     const int r = idx / (WG_T / 4), c = 4 * (idx % (WG_T / 4));
     float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
     {
-      const float* q = src + (int64_t)(r0 + r) * ld + c0 + c;
+      const int R = r0 + r;
+      const float* q;
+      if (seg_rows > 0) {
+        const int sgm = R / seg_rows;
+        q = src + (int64_t)sgm * seg_stride + (int64_t)(R - sgm * seg_rows) * ld + c0 + c;
+      } else {
+        q = src + (int64_t)R * ld + c0 + c;
+      }
       if (vec && c0 + c + 3 < ncols) {
         val = __ldg(reinterpret_cast<const float4*>(q));
       } else {
@@ -63,27 +73,28 @@ __global__ void __launch_bounds__(256) wgrad_grouped_kernel(const __grid_constan
   const float* __restrict__ x = P.x;
   float* __restrict__ dW = P.dW;
   float* __restrict__ db = P.db;
-  const int rows = P.rows, n_out = P.n_out, n_in = P.n_in, ldg = P.ldg, ldx = P.ldx;
+  const int rows = P.rows, n_out = P.n_out, n_in = P.n_in, ldg = P.ldg, ldx = P.ldx, seg_rows = P.seg_rows;
+  const int64_t sg = P.seg_stride_g, sx = P.seg_stride_x;
   const bool has_w = (dW != nullptr);
   // a CTA owns a 64 x (WG_STRIP * 64) strip of dW: WG_STRIP output tiles along n_in share one staged gy tile (13 600
   // one-tile CTAs per chignolin step were bound by CTA turnover, not by the stores)
   const int strips_k = has_w ? (n_in + WG_STRIP * WG_T - 1) / (WG_STRIP * WG_T) : 1;
   const int t = bid - batch.tile_begin[lo];
   const int n0 = (t / strips_k) * WG_T, kstrip = (t % strips_k) * WG_STRIP * WG_T;
-  const bool g_vec = ((reinterpret_cast<uintptr_t>(gy) & 15) == 0) && (ldg % 4 == 0);
-  const bool x_vec = has_w && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && (ldx % 4 == 0);
+  const bool g_vec = ((reinterpret_cast<uintptr_t>(gy) & 15) == 0) && (ldg % 4 == 0) && (seg_rows == 0 || sg % 4 == 0);
+  const bool x_vec = has_w && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && (ldx % 4 == 0) && (seg_rows == 0 || sx % 4 == 0);
   const bool w_vec = has_w && ((reinterpret_cast<uintptr_t>(dW) & 15) == 0) && (n_in % 4 == 0);
   const int ty = tid >> 4, tx = tid & 15;       // outputs n0 + 4*ty + a, k0 + 4*tx + b
   const bool one_chunk = rows <= WG_ROWS;       // the gy tile is staged once for the whole strip
 
-  if (one_chunk) stage_rows(gs, gy, ldg, 0, rows, n0, n_out, g_vec, tid);
+  if (one_chunk) stage_rows(gs, gy, ldg, 0, rows, n0, n_out, g_vec, tid, seg_rows, sg);
   if (db != nullptr && kstrip == 0) {
     // bias gradient: column sums of gy, rows in order
     float bsum = 0.f;
     for (int r0 = 0; r0 < rows; r0 += WG_ROWS) {
       if (!one_chunk) {
         __syncthreads();
-        stage_rows(gs, gy, ldg, r0, rows, n0, n_out, g_vec, tid);
+        stage_rows(gs, gy, ldg, r0, rows, n0, n_out, g_vec, tid, seg_rows, sg);
       }
       __syncthreads();
       const int rn = min(WG_ROWS, rows - r0);
@@ -103,8 +114,8 @@ __global__ void __launch_bounds__(256) wgrad_grouped_kernel(const __grid_constan
       for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
     for (int r0 = 0; r0 < rows; r0 += WG_ROWS) {
       __syncthreads();                           // previous readers of xs (and of gs when it is re-staged) are done
-      if (!one_chunk) stage_rows(gs, gy, ldg, r0, rows, n0, n_out, g_vec, tid);
-      stage_rows(xs, x, ldx, r0, rows, k0, n_in, x_vec, tid);
+      if (!one_chunk) stage_rows(gs, gy, ldg, r0, rows, n0, n_out, g_vec, tid, seg_rows, sg);
+      stage_rows(xs, x, ldx, r0, rows, k0, n_in, x_vec, tid, seg_rows, sx);
       __syncthreads();
       const int rn = min(WG_ROWS, rows - r0);
 #pragma unroll 4
@@ -151,6 +162,8 @@ int cgvae_wgrad_grouped(const cgvae_wgrad_problem* problems, int n_problems, cgv
     CGVAE_REQUIRE(!q.dW || q.x, "wgrad_grouped: problem %d: dW without x", i);
     CGVAE_REQUIRE(q.rows >= 0 && q.n_out >= 1 && q.ldg >= q.n_out, "wgrad_grouped: problem %d: bad gy shape", i);
     CGVAE_REQUIRE(!q.dW || (q.n_in >= 1 && q.ldx >= q.n_in), "wgrad_grouped: problem %d: bad x shape", i);
+    CGVAE_REQUIRE(q.seg_rows >= 0 && (q.seg_rows == 0 || q.rows % q.seg_rows == 0),
+                  "wgrad_grouped: problem %d: rows must be a multiple of seg_rows", i);
   }
   cudaStream_t st = (cudaStream_t)stream;
   for (int base = 0; base < n_problems; base += WG_MAXP) {

@@ -407,7 +407,7 @@ def linear_bwd_input(gy, W, z_in=None, dact=0, add=None):
 # rows) cost as much as writing them; one launch per layer cannot keep enough stores in flight (1.2 ms per chignolin
 # step in 92 + 56 launches).  Nothing in the backward pass reads them, so while a DeferredGrads scope is open
 # (train.TrainStep opens one around loss.backward() when gradient sinks are registered) they are only RECORDED, and
-# flush() produces all of them with cgvae_wgrad_grouped: one launch per 64 problems.  The recorded operands stay
+# flush() produces all of them with cgvae_wgrad_grouped: one launch per 48 problems.  The recorded operands stay
 # referenced until the flush, which is enqueued on the stream the backward ran on.
 DEFER_MAX_ROWS = 128
 _DEFERRED = None
@@ -417,7 +417,17 @@ def deferring(rows):
     return _DEFERRED is not None and rows <= DEFER_MAX_ROWS
 
 
+WGRAD_PROBLEMS_PER_LAUNCH = 48
+
+
 class DeferredGrads(object):
+    """flush=True: the grouped launch is issued when the scope closes.  flush=False: the merged problem list is left in
+    ``self.pending`` for the caller (data-parallel training gathers the FACTORS of all ranks first, train.TrainStep)."""
+
+    def __init__(self, flush=True):
+        self.flush = flush
+        self.pending = []
+
     def __enter__(self):
         global _DEFERRED
         if _DEFERRED is not None:
@@ -429,7 +439,9 @@ class DeferredGrads(object):
         global _DEFERRED
         pending, _DEFERRED = _DEFERRED, None
         if exc_type is None:
-            flush_deferred(pending)
+            self.pending = merge_deferred(pending)
+            if self.flush:
+                wgrad_grouped(self.pending)
         return False
 
 
@@ -442,18 +454,15 @@ def _wgrad_dtype():
         import numpy as np
         _WGRAD_DTYPE = np.dtype([("gy", np.uint64), ("x", np.uint64), ("dW", np.uint64), ("db", np.uint64),
                                  ("rows", np.int32), ("n_out", np.int32), ("n_in", np.int32), ("ldg", np.int32),
-                                 ("ldx", np.int32), ("reserved", np.int32)], align=True)
-        assert _WGRAD_DTYPE.itemsize == 56
+                                 ("ldx", np.int32), ("seg_rows", np.int32), ("seg_stride_g", np.int64),
+                                 ("seg_stride_x", np.int64)], align=True)
+        assert _WGRAD_DTYPE.itemsize == 72
     return _WGRAD_DTYPE
 
 
-def wgrad_grouped(problems):
-    """problems: list of (gy [rows,n_out], x [rows,n_in] or None, dW [n_out,n_in] or None, db [n_out] or None);
-    cgvae_wgrad_grouped: every dW = gy^T x and db = colsum(gy) in one launch per 64 problems."""
-    if not problems:
-        return
+def wgrad_table(problems):
+    """numpy table (struct cgvae_wgrad_problem) of a list of (gy [rows,n_out], x [rows,n_in] or None, dW or None, db or None)."""
     import numpy as np
-    lib = _lib.load()
     table = np.zeros(len(problems), dtype=_wgrad_dtype())
     for i, (gy, x, dW, db) in enumerate(problems):
         _need_cuda(gy)
@@ -463,17 +472,33 @@ def wgrad_grouped(problems):
             raise ValueError("wgrad_grouped: dW must be contiguous")
         table[i] = (gy.data_ptr(), x.data_ptr() if x is not None else 0, dW.data_ptr() if dW is not None else 0,
                     db.data_ptr() if db is not None else 0, gy.shape[0], gy.shape[1], x.shape[1] if x is not None else 0,
-                    gy.stride(0), x.stride(0) if x is not None else 0, 0)
+                    gy.stride(0), x.stride(0) if x is not None else 0, 0, 0, 0)
+    return table
+
+
+def wgrad_grouped_table(table, out_floats=0, keep=None):
+    """launch cgvae_wgrad_grouped on a prepared table (device pointers inside; the table itself is host memory)."""
+    if len(table) == 0:
+        return
+    lib = _lib.load()
     t0 = TIMER.begin("wgrad_grouped") if TIMER is not None else None
-    _lib.check(lib.cgvae_wgrad_grouped(table.ctypes.data, len(problems), _stream()), "wgrad_grouped")
+    _lib.check(lib.cgvae_wgrad_grouped(table.ctypes.data, len(table), _stream()), "wgrad_grouped")
     if t0 is not None:
-        TIMER.end("wgrad_grouped", t0, dict(problems=len(problems), table=(list(problems) if TIMER.keep_operands else None),
-                                           out_floats=sum((p[2].numel() if p[2] is not None else 0) +
-                                                          (p[3].numel() if p[3] is not None else 0) for p in problems)))
+        TIMER.end("wgrad_grouped", t0, dict(problems=len(table), table=(keep if TIMER.keep_operands else None),
+                                           out_floats=out_floats))
 
 
-def flush_deferred(pending):
-    """merge the bias problem of a layer into its weight problem (same gy) and launch."""
+def wgrad_grouped(problems):
+    """problems: list of (gy [rows,n_out], x [rows,n_in] or None, dW [n_out,n_in] or None, db [n_out] or None);
+    cgvae_wgrad_grouped: every dW = gy^T x and db = colsum(gy) in one launch per 48 problems."""
+    if not problems:
+        return
+    out_floats = sum((p[2].numel() if p[2] is not None else 0) + (p[3].numel() if p[3] is not None else 0) for p in problems)
+    wgrad_grouped_table(wgrad_table(problems), out_floats, list(problems))
+
+
+def merge_deferred(pending):
+    """merge the bias problem of a layer into its weight problem (same gy)."""
     merged, by_gy = [], {}
     for gy, x, dW, db in pending:
         key = (gy.data_ptr(), gy.shape[0], gy.shape[1], gy.stride(0))
@@ -485,7 +510,12 @@ def flush_deferred(pending):
             continue
         by_gy[key] = len(merged)
         merged.append((gy, x, dW, db))
-    wgrad_grouped(merged)
+    return merged
+
+
+def flush_deferred(pending):
+    """merge and launch."""
+    wgrad_grouped(merge_deferred(pending))
 
 
 def linear_bwd_weight(gy, x, param=None):

@@ -135,6 +135,13 @@ class TrainStep(object):
         self.flat_p = self.exp_avg = self.exp_avg_sq = self.step_count = None
         import os
         self.defer_grads = os.environ.get("CGVAE_DEFER_WGRAD", "1") != "0"
+        # data parallel: exchange the FACTORS of the deferred weight gradients (all-gather of ~20 MB) instead of the
+        # gradients themselves (all-reduce of 222 MB at chignolin): dW = sum_r gy_r^T x_r is one contraction over the
+        # rows of all ranks.  Needs the fused optimiser layout (deferred parameters at the end of the flat buffers).
+        self.gather_factors = os.environ.get("CGVAE_GATHER_FACTORS", "1") != "0"
+        self.n_reduce = None            # floats at the head of the flat gradient buffer that still need the all-reduce
+        self._arena = self._gathered = self._factor_table = None
+        self._factor_layout = None
 
     def _loss(self, batch, eps):
         out = self.model(batch, eps=eps) if eps is not None else self.model(batch)
@@ -146,6 +153,10 @@ class TrainStep(object):
         used = used_parameters(self.model, lambda: self._loss(batch, eps).backward())
         params = [p for _, p in used]
         on_cuda = bool(params) and params[0].is_cuda
+        self.gather_factors = bool(self.gather_factors and on_cuda and self.optimizer == "fused" and self.defer_grads
+                                   and self._world() > 1)
+        if self.gather_factors:
+            params = self._deferred_last(params, batch, eps)
         if on_cuda and self.optimizer == "fused":
             # parameters of the used set become views of ONE buffer (same order as the gradient buffer): the optimiser
             # is then a single streaming pass.  Must happen before FlatGrads registers the sinks (keyed by data_ptr).
@@ -170,28 +181,113 @@ class TrainStep(object):
                 raise RuntimeError("gradient sink views were not adopted by autograd")
         return [k for k, _ in used]
 
+    def _deferred_last(self, params, batch, eps):
+        """order the used parameters so that those whose gradients come from the deferred grouped launch sit at the END of
+        the flat buffers: the head [0, n_reduce) is what the data-parallel all-reduce still has to cover."""
+        from . import ops
+        probe = FlatGrads(params)
+        try:
+            loss = self._loss(batch, eps)
+            with ops.DeferredGrads(flush=False) as scope:
+                loss.backward()
+            base = probe.flat.data_ptr()
+            deferred_offsets = set()
+            for _, _, dW, db in scope.pending:
+                for t in (dW, db):
+                    if t is not None:
+                        deferred_offsets.add((t.data_ptr() - base) // 4)
+            head, tail = [], []
+            for p, (off, _) in zip(probe.params, probe.views):
+                (tail if off in deferred_offsets else head).append(p)
+        finally:
+            probe.release()
+            for p in params:
+                p.grad = None
+        self.n_reduce = sum(p.numel() for p in head)
+        return head + tail
+
     def forward_backward(self, batch, eps=None):
         self.flat.zero_()
         loss = self._loss(batch, eps)
         if self.flat.sink and self.defer_grads:
             from . import ops
-            with ops.DeferredGrads():      # small-graph weight / bias gradients: recorded, then ONE grouped launch
-                loss.backward()
+            if self.gather_factors:        # recorded only: the factors are packed for the all-gather, the grouped
+                with ops.DeferredGrads(flush=False) as scope:      # launch follows the exchange (apply_gradients)
+                    loss.backward()
+                self._pack_factors(scope.pending)
+            else:
+                with ops.DeferredGrads():  # small-graph weight / bias gradients: recorded, then ONE grouped launch
+                    loss.backward()
         else:
             loss.backward()
         return loss
+
+    def _pack_factors(self, pending):
+        """copy gy / x of every deferred problem into one contiguous arena (one torch.cat) in a fixed layout; on the first
+        call allocate the arena, the all-gather destination and the problem table over the gathered rows."""
+        import numpy as np
+        from . import ops
+        world = self._world()
+        dev = self.flat.flat.device
+        if getattr(self, "_pad", None) is None:
+            self._pad = torch.zeros(4, dtype=torch.float32, device=dev)
+        pieces, layout, off = [], [], 0
+
+        def add(t):
+            nonlocal off
+            start = off
+            pieces.append(t.contiguous().view(-1))          # strided views (basis columns) are compacted here
+            off += t.numel()
+            if off % 4:                                      # keep every piece 16-byte aligned inside the arena
+                pieces.append(self._pad[:4 - off % 4])
+                off += 4 - off % 4
+            return start
+
+        for gy, x, dW, db in pending:
+            rows, n_out = gy.shape
+            n_in = x.shape[1] if x is not None else 0
+            g_off = add(gy)
+            x_off = add(x) if x is not None else 0
+            layout.append((rows, n_out, n_in, g_off, x_off, dW.data_ptr() if dW is not None else 0,
+                           db.data_ptr() if db is not None else 0))
+        if self._factor_layout is None:
+            self._factor_layout = layout
+            L = off
+            self._arena = torch.zeros(L, dtype=torch.float32, device=dev)
+            self._gathered = torch.zeros(world * L, dtype=torch.float32, device=dev)
+            table = np.zeros(len(layout), dtype=ops._wgrad_dtype())
+            base = self._gathered.data_ptr()
+            for i, (rows, n_out, n_in, g_off, x_off, dW_ptr, db_ptr) in enumerate(layout):
+                table[i] = (base + 4 * g_off, (base + 4 * x_off) if n_in else 0, dW_ptr, db_ptr, rows * world, n_out, n_in,
+                            n_out, n_in, rows, L, L)
+            self._factor_table = table
+            self._factor_out_floats = sum(n_out * n_in + n_out for _, n_out, n_in, _, _, _, _ in layout)
+        elif layout != self._factor_layout:
+            raise RuntimeError("deferred-gradient layout changed between steps (shapes must be static for data-parallel "
+                               "factor exchange; set CGVAE_GATHER_FACTORS=0)")
+        if pieces:
+            torch.cat(pieces, out=self._arena)               # one batched copy kernel per 128 pieces
 
     def _world(self):
         import torch.distributed as dist
         return dist.get_world_size(self.group) if (dist.is_available() and dist.is_initialized()) else 1
 
     def exchange_gradients(self):
-        """data-parallel gradient mean; with the fused optimiser the 1/world factor is applied inside its kernel."""
+        """data-parallel gradient mean; with the fused optimiser the 1/world factor is applied inside its kernel.  With
+        factor exchange: all-reduce of the head of the gradient buffer + all-gather of the packed factors."""
+        if self.gather_factors:
+            import torch.distributed as dist
+            if self.n_reduce:
+                dist.all_reduce(self.flat.flat[:self.n_reduce], op=dist.ReduceOp.SUM, group=self.group)
+            dist.all_gather_into_tensor(self._gathered, self._arena, group=self.group)
+            return
         self.flat.allreduce_mean_(self.group, scale_in_optimizer=self.flat_p is not None)
 
     def apply_gradients(self):
         if self.flat_p is not None:
             from . import ops
+            if self.gather_factors:        # every rank forms the SUM over ranks of the deferred gradients itself
+                ops.wgrad_grouped_table(self._factor_table, self._factor_out_floats)
             ops.adam_clip_step(self.flat_p, self.flat.flat, self.exp_avg, self.exp_avg_sq, self.step_count, self.max_norm, self.lr,
                                grad_scale=1.0 / self._world())
         else:

@@ -140,16 +140,20 @@ int cgvae_colsum(const float* X, int64_t ldx, int64_t M, int64_t N, float* out, 
  * nn.Linear for the 12..96-row decoder graphs): for every problem
  *   dW[n_out][n_in] = gy[rows][n_out]^T x[rows][n_in]   (dW contiguous; skipped when dW == NULL)
  *   db[n_out]       = column sums of gy                 (skipped when db == NULL)
- * All problems of the table are produced by ONE launch per 64 problems (the cost is writing dW, and one
+ * All problems of the table are produced by ONE launch per 48 problems (the cost is writing dW, and one
  * launch per layer cannot keep enough stores in flight).  `problems` is a HOST array (the table is
  * passed to the device in the kernel parameters; it may be freed when the call returns); the pointers
- * inside are device pointers.  Row sums run in row order: deterministic. */
+ * inside are device pointers.  Row sums run in row order: deterministic.
+ * seg_rows > 0: the operands are row-wise concatenations of rows / seg_rows matrices of seg_rows rows each, lying
+ * seg_stride_g / seg_stride_x ELEMENTS apart -- the all-gathered factors of data-parallel ranks: the sum over ranks
+ * of the per-rank gradients gy_r^T x_r is one contraction over all rows, in rank order (no gradient all-reduce). */
 typedef struct cgvae_wgrad_problem {
   const float* gy;   /* [rows][n_out], row stride ldg */
   const float* x;    /* [rows][n_in], row stride ldx; may be NULL when dW is NULL */
   float* dW;         /* [n_out][n_in] contiguous, or NULL */
   float* db;         /* [n_out], or NULL */
-  int32_t rows, n_out, n_in, ldg, ldx, reserved;
+  int32_t rows, n_out, n_in, ldg, ldx, seg_rows;
+  int64_t seg_stride_g, seg_stride_x;
 } cgvae_wgrad_problem;
 int cgvae_wgrad_grouped(const cgvae_wgrad_problem* problems, int n_problems, cgvae_stream_t stream);
 

@@ -373,7 +373,7 @@ def test_train_step_gradient_sink_matches_plain_autograd():
 
 def test_wgrad_grouped_vs_float64():
     """cgvae_wgrad_grouped: every dW = gy^T x and db = colsum(gy) of a table of ragged problems (odd sizes, strided
-    operands, bias-only and weight-only entries, more than one 64-problem launch) against float64."""
+    operands, bias-only and weight-only entries, more than one launch) against float64."""
     g = torch.Generator().manual_seed(11)
     shapes = [(12, 600, 600), (12, 5400, 600), (36, 600, 600), (1, 7, 5), (60, 5400, 10), (97, 130, 77), (33, 64, 64),
               (128, 200, 36), (12, 1800, 1200)] + [(5 + i % 9, 17 + 3 * i, 9 + 5 * i) for i in range(70)]
@@ -389,7 +389,7 @@ def test_wgrad_grouped_vs_float64():
         want.append((gy.double().t() @ x.double(), gy.double().sum(0)))
     before = ops.launch_count()
     ops.wgrad_grouped(problems)
-    assert ops.launch_count() - before == (len(problems) + 63) // 64
+    assert ops.launch_count() - before == (len(problems) + ops.WGRAD_PROBLEMS_PER_LAUNCH - 1) // ops.WGRAD_PROBLEMS_PER_LAUNCH
     for (gy, x, dW, db), (w_ref, b_ref) in zip(problems, want):
         if dW is not None:
             assert rel_err(dW, w_ref) < GEMM_TOL, (tuple(gy.shape), tuple(dW.shape))
