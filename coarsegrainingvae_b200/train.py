@@ -236,7 +236,7 @@ class TrainStep(object):
         def add(t):
             nonlocal off
             start = off
-            pieces.append(t.contiguous().view(-1))          # strided views (basis columns) are compacted here
+            pieces.append(t.detach().contiguous().view(-1))  # strided views (basis columns) are compacted here
             off += t.numel()
             if off % 4:                                      # keep every piece 16-byte aligned inside the arena
                 pieces.append(self._pad[:4 - off % 4])
@@ -266,7 +266,8 @@ class TrainStep(object):
             raise RuntimeError("deferred-gradient layout changed between steps (shapes must be static for data-parallel "
                                "factor exchange; set CGVAE_GATHER_FACTORS=0)")
         if pieces:
-            torch.cat(pieces, out=self._arena)               # one batched copy kernel per 128 pieces
+            with torch.no_grad():
+                torch.cat(pieces, out=self._arena)           # one batched copy kernel per 128 pieces
 
     def _world(self):
         import torch.distributed as dist
