@@ -138,7 +138,11 @@ class TrainStep(object):
         # data parallel: exchange the FACTORS of the deferred weight gradients (all-gather of ~20 MB) instead of the
         # gradients themselves (all-reduce of 222 MB at chignolin): dW = sum_r gy_r^T x_r is one contraction over the
         # rows of all ranks.  Needs the fused optimiser layout (deferred parameters at the end of the flat buffers).
-        self.gather_factors = os.environ.get("CGVAE_GATHER_FACTORS", "1") != "0"
+        # Measured on 2 x B200 (tools/check_ddp.py): all-reduce 24 MB + all-gather 32 MB per rank instead of an all-reduce
+        # of 270 MB, 3.99 vs 4.16 ms per step.  The gathered volume grows with the world size (8 ranks: 258 MB received,
+        # 8x the rows in the grouped kernel) while a ring all-reduce does not, so "auto" enables it for 2 ranks only;
+        # CGVAE_GATHER_FACTORS=1 / 0 forces / disables it.
+        self.gather_factors = os.environ.get("CGVAE_GATHER_FACTORS", "auto")
         self.n_reduce = None            # floats at the head of the flat gradient buffer that still need the all-reduce
         self._arena = self._gathered = self._factor_table = None
         self._factor_layout = None
@@ -153,8 +157,9 @@ class TrainStep(object):
         used = used_parameters(self.model, lambda: self._loss(batch, eps).backward())
         params = [p for _, p in used]
         on_cuda = bool(params) and params[0].is_cuda
-        self.gather_factors = bool(self.gather_factors and on_cuda and self.optimizer == "fused" and self.defer_grads
-                                   and self._world() > 1)
+        want = self.gather_factors
+        want = (self._world() == 2) if want == "auto" else (want not in ("0", False, None))
+        self.gather_factors = bool(want and on_cuda and self.optimizer == "fused" and self.defer_grads and self._world() > 1)
         if self.gather_factors:
             params = self._deferred_last(params, batch, eps)
         if on_cuda and self.optimizer == "fused":

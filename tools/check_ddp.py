@@ -69,7 +69,7 @@ print("rank %d: exchanged gradients == all-reduced plain gradients, worst rel er
 
 # ---- (2) + (3) graphed steps in both modes
 for mode in ("1", "0"):
-    os.environ["CGVAE_GATHER_FACTORS"] = mode
+    os.environ["CGVAE_GATHER_FACTORS"] = mode          # "1" forces the factor exchange at any world size
     m = make()
     t = TrainStep(m, cfg["beta"], cfg["gamma"], capturable=True)
     t.prepare(batches[0], eps)
@@ -95,13 +95,14 @@ for mode in ("1", "0"):
         print("gather_factors=%s: %.3f ms per step (max over ranks), loss %.5f, parameters identical on all ranks: %s" %
               (mode, float(ms), float(loss), same), flush=True)
     assert same and torch.isfinite(loss)
+    named = {k: p.detach().clone() for k, p in m.named_parameters()}      # by NAME: the two modes order the flat buffer differently
     if mode == "1":
-        p_gather = flat.clone()
+        p_gather = named
     else:
-        rel = float((flat - p_gather).abs().max() / flat.abs().max())
+        rel = max(float((named[k] - p_gather[k]).abs().max() / named[k].abs().max().clamp_min(1e-30)) for k in named)
         if rank == 0:
             print("parameters after 25 steps, factor exchange vs full all-reduce: max rel diff %.2e" % rel, flush=True)
-        assert rel < 1e-4
+        assert rel < 1e-3
     t.flat.release()
 dist.barrier()
 dist.destroy_process_group()
