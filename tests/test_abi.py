@@ -66,3 +66,33 @@ def test_argument_errors_are_reported_without_a_gpu():
     assert rc < 0 and "n_split" in _lib.last_error()
     with pytest.raises(RuntimeError):
         _lib.check(rc, "message_fwd")
+
+
+def test_wgrad_problem_table_layout_matches_header_struct():
+    """ops builds the problem table of cgvae_wgrad_grouped as a numpy struct array: it must be byte-compatible with
+    `struct cgvae_wgrad_problem` of the header (4 pointers, 6 int32, 2 int64 = 72 bytes, natural alignment)."""
+    import ctypes
+    import re
+    from coarsegrainingvae_b200 import _lib, ops
+
+    class Problem(ctypes.Structure):
+        _fields_ = [("gy", ctypes.c_void_p), ("x", ctypes.c_void_p), ("dW", ctypes.c_void_p), ("db", ctypes.c_void_p),
+                    ("rows", ctypes.c_int32), ("n_out", ctypes.c_int32), ("n_in", ctypes.c_int32), ("ldg", ctypes.c_int32),
+                    ("ldx", ctypes.c_int32), ("seg_rows", ctypes.c_int32), ("seg_stride_g", ctypes.c_int64),
+                    ("seg_stride_x", ctypes.c_int64)]
+
+    with open(_lib.HEADER_PATH) as fh:
+        text = fh.read()
+    body = re.search(r"typedef struct cgvae_wgrad_problem \{(.*?)\} cgvae_wgrad_problem;", text, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if decl:
+            names += [n.strip().lstrip("*") for n in decl.split(",")]
+            names[-len(decl.split(",")):] = [re.split(r"[\s\*]+", n.strip())[-1] for n in decl.split(",")]
+    assert names == [f[0] for f in Problem._fields_]
+    dt = ops._wgrad_dtype()
+    assert dt.itemsize == ctypes.sizeof(Problem) == 72
+    for name, _ in Problem._fields_:
+        assert dt.fields[name][1] == getattr(Problem, name).offset, name
