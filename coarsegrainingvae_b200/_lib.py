@@ -37,6 +37,7 @@ SIGNATURES = {
     "cgvae_segment_rank": (_INT, [_P, _I64, _I64, _P, _P, _P, _P, _P, _P]),
     "cgvae_edge_geometry": (_INT, [_P, _P, _P, _P, _P, _I64, _I64, _P, _INT, _INT, _F32, _P, _P, _P, _P, _P]),
     "cgvae_gemm": (_INT, [_INT, _P, _I64, _P, _I64, _P, _I64, _I64, _I64, _I64, _P, _INT, _P, _P, _INT, _P, _P, _SZ, _P, _INT, _P]),
+    "cgvae_dense_pair_fwd": (_INT, [_P, _I64, _P, _I64, _I64, _I64, _I64, _I64, _P, _P, _P]),
     "cgvae_colsum": (_INT, [_P, _I64, _I64, _I64, _P, _P]),
     "cgvae_wgrad_grouped": (_INT, [_P, _INT, _P]),
     "cgvae_message_fwd": (_INT, [_INT, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _INT, _INT, _INT, _P, _P, _INT,

@@ -772,9 +772,29 @@ int launch_gemm_stream(int form, const float* A, int64_t lda, const float* B, in
                        const float* add, cudaStream_t st);
 }
 
+namespace cgvae {
+int launch_dense_pair_stream(const float* X, int64_t ldx, const float* W, int64_t ldw, float* C1, int64_t ldc1, float* C2,
+                             int64_t ldc2, int64_t M, int64_t N1, int64_t N2, int64_t K, cudaStream_t st);
+}
+
 using namespace cgvae;
 
 extern "C" {
+
+int cgvae_dense_pair_fwd(const float* x, int64_t ldx, const float* W, int64_t ldw, int64_t M, int64_t N1, int64_t N2, int64_t K,
+                         float* C1, float* C2, cgvae_stream_t stream) {
+  CGVAE_REQUIRE(M >= 0 && N1 >= 1 && N2 >= 1 && K >= 1, "dense_pair_fwd: bad sizes");
+  if (M == 0) return 0;
+  CGVAE_REQUIRE(x && W && C1 && C2, "dense_pair_fwd: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (launch_dense_pair_stream(x, ldx, W, ldw, C1, N1, C2, N2, M, N1, N2, K, st)) return launched("dense_pair_stream");
+  // not eligible for the weight-streaming kernel: two ordinary launches
+  if (int rc = cgvae_gemm(CGVAE_GEMM_NT, x, ldx, W, ldw, C1, N1, M, N1, K, nullptr, 0, nullptr, nullptr, 0, nullptr, nullptr, 0,
+                          nullptr, 0, stream))
+    return rc;
+  return cgvae_gemm(CGVAE_GEMM_NT, x, ldx, W + N1 * ldw, ldw, C2, N2, M, N2, K, nullptr, 0, nullptr, nullptr, 0, nullptr, nullptr, 0,
+                    nullptr, 0, stream);
+}
 
 int cgvae_gemm(int form, const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t M, int64_t N,
                int64_t K, const float* bias, int act, float* z_out, const float* z_in, int dact, const float* add,

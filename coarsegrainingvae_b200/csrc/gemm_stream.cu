@@ -30,6 +30,11 @@ struct StreamEpilogue {
   const float* z_in;
   int dact;
   const float* add;
+  // NT only: output columns n >= n_split go to a second matrix C2[m][n - n_split] (row stride ldc2): two Dense layers
+  // that share their input and whose weights are adjacent in memory run as ONE launch (u_mat / v_mat of UpdateBlock)
+  float* C2;
+  int n_split;
+  int64_t ldc2;
 };
 
 __device__ __forceinline__ float stream_epilogue(const StreamEpilogue& ep, float v, int64_t m, int64_t n, int64_t ldc) {
@@ -197,7 +202,10 @@ __global__ void __launch_bounds__(MR > 16 ? 256 : 512) gemm_nt_stream_kernel(
         const int idx = base + i;
         const int r = idx / MR, m = idx % MR;
         const int n = row0 + t0 + r;
-        if (m < M && t0 + r < rows) C[(int64_t)m * ldc + n] = stream_epilogue(ep, acc[i], m, n, ldc);
+        if (m < M && t0 + r < rows) {
+          if (ep.C2 != nullptr && n >= ep.n_split) ep.C2[(int64_t)m * ep.ldc2 + (n - ep.n_split)] = acc[i];
+          else C[(int64_t)m * ldc + n] = stream_epilogue(ep, acc[i], m, n, ldc);
+        }
       }
     }
   }
@@ -408,7 +416,7 @@ int launch_gemm_stream(int form, const float* A, int64_t lda, const float* B, in
   static const bool enabled = [] { const char* e = getenv("CGVAE_STREAM_GEMM"); return !(e && e[0] == '0'); }();
   if (!enabled || M > 48 || M < 1 || form == CGVAE_GEMM_TN) return 0;
   if (N * K < 64 * 64 || N >= (1 << 24) || K >= (1 << 24)) return 0;
-  const StreamEpilogue ep{bias, act, z_out, z_in, dact, add};
+  const StreamEpilogue ep{bias, act, z_out, z_in, dact, add, nullptr, 0, 0};
   const int m = (int)M, n = (int)N, k = (int)K;
   if (form == CGVAE_GEMM_NT) {
     // rows of X and W travel as bulk copies: 16-byte aligned rows of a multiple of 16 bytes
@@ -429,6 +437,20 @@ int launch_gemm_stream(int form, const float* A, int64_t lda, const float* B, in
   if (!nn_wide_rows) return 0;
   if (M <= 36) return launch_nn<36, 2, 8>(A, lda, B, ldb, C, ldc, m, n, k, ep, st);
   return launch_nn<48, 2, 8>(A, lda, B, ldb, C, ldc, m, n, k, ep, st);
+}
+
+// two Dense layers on the same input, weights adjacent in memory: W = [W1 (N1 rows); W2 (N2 rows)], no bias / activation
+int launch_dense_pair_stream(const float* X, int64_t ldx, const float* W, int64_t ldw, float* C1, int64_t ldc1, float* C2,
+                             int64_t ldc2, int64_t M, int64_t N1, int64_t N2, int64_t K, cudaStream_t st) {
+  static const bool enabled = [] { const char* e = getenv("CGVAE_STREAM_GEMM"); return !(e && e[0] == '0'); }();
+  if (!enabled || M > 48 || M < 1 || N1 + N2 >= (1 << 24) || K >= (1 << 24)) return 0;
+  if (K % 4 != 0 || K < 128 || ldx % 4 != 0 || ldw % 4 != 0 || !aligned16(X) || !aligned16(W)) return 0;
+  const StreamEpilogue ep{nullptr, 0, nullptr, nullptr, 0, nullptr, C2, (int)N1, ldc2};
+  const int m = (int)M, n = (int)(N1 + N2), k = (int)K;
+  if (M <= 12) return launch_nt<12, 4>(X, ldx, W, ldw, C1, ldc1, m, n, k, ep, st);
+  if (M <= 16) return launch_nt<16, 4>(X, ldx, W, ldw, C1, ldc1, m, n, k, ep, st);
+  if (M <= 36) return launch_nt<36, 2>(X, ldx, W, ldw, C1, ldc1, m, n, k, ep, st);
+  return launch_nt<48, 2>(X, ldx, W, ldw, C1, ldc1, m, n, k, ep, st);
 }
 
 }  // namespace cgvae

@@ -138,8 +138,8 @@ class UpdateBlockFn(Function):
         s, v = s.contiguous(), v.contiguous()
         N, F = s.shape
         v2 = v.view(3 * N, F)
-        Uv = ops.linear_fwd(v2, U, None, 0).view(N, 3, F)
-        Vv = ops.linear_fwd(v2, V, None, 0).view(N, 3, F)
+        Uv, Vv = ops.linear_pair_fwd(v2, U, V)          # one launch when U and V are adjacent in the flat parameter buffer
+        Uv, Vv = Uv.view(N, 3, F), Vv.view(N, 3, F)
         x = ops.update_norm_fwd(s, Vv)
         h, z = ops.linear_fwd(x, A0, c0, SWISH, save_pre=True)
         q = ops.linear_fwd(h, A1, c1, 0).view(N, 3, F)

@@ -396,6 +396,24 @@ def linear_fwd(x, W, b, act=0, save_pre=False):
     return gemm(GEMM_NT, x, W, M, N, K, bias=b, act=act, z_out=save_pre)
 
 
+def linear_pair_fwd(x, W1, W2):
+    """(x W1^T, x W2^T) for two bias-free Dense layers on the same input.  When the two weight matrices are adjacent in
+    memory (consecutive parameters of the flat parameter buffer of train.TrainStep) this is ONE weight-streaming launch
+    (cgvae_dense_pair_fwd); otherwise two."""
+    M, K = x.shape
+    N1, N2 = W1.shape[0], W2.shape[0]
+    adjacent = (W1.is_contiguous() and W2.is_contiguous() and W1.shape[1] == K and W2.shape[1] == K
+                and W2.data_ptr() == W1.data_ptr() + 4 * W1.numel())
+    if not adjacent:
+        return linear_fwd(x, W1, None, 0), linear_fwd(x, W2, None, 0)
+    _need_cuda(x, W1)
+    lib = _lib.load()
+    C1 = torch.empty((M, N1), dtype=torch.float32, device=x.device)
+    C2 = torch.empty((M, N2), dtype=torch.float32, device=x.device)
+    _lib.check(lib.cgvae_dense_pair_fwd(_p(x), x.stride(0), _p(W1), K, M, N1, N2, K, _p(C1), _p(C2), _stream()), "dense_pair_fwd")
+    return C1, C2
+
+
 def linear_bwd_input(gy, W, z_in=None, dact=0, add=None):
     """gx = (gy W) [* act'(z_in)] [+ add]"""
     M, N = gy.shape

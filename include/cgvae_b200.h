@@ -133,6 +133,11 @@ int cgvae_gemm(int form, const float* A, int64_t lda, const float* B, int64_t ld
                int64_t M, int64_t N, int64_t K, const float* bias, int act, float* z_out,
                const float* z_in, int dact, const float* add, void* ws, size_t ws_bytes,
                int32_t* counters, int n_counters, cgvae_stream_t stream);
+/* Two bias-free Dense layers on the SAME input whose weight matrices are adjacent in memory (W = [W1: N1 rows; W2: N2 rows],
+ * row stride ldw): C1[M,N1] = x W1^T, C2[M,N2] = x W2^T (both contiguous) in ONE weight-streaming launch when M <= 48
+ * (u_mat / v_mat of UpdateBlock.forward conv.py:592-598 on the planar [3N,F] view); otherwise two cgvae_gemm launches. */
+int cgvae_dense_pair_fwd(const float* x, int64_t ldx, const float* W, int64_t ldw, int64_t M, int64_t N1, int64_t N2,
+                         int64_t K, float* C1, float* C2, cgvae_stream_t stream);
 /* out[N] = sum over rows of X[M][N] (bias gradients); deterministic. */
 int cgvae_colsum(const float* X, int64_t ldx, int64_t M, int64_t N, float* out, cgvae_stream_t stream);
 

@@ -604,3 +604,20 @@ def test_message_layer_ragged_degrees_vs_oracle(cls, K):
     isolated = [i for i in range(n) if i not in degs and i not in set(send)]
     assert isolated and float(ds.detach()[isolated].abs().max()) == 0.0 and float(dv.detach()[isolated].abs().max()) == 0.0
     pc._check_grads(blk, P, TOL, "blk.")
+
+
+@pytest.mark.parametrize("M,N1,N2,K", [(36, 600, 600, 600), (12, 600, 1800, 600), (40, 130, 70, 260), (200, 64, 64, 128)])
+def test_dense_pair_forward(M, N1, N2, K):
+    """cgvae_dense_pair_fwd: two bias-free Dense layers on one input, weights adjacent in memory, one launch (streaming
+    kernel up to 48 rows, two tiled launches beyond); non-adjacent weights take the two-launch route in ops."""
+    g = torch.Generator().manual_seed(M + N1)
+    x = torch.randn(M, K, generator=g).to(DEV)
+    W = (torch.randn(N1 + N2, K, generator=g) / K ** 0.5).to(DEV)
+    W1, W2 = W[:N1], W[N1:]
+    before = ops.launch_count()
+    y1, y2 = ops.linear_pair_fwd(x, W1, W2)
+    launches = ops.launch_count() - before
+    assert launches == (1 if M <= 48 else 2)
+    assert rel_err(y1, x.double() @ W1.double().t()) < GEMM_TOL and rel_err(y2, x.double() @ W2.double().t()) < GEMM_TOL
+    z1, z2 = ops.linear_pair_fwd(x, W1.clone(), W2.clone())          # not adjacent: same numbers from two launches
+    assert rel_err(z1, y1) < 1e-6 and rel_err(z2, y2) < 1e-6
