@@ -204,13 +204,8 @@ class CGprior(nn.Module):
 
 
 def _act_code_of(module):
-    if isinstance(module, nn.ReLU):
-        return 2
-    if isinstance(module, nn.Tanh):
-        return 3
-    if module.__class__.__name__ == "Swish":
-        return 1
-    raise NotImplementedError("activation %s has no sm_100a epilogue" % module.__class__.__name__)
+    from .modules import module_activation_code
+    return module_activation_code(module)
 
 
 class CGequiVAE(nn.Module):

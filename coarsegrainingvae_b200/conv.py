@@ -13,13 +13,21 @@ from torch import nn
 
 from . import functions as fn
 from . import ops
-from .modules import Dense, DistanceEmbed, Swish, activation_code, make_directed  # noqa: F401 (re-export)
+from .modules import Dense, DistanceEmbed, Swish, shifted_softplus, activation_code, make_directed  # noqa: F401 (re-export)
 
 
 def to_module(activation):
+    """marker module of the reference's layer_types registry (modules.py:32-42)"""
+    activation_code(activation)                 # raises for unknown names
     if activation == "swish":
         return Swish()
-    return getattr(nn, activation)() if hasattr(nn, activation) else Swish()
+    if activation == "shifted_softplus":
+        return shifted_softplus()
+    if activation == "sigmoid":
+        return nn.Sigmoid()
+    if activation == "linear":
+        return nn.Identity()
+    return getattr(nn, activation)()
 
 
 def _geometry_from_edges(nbrs, r_ij, n_nodes, n_rbf, cutoff, edge_wgt=None):
@@ -40,8 +48,7 @@ class InvariantMessage(nn.Module):
         self.dist_embed = DistanceEmbed(n_rbf=n_rbf, cutoff=cutoff, feat_dim=out_feat_dim, dropout=dropout)
         self.dist_filter = Dense(in_features=in_feat_dim, out_features=out_feat_dim, bias=True, dropout_rate=0.0)
         self.offset = torch.linspace(0.0, cutoff, in_feat_dim)
-        if activation_code(activation) != 1:
-            raise NotImplementedError("message blocks are built for activation='swish' (the only one the drivers use)")
+        self.act = activation_code(activation)
         self.n_rbf, self.cutoff = n_rbf, cutoff
 
     def params(self):
@@ -59,12 +66,13 @@ class _MessageBase(nn.Module):
 
     def fused(self, s, v, geom):
         """(s, v) + message, planar layout; v may be None (all zero)."""
-        return fn.MessageBlock.apply(geom, self.n_split, "self", s, v, None, None, *self.inv_message.params())
+        return fn.MessageBlock.apply(geom, self.n_split, "self", self.inv_message.act, s, v, None, None,
+                                     *self.inv_message.params())
 
     def forward(self, s_j, v_j, r_ij, nbrs, edge_wgt=None):
         geom = _geometry_from_edges(nbrs, r_ij, s_j.shape[0], self.inv_message.n_rbf, self.inv_message.cutoff, edge_wgt)
         # the layout conversions [N,F,3] <-> [N,3,F] are autograd nodes of their own
-        ds, dv = fn.MessageBlock.apply(geom, self.n_split, "delta", s_j, _Planar.apply(v_j), None, None,
+        ds, dv = fn.MessageBlock.apply(geom, self.n_split, "delta", self.inv_message.act, s_j, _Planar.apply(v_j), None, None,
                                        *self.inv_message.params())
         return ds, _Unplanar.apply(dv)
 
@@ -120,13 +128,13 @@ class EquiMessagePsuedo(nn.Module):
                                             n_rbf=n_rbf, cutoff=cutoff, dropout=dropout)
 
     def fused(self, s, sbar, v, vbar, geom):
-        return fn.Message9Block.apply(geom, True, s, sbar, v, vbar, *self.inv_message.params())
+        return fn.Message9Block.apply(geom, True, self.inv_message.act, s, sbar, v, vbar, *self.inv_message.params())
 
     def forward(self, s_j, sbar_j, v_j, vbar_j, r_ij, nbrs, edge_wgt=None):
         if edge_wgt is not None:
             raise NotImplementedError("EquiMessagePsuedo ignores edge_wgt in the reference as well (conv.py:187)")
         geom = _geometry_from_edges(nbrs, r_ij, s_j.shape[0], self.inv_message.n_rbf, self.inv_message.cutoff)
-        ds, dsbar, dv, dvbar = fn.Message9Block.apply(geom, False, s_j, sbar_j, _Planar.apply(v_j), _Planar.apply(vbar_j),
+        ds, dsbar, dv, dvbar = fn.Message9Block.apply(geom, False, self.inv_message.act, s_j, sbar_j, _Planar.apply(v_j), _Planar.apply(vbar_j),
                                                       *self.inv_message.params())
         return ds, dsbar, _Unplanar.apply(dv), _Unplanar.apply(dvbar)
 
@@ -142,18 +150,17 @@ class UpdateBlock(nn.Module):
             Dense(in_features=2 * feat_dim, out_features=feat_dim, bias=True, dropout_rate=dropout,
                   activation=to_module(activation)),
             Dense(in_features=feat_dim, out_features=3 * feat_dim, bias=True, dropout_rate=dropout))
-        if activation_code(activation) != 1:
-            raise NotImplementedError("UpdateBlock is built for activation='swish'")
+        self.act = activation_code(activation)
 
     def params(self):
         return (self.u_mat.weight, self.v_mat.weight, self.s_dense[0].weight, self.s_dense[0].bias,
                 self.s_dense[1].weight, self.s_dense[1].bias)
 
     def fused(self, s, v):
-        return fn.UpdateBlockFn.apply(True, s, v, *self.params())
+        return fn.UpdateBlockFn.apply(True, self.act, s, v, *self.params())
 
     def forward(self, s_i, v_i):
-        ds, dv = fn.UpdateBlockFn.apply(False, s_i, _Planar.apply(v_i), *self.params())
+        ds, dv = fn.UpdateBlockFn.apply(False, self.act, s_i, _Planar.apply(v_i), *self.params())
         return ds, _Unplanar.apply(dv)
 
 
@@ -184,6 +191,7 @@ class ContractiveMessageBlock(nn.Module):
                   activation=to_module(activation)),
             Dense(in_features=feat_dim, out_features=3 * feat_dim, bias=True, dropout_rate=dropout))
         self.dist_embed = DistanceEmbed(n_rbf=n_rbf, cutoff=cutoff, feat_dim=3 * feat_dim, dropout=dropout)
+        self.act = activation_code(activation)
         self.n_rbf, self.cutoff = n_rbf, cutoff
 
     def params(self):
@@ -192,7 +200,7 @@ class ContractiveMessageBlock(nn.Module):
 
     def fused(self, s, v, H, V, geom):
         """(H, V) + contraction of atom state (s, v) over the atoms->beads graph."""
-        return fn.MessageBlock.apply(geom, 3, "other", s, v, H, V, *self.params())
+        return fn.MessageBlock.apply(geom, 3, "other", self.act, s, v, H, V, *self.params())
 
     def forward(self, s_i, v_i, r_iI, mapping):
         # scatter_add without dim_size (conv.py:725-731): the output has max(mapping)+1 rows -- one host read,
@@ -201,5 +209,5 @@ class ContractiveMessageBlock(nn.Module):
         seg = ops.build_segments(mapping, n_beads)
         graph = ops.contraction_graph(seg)
         geom = ops.edge_geometry(graph, None, None, self.n_rbf, self.cutoff, r_edge=r_iI)
-        dS, dV = fn.MessageBlock.apply(geom, 3, "delta", s_i, _Planar.apply(v_i), None, None, *self.params())
+        dS, dV = fn.MessageBlock.apply(geom, 3, "delta", self.act, s_i, _Planar.apply(v_i), None, None, *self.params())
         return dS, _Unplanar.apply(dV)

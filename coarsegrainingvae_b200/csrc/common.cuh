@@ -112,11 +112,18 @@ __device__ __forceinline__ float dswish_f(float z) {
   return sig * (1.0f + z * (1.0f - sig));
 }
 
+__device__ __forceinline__ float sigmoid_f(float z) { return 1.0f / (1.0f + expf(-z)); }
+
 __device__ __forceinline__ float act_fwd(int act, float z) {
   switch (act) {
     case CGVAE_ACT_SWISH: return swish_f(z);
     case CGVAE_ACT_RELU: return z > 0.f ? z : 0.f;
     case CGVAE_ACT_TANH: return tanhf(z);
+    case CGVAE_ACT_SIGMOID: return sigmoid_f(z);
+    // F.softplus(z) - ln 2 (modules.py:8-14); torch switches to the identity above its threshold of 20
+    case CGVAE_ACT_SHIFTED_SOFTPLUS: return (z > 20.f ? z : log1pf(expf(z))) - 0.6931471805599453f;
+    case CGVAE_ACT_LEAKY_RELU: return z > 0.f ? z : 0.01f * z;            // nn.LeakyReLU default slope
+    case CGVAE_ACT_ELU: return z > 0.f ? z : expm1f(z);                   // nn.ELU default alpha = 1
     default: return z;
   }
 }
@@ -125,6 +132,10 @@ __device__ __forceinline__ float act_bwd(int act, float z) {
     case CGVAE_ACT_SWISH: return dswish_f(z);
     case CGVAE_ACT_RELU: return z > 0.f ? 1.f : 0.f;
     case CGVAE_ACT_TANH: { float t = tanhf(z); return 1.f - t * t; }
+    case CGVAE_ACT_SIGMOID: { float sg = sigmoid_f(z); return sg * (1.f - sg); }
+    case CGVAE_ACT_SHIFTED_SOFTPLUS: return z > 20.f ? 1.f : sigmoid_f(z);
+    case CGVAE_ACT_LEAKY_RELU: return z > 0.f ? 1.f : 0.01f;
+    case CGVAE_ACT_ELU: return z > 0.f ? 1.f : expf(z);
     default: return 1.f;
   }
 }

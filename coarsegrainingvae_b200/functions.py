@@ -66,9 +66,9 @@ class MessageBlock(Function):
     """
 
     @staticmethod
-    def forward(ctx, geom, n_split, mode, s, v, res_s, res_v, W1, b1, W2, b2, Wf, bf):
+    def forward(ctx, geom, n_split, mode, act, s, v, res_s, res_v, W1, b1, W2, b2, Wf, bf):
         s = s.contiguous()
-        a1, z1, phi = _phi_forward(s, W1, b1, W2, b2)
+        a1, z1, phi = _phi_forward(s, W1, b1, W2, b2, act)
         N, F = s.shape
         phi3 = phi.view(N, n_split, F)
         if mode == "self":
@@ -79,7 +79,7 @@ class MessageBlock(Function):
             rs, rv = None, None
         out_s, out_v, q = ops.message_fwd(n_split, phi3, v, v if n_split == 4 else None, geom, Wf, bf, rs, rv,
                                           want_q=(n_split == 4 and v is not None))
-        ctx.geom, ctx.n_split, ctx.mode = geom, n_split, mode
+        ctx.geom, ctx.n_split, ctx.mode, ctx.act = geom, n_split, mode, act
         ctx.v_none = v is None
         ctx.res_v_none = res_v is None
         ctx.save_for_backward(s, v, a1, z1, phi3, q, W1, b1, W2, b2, Wf, bf)
@@ -97,24 +97,24 @@ class MessageBlock(Function):
                                                     g_s, g_v, residual and not ctx.v_none)
         N, F = s.shape
         gs, gW1, gb1, gW2, gb2 = _phi_backward(g_phi.view(N, n_split * F), s, a1, z1, W1, b1, W2, b2,
-                                               g_s if residual else None)
+                                               g_s if residual else None, ctx.act)
         gv = None if ctx.v_none else g_v_send
         g_res_s = g_s if mode == "other" else None
         g_res_v = g_v if (mode == "other" and not ctx.res_v_none) else None
-        return None, None, None, gs, gv, g_res_s, g_res_v, gW1, gb1, gW2, gb2, dWf, dbf
+        return None, None, None, None, gs, gv, g_res_s, g_res_v, gW1, gb1, gW2, gb2, dWf, dbf
 
 
 class Message9Block(Function):
     """InvariantMessage (9 splits) + EquiMessagePsuedo, conv.py:180-242; residual adds of cgvae.py:108-111 fused."""
 
     @staticmethod
-    def forward(ctx, geom, residual, s, sbar, v, vbar, W1, b1, W2, b2, Wf, bf):
+    def forward(ctx, geom, residual, act, s, sbar, v, vbar, W1, b1, W2, b2, Wf, bf):
         s, sbar, v, vbar = s.contiguous(), sbar.contiguous(), v.contiguous(), vbar.contiguous()
-        a1, z1, phi = _phi_forward(s, W1, b1, W2, b2)
+        a1, z1, phi = _phi_forward(s, W1, b1, W2, b2, act)
         N, F = s.shape
         phi3 = phi.view(N, 9, F)
         outs = ops.message9_fwd(phi3, s, sbar, v, vbar, geom, Wf, bf, residual)
-        ctx.geom, ctx.residual = geom, residual
+        ctx.geom, ctx.residual, ctx.act = geom, residual, act
         ctx.save_for_backward(s, sbar, v, vbar, a1, z1, phi3, W1, b1, W2, b2, Wf, bf)
         return tuple(outs)
 
@@ -126,25 +126,25 @@ class Message9Block(Function):
             phi3, s, sbar, v, vbar, ctx.geom, Wf, bf, ctx.residual,
             g_s.contiguous(), g_sbar.contiguous(), g_v.contiguous(), g_vbar.contiguous())
         N, F = s.shape
-        gs, gW1, gb1, gW2, gb2 = _phi_backward(g_phi.view(N, 9 * F), s, a1, z1, W1, b1, W2, b2, gi_s)
-        return None, None, gs, gi_sbar, gi_v, gi_vbar, gW1, gb1, gW2, gb2, dWf, dbf
+        gs, gW1, gb1, gW2, gb2 = _phi_backward(g_phi.view(N, 9 * F), s, a1, z1, W1, b1, W2, b2, gi_s, ctx.act)
+        return None, None, None, gs, gi_sbar, gi_v, gi_vbar, gW1, gb1, gW2, gb2, dWf, dbf
 
 
 class UpdateBlockFn(Function):
     """UpdateBlock.forward conv.py:588-616 on planar vectors; residual of cgvae.py:122-123 optionally fused."""
 
     @staticmethod
-    def forward(ctx, residual, s, v, U, V, A0, c0, A1, c1):
+    def forward(ctx, residual, act, s, v, U, V, A0, c0, A1, c1):
         s, v = s.contiguous(), v.contiguous()
         N, F = s.shape
         v2 = v.view(3 * N, F)
         Uv, Vv = ops.linear_pair_fwd(v2, U, V)          # one launch when U and V are adjacent in the flat parameter buffer
         Uv, Vv = Uv.view(N, 3, F), Vv.view(N, 3, F)
         x = ops.update_norm_fwd(s, Vv)
-        h, z = ops.linear_fwd(x, A0, c0, SWISH, save_pre=True)
+        h, z = ops.linear_fwd(x, A0, c0, act, save_pre=True)
         q = ops.linear_fwd(h, A1, c1, 0).view(N, 3, F)
         s_out, v_out = ops.update_combine_fwd(s, v, Uv, Vv, q, residual)
-        ctx.residual = residual
+        ctx.residual, ctx.act = residual, act
         ctx.save_for_backward(v, Uv, Vv, x, h, z, q, U, V, A0, c0, A1, c1)
         return s_out, v_out
 
@@ -159,7 +159,7 @@ class UpdateBlockFn(Function):
         v2 = v.view(3 * N, F)
         gUv2, gVv2 = gUv.view(3 * N, F), gVv.view(3 * N, F)
         fork = ops.Fork(g_s.device, enabled=not ops.deferring(3 * N))
-        gz = ops.linear_bwd_input(gq2, A1, z_in=z, dact=SWISH)
+        gz = ops.linear_bwd_input(gq2, A1, z_in=z, dact=ctx.act)
         with fork.branch():                                                 # parameter gradients: off the critical path
             gA1 = ops.linear_bwd_weight(gq2, h, A1)
             gc1 = ops.colsum(gq2, c1)
@@ -176,7 +176,7 @@ class UpdateBlockFn(Function):
         with fork.branch():
             gV = ops.linear_bwd_weight(gVv2, v2, V)
         fork.join()
-        return None, gs_in, gv_in, gU, gV, gA0, gc0, gA1, gc1
+        return None, None, gs_in, gv_in, gU, gV, gA0, gc0, gA1, gc1
 
 
 class SegmentReduce(Function):

@@ -11,9 +11,9 @@ from torch.nn.init import xavier_uniform_, zeros_
 from . import ops
 
 # activation names of the reference's ``layer_types`` registry (modules.py:32-42) -> kernel codes.
-# The hot path ships swish / ReLU / Tanh / linear; the remaining registry entries are listed in
-# DESIGN.md as "next".
-ACTIVATION_CODES = {"swish": 1, "ReLU": 2, "Tanh": 3, "linear": 0}
+# "Dropout" is not an activation (the drivers run dropout = 0.0 everywhere).
+ACTIVATION_CODES = {"linear": 0, "swish": 1, "ReLU": 2, "Tanh": 3, "sigmoid": 4, "shifted_softplus": 5, "LeakyReLU": 6,
+                    "ELU": 7}
 
 
 def activation_code(name):
@@ -25,6 +25,25 @@ def activation_code(name):
 class Swish(nn.Module):
     """x * sigmoid(x) (modules.py:16-21); parameter-free marker, fused into GEMM epilogues."""
     code = 1
+
+
+class shifted_softplus(nn.Module):
+    """softplus(x) - ln 2 (modules.py:8-14); parameter-free marker, fused into GEMM epilogues."""
+    code = 5
+
+
+# module class of an activation marker -> kernel code (the heads atom_munet / atom_sigmanet / prior are nn.Sequential
+# (Linear, activation module, Linear) built by the drivers: scripts/run_ala.py:184-185)
+MODULE_CODES = {"Swish": 1, "ReLU": 2, "Tanh": 3, "Sigmoid": 4, "shifted_softplus": 5, "LeakyReLU": 6, "ELU": 7}
+
+
+def module_activation_code(module):
+    name = module.__class__.__name__
+    if name not in MODULE_CODES:
+        raise NotImplementedError("activation module %s has no sm_100a epilogue" % name)
+    if name == "LeakyReLU" and abs(module.negative_slope - 0.01) > 0 or name == "ELU" and module.alpha != 1.0:
+        raise NotImplementedError("%s with non-default parameters has no sm_100a epilogue" % name)
+    return MODULE_CODES[name]
 
 
 class Dense(nn.Linear):

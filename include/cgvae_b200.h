@@ -42,7 +42,9 @@ typedef void* cgvae_stream_t; /* cudaStream_t */
 #define CGVAE_ABI_VERSION 1
 
 /* activation codes (reference modules.py:32-42 `layer_types`) */
-enum { CGVAE_ACT_NONE = 0, CGVAE_ACT_SWISH = 1, CGVAE_ACT_RELU = 2, CGVAE_ACT_TANH = 3 };
+enum { CGVAE_ACT_NONE = 0, CGVAE_ACT_SWISH = 1, CGVAE_ACT_RELU = 2, CGVAE_ACT_TANH = 3,
+       /* the rest of the reference's layer_types registry (modules.py:32-42) */
+       CGVAE_ACT_SIGMOID = 4, CGVAE_ACT_SHIFTED_SOFTPLUS = 5, CGVAE_ACT_LEAKY_RELU = 6, CGVAE_ACT_ELU = 7 };
 /* GEMM operand forms */
 enum { CGVAE_GEMM_NT = 0, /* C[M,N] = A[M,K] * B[N,K]^T   (y = x W^T, Dense.forward modules.py:101) */
        CGVAE_GEMM_NN = 1, /* C[M,N] = A[M,K] * B[K,N]     (grad_in = grad_out W)                    */

@@ -19,7 +19,10 @@ from coarsegrainingvae_b200 import ops
 
 
 def _act(code, z):
-    return {0: lambda t: t, 1: lambda t: t * torch.sigmoid(t), 2: torch.relu, 3: torch.tanh}[code](z)
+    import math
+    F = torch.nn.functional
+    return {0: lambda t: t, 1: lambda t: t * torch.sigmoid(t), 2: torch.relu, 3: torch.tanh, 4: torch.sigmoid,
+            5: lambda t: F.softplus(t) - math.log(2.0), 6: F.leaky_relu, 7: F.elu}[code](z)
 
 
 def _dact(code, z):
@@ -30,6 +33,15 @@ def _dact(code, z):
         return (z > 0).to(z.dtype)
     if code == 3:
         return 1 - torch.tanh(z) ** 2
+    if code == 4:
+        sig = torch.sigmoid(z)
+        return sig * (1 - sig)
+    if code == 5:
+        return torch.sigmoid(z)
+    if code == 6:
+        return torch.where(z > 0, torch.ones_like(z), torch.full_like(z, 0.01))
+    if code == 7:
+        return torch.where(z > 0, torch.ones_like(z), torch.exp(z))
     return torch.ones_like(z)
 
 

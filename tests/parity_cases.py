@@ -248,3 +248,78 @@ def pcn_model(dev, tag, dtype, tol, gold_tol=5e-5):
     _check_grads(model, P, tol)
     if dtype == torch.float32:
         _check_golden_grads(model, G, gold_tol)
+
+
+ACTIVATIONS = ("ReLU", "Tanh", "sigmoid", "shifted_softplus", "LeakyReLU", "ELU")
+
+
+def blocks_with_activation(dev, act, dtype, tol):
+    """every block type built with a non-default entry of the reference's layer_types registry (modules.py:32-42): outputs,
+    input gradients and parameter gradients vs the oracle run with the same activation (golden inputs and weights)."""
+    z = load("blocks_small.npz")
+    F, R, cutoff = int(z["meta/F"]), int(z["meta/R"]), float(z["meta/cutoff"])
+    nbrs = torch.from_numpy(z["in/nbrs"])
+    r = torch.from_numpy(z["in/r"]).to(dtype)
+    # 3-split message block
+    sec = section(z, "k3")
+    blk = cg.EquiMessageBlock(feat_dim=F, activation=act, n_rbf=R, cutoff=cutoff, dropout=0.0)
+    _load_params(blk, sec, dtype, dev)
+    gs, gv = sec["gs"].to(dtype), sec["gv"].to(dtype)
+    s, v = _leaf(sec["s"], dtype, dev), _leaf(sec["v"], dtype, dev)
+    ds, dv = blk(s, v, r.to(dev), nbrs.to(dev))
+    ((ds * gs.to(dev)).sum() + (dv * gv.to(dev)).sum()).backward()
+    P = _oracle_params(blk, "blk.")
+    so, vo = _leaf(sec["s"], dtype, "cpu"), _leaf(sec["v"], dtype, "cpu")
+    ods, odv = orc.equi_message(P, "blk", so, vo, r, nbrs, R, cutoff, act=act)
+    ((ods * gs).sum() + (odv * gv).sum()).backward()
+    assert rel_err(ds, ods) < tol and rel_err(dv, odv) < tol
+    assert rel_err(s.grad, so.grad) < tol and rel_err(v.grad, vo.grad) < tol
+    _check_grads(blk, P, tol, "blk.")
+    # 9-split block
+    sec = section(z, "k9")
+    blk = cg.EquiMessagePsuedo(feat_dim=F, activation=act, n_rbf=R, cutoff=cutoff, dropout=0.0)
+    _load_params(blk, sec, dtype, dev)
+    names, onames = ("s", "sbar", "v", "vbar"), ("ds", "dsbar", "dv", "dvbar")
+    ins = [_leaf(sec[k], dtype, dev) for k in names]
+    outs = blk(*ins, r.to(dev), nbrs.to(dev))
+    sum((o * sec["g_" + k].to(dtype).to(dev)).sum() for o, k in zip(outs, onames)).backward()
+    P = _oracle_params(blk, "blk.")
+    oins = [_leaf(sec[k], dtype, "cpu") for k in names]
+    oouts = orc.equi_message_pseudo(P, "blk", *oins, r, nbrs, R, cutoff, act=act)
+    sum((o * sec["g_" + k].to(dtype)).sum() for o, k in zip(oouts, onames)).backward()
+    for a, b, k in zip(outs, oouts, onames):
+        assert rel_err(a, b) < tol, k
+    for a, b, k in zip(ins, oins, names):
+        assert rel_err(a.grad, b.grad) < tol, k
+    _check_grads(blk, P, tol, "blk.")
+    # update block
+    sec = section(z, "upd")
+    blk = cg.UpdateBlock(feat_dim=F, activation=act, dropout=0.0)
+    _load_params(blk, sec, dtype, dev)
+    gs, gv = sec["gs"].to(dtype), sec["gv"].to(dtype)
+    s, v = _leaf(sec["s"], dtype, dev), _leaf(sec["v"], dtype, dev)
+    ds, dv = blk(s, v)
+    ((ds * gs.to(dev)).sum() + (dv * gv.to(dev)).sum()).backward()
+    P = _oracle_params(blk, "blk.")
+    so, vo = _leaf(sec["s"], dtype, "cpu"), _leaf(sec["v"], dtype, "cpu")
+    ods, odv = orc.update_block(P, "blk", so, vo, act=act)
+    ((ods * gs).sum() + (odv * gv).sum()).backward()
+    assert rel_err(ds, ods) < tol and rel_err(dv, odv) < tol
+    assert rel_err(s.grad, so.grad) < tol and rel_err(v.grad, vo.grad) < tol
+    _check_grads(blk, P, tol, "blk.")
+    # atoms -> beads contraction
+    sec = section(z, "con")
+    blk = cg.ContractiveMessageBlock(feat_dim=F, activation=act, n_rbf=R, cutoff=20.0, dropout=0.0)
+    _load_params(blk, sec, dtype, dev)
+    gS, gV = sec["gS"].to(dtype), sec["gV"].to(dtype)
+    r_iI = sec["r_iI"].to(dtype)
+    s, v = _leaf(sec["s"], dtype, dev), _leaf(sec["v"], dtype, dev)
+    dS, dV = blk(s, v, r_iI.to(dev), sec["mapping"].to(dev))
+    ((dS * gS.to(dev)).sum() + (dV * gV.to(dev)).sum()).backward()
+    P = _oracle_params(blk, "blk.")
+    so, vo = _leaf(sec["s"], dtype, "cpu"), _leaf(sec["v"], dtype, "cpu")
+    odS, odV = orc.contractive_message(P, "blk", so, vo, r_iI, sec["mapping"], R, act=act)
+    ((odS * gS).sum() + (odV * gV).sum()).backward()
+    assert rel_err(dS, odS) < tol and rel_err(dV, odV) < tol
+    assert rel_err(s.grad, so.grad) < tol and rel_err(v.grad, vo.grad) < tol
+    _check_grads(blk, P, tol, "blk.")

@@ -621,3 +621,10 @@ def test_dense_pair_forward(M, N1, N2, K):
     assert rel_err(y1, x.double() @ W1.double().t()) < GEMM_TOL and rel_err(y2, x.double() @ W2.double().t()) < GEMM_TOL
     z1, z2 = ops.linear_pair_fwd(x, W1.clone(), W2.clone())          # not adjacent: same numbers from two launches
     assert rel_err(z1, y1) < 1e-6 and rel_err(z2, y2) < 1e-6
+
+
+@pytest.mark.parametrize("act", pc.ACTIVATIONS)
+def test_blocks_with_every_registry_activation(act):
+    """every block type with the non-default activations of the reference's layer_types registry (epilogue codes 2..7 of the
+    kernels) vs the oracle: outputs, input and parameter gradients"""
+    pc.blocks_with_activation(DEV, act, torch.float32, TOL)

@@ -41,6 +41,12 @@ def test_update_and_contraction_api(dtype, tol):
     pc.contraction_block_api("cpu", dtype, tol)
 
 
+@pytest.mark.parametrize("act", pc.ACTIVATIONS)
+def test_blocks_with_every_registry_activation(act):
+    """activation plumbing of the autograd nodes (forward code + derivative code) in float64 against the oracle"""
+    pc.blocks_with_activation("cpu", act, torch.float64, 1e-10)
+
+
 @pytest.mark.parametrize("tag", ["vae_sym", "vae_nosym"])
 @pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-9), (torch.float32, 5e-5)])
 def test_cgvae_model(tag, dtype, tol):
