@@ -253,7 +253,10 @@ class CGequiVAE(nn.Module):
             g.seg = ops.build_segments(mapping, cg_xyz.shape[0])
         cg_s, cg_v = self.equivaraintconv(cg_xyz, CG_nbr_list, mapping, S_I, graphs=g, planar=True)
         if self.equivariant is False:
-            raise NotImplementedError("the non-equivariant decoder head (cgvae.py:469-471) is listed as 'next' in DESIGN.md")
+            # cgvae.py:469-471: dv = euclidean(cg_s).reshape(Nc, F, 3) replaces the equivariant vectors; [Nc,F,3] -> planar
+            from .conv import _Planar
+            n_b, F = cg_s.shape
+            cg_v = _Planar.apply(fn.LinearFn.apply(cg_s, self.euclidean.weight, self.euclidean.bias).view(n_b, F, 3))
         return fn.Lift.apply(g.seg, 1 if self.offset else 0, None, cg_v, cg_xyz.contiguous())
 
     def forward(self, batch, eps=None):

@@ -55,6 +55,29 @@ class MLP2(Function):
         return None, gx, gW1, gb1, gW2, gb2
 
 
+class LinearFn(Function):
+    """y = x W^T + b (nn.Linear): the non-equivariant decoder head cgvae.py:469-471."""
+
+    @staticmethod
+    def forward(ctx, x, W, b):
+        x = x.contiguous()
+        ctx.save_for_backward(x, W, b)
+        return ops.linear_fwd(x, W, b, 0)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        x, W, b = ctx.saved_tensors
+        gy = gy.contiguous()
+        fork = ops.Fork(gy.device, enabled=not ops.deferring(gy.shape[0]))
+        gx = ops.linear_bwd_input(gy, W)
+        with fork.branch():
+            gW = ops.linear_bwd_weight(gy, x, W)
+            gb = ops.colsum(gy, b) if b is not None else None
+        fork.join()
+        return gx, gW, gb
+
+
 class MessageBlock(Function):
     """InvariantMessage + EquiMessageBlock (n_split 3, conv.py:505-563) / EquiMessageCross (4, conv.py:358-402) /
     ContractiveMessageBlock (3 on the atoms->beads graph, conv.py:703-733).

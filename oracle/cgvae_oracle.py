@@ -312,6 +312,9 @@ def cgvae_forward(P, spec, batch, eps=None):
             eps = torch.randn_like(sigma)
         zs = eps * sigma + mu
     S, V = decoder_stack_forward(P, "equivaraintconv", spec, cg_xyz, batch["CG_nbr_list"], zs)
+    if spec.get("equivariant", True) is False:
+        # cgvae.py:469-471: the vectors come from a plain Linear(F, 3F) on the scalars instead of the equivariant channel
+        V = affine(P, "euclidean", S).reshape(S.shape[0], S.shape[1], 3)
     xyz_recon = lift(V, cg_xyz, mapping, offset=spec.get("offset", True))
     return mu, sigma, pmu, pstd, xyz, xyz_recon
 

@@ -160,14 +160,17 @@ def _molecule_batch(ref_data, gen, n_conf, n_atoms, mapping, atom_cutoff, cg_cut
     return ref_data.CG_collate(samples)
 
 
-def cgvae_small(ref_cgvae, ref_data):
+def cgvae_small(ref_cgvae, ref_data, fname="cgvae_small.npz", cases=(("vae_sym", True, True), ("vae_nosym", False, True)),
+                seed=21):
+    """cases: (tag, breaksym, equivariant).  The default call writes cgvae_small.npz exactly as before; the second call in
+    main() adds cgvae_noneq.npz for the non-equivariant decoder head (cgvae.py:469-471)."""
     from torch import nn
-    gen = torch.Generator().manual_seed(21)
+    gen = torch.Generator().manual_seed(seed)
     F, R, enc, dec = 24, 5, 2, 2
     atom_cutoff, cg_cutoff = 3.5, 6.0
     mapping = torch.tensor([0, 0, 0, 1, 1, 2, 2, 2, 2])
     store = {}
-    for tag, breaksym in (("vae_sym", True), ("vae_nosym", False)):
+    for tag, breaksym, equivariant in cases:
         batch = _molecule_batch(ref_data, gen, 3, 9, mapping, atom_cutoff, cg_cutoff, 1.4)
         torch.manual_seed(123)
         dec_net = ref_cgvae.EquivariantPsuedoDecoder(n_atom_basis=F, n_rbf=R, cutoff=atom_cutoff,
@@ -179,7 +182,7 @@ def cgvae_small(ref_cgvae, ref_data):
         mu_net = nn.Sequential(nn.Linear(F, F), nn.ReLU(), nn.Linear(F, F))
         sg_net = nn.Sequential(nn.Linear(F, F), nn.ReLU(), nn.Linear(F, F))
         model = ref_cgvae.CGequiVAE(enc_net, dec_net, mu_net, sg_net, 3, feature_dim=F, prior_net=prior,
-                                    det=False, equivariant=True)
+                                    det=False, equivariant=equivariant)
         # reparametrize draws torch.randn_like(sigma): reseed right before forward and
         # regenerate the same eps afterwards (same generator state, same shape).
         torch.manual_seed(999)
@@ -206,7 +209,7 @@ def cgvae_small(ref_cgvae, ref_data):
                      ("chan", chan)):
             store["%s/%s" % (tag, k)] = _np(t)
         store["%s/meta" % tag] = np.array([F, R, enc, dec, atom_cutoff, cg_cutoff, int(breaksym), beta, gamma])
-    _save("cgvae_small.npz", store)
+    _save(fname, store)
 
 
 def pcn_small(ref_cgvae, ref_data):
@@ -276,6 +279,7 @@ def main():
     ref_modules, ref_conv, ref_cgvae, ref_data = ref_shim.import_reference()
     blocks(ref_conv)
     cgvae_small(ref_cgvae, ref_data)
+    cgvae_small(ref_cgvae, ref_data, fname="cgvae_noneq.npz", cases=(("vae_noneq", True, False),), seed=22)
     pcn_small(ref_cgvae, ref_data)
     graphs(ref_data, ref_cgvae)
 

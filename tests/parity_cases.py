@@ -178,7 +178,7 @@ def contraction_block_api(dev, dtype, tol, gold_tol=2e-5):
         _check_golden_grads(blk, G, gold_tol)
 
 
-def build_vae(F, R, enc, dec, acut, ccut, breaksym, n_cgs=3):
+def build_vae(F, R, enc, dec, acut, ccut, breaksym, n_cgs=3, equivariant=True):
     """the constructor calls of scripts/run_ala.py:184-209"""
     dec_net = cg.EquivariantPsuedoDecoder(n_atom_basis=F, n_rbf=R, cutoff=acut, num_conv=dec, activation="swish",
                                           breaksym=breaksym)
@@ -186,7 +186,7 @@ def build_vae(F, R, enc, dec, acut, ccut, breaksym, n_cgs=3):
     prior = cg.CGprior(n_conv=enc, n_atom_basis=F, n_rbf=R, cutoff=ccut, activation="swish", dir_mp=False)
     mu = nn.Sequential(nn.Linear(F, F), nn.ReLU(), nn.Linear(F, F))
     sg = nn.Sequential(nn.Linear(F, F), nn.ReLU(), nn.Linear(F, F))
-    return cg.CGequiVAE(enc_net, dec_net, mu, sg, n_cgs, feature_dim=F, prior_net=prior, det=False, equivariant=True)
+    return cg.CGequiVAE(enc_net, dec_net, mu, sg, n_cgs, feature_dim=F, prior_net=prior, det=False, equivariant=equivariant)
 
 
 def _batch_to(batch, dtype, dev):
@@ -195,10 +195,11 @@ def _batch_to(batch, dtype, dev):
 
 
 def cgvae_model(dev, tag, dtype, tol, gold_tol=5e-5):
-    z = load("cgvae_small.npz")
+    equivariant = tag != "vae_noneq"                      # cgvae_noneq.npz: the Linear(F, 3F) decoder head
+    z = load("cgvae_small.npz" if equivariant else "cgvae_noneq.npz")
     sec = section(z, tag)
     F, R, enc, dec, acut, ccut, breaksym, beta, gamma = [float(x) for x in sec["meta"]]
-    model = build_vae(int(F), int(R), int(enc), int(dec), acut, ccut, bool(breaksym))
+    model = build_vae(int(F), int(R), int(enc), int(dec), acut, ccut, bool(breaksym), equivariant=equivariant)
     G = _load_params(model, sec, dtype, dev)
     batch = {k[len("batch/"):]: v for k, v in sec.items() if k.startswith("batch/")}
     cpu_batch = _batch_to(batch, dtype, "cpu")
@@ -208,7 +209,7 @@ def cgvae_model(dev, tag, dtype, tol, gold_tol=5e-5):
     loss = orc.training_loss(out, dev_batch, beta, gamma)[0]
     loss.backward()
     spec = dict(n_basis=int(F), n_rbf=int(R), enc_nconv=int(enc), dec_nconv=int(dec), atom_cutoff=acut, cg_cutoff=ccut,
-                decoder="pseudo", breaksym=bool(breaksym), activation="swish")
+                decoder="pseudo", breaksym=bool(breaksym), activation="swish", equivariant=equivariant)
     P = _oracle_params(model)
     oout = orc.cgvae_forward(P, spec, cpu_batch, eps=eps)
     oloss = orc.training_loss(oout, cpu_batch, beta, gamma)[0]

@@ -192,7 +192,7 @@ def test_update_and_contraction_api():
     pc.contraction_block_api(DEV, torch.float32, TOL)
 
 
-@pytest.mark.parametrize("tag", ["vae_sym", "vae_nosym"])
+@pytest.mark.parametrize("tag", ["vae_sym", "vae_nosym", "vae_noneq"])
 def test_cgvae_model_golden(tag):
     pc.cgvae_model(DEV, tag, torch.float32, TOL)
 

@@ -47,7 +47,7 @@ def test_blocks_with_every_registry_activation(act):
     pc.blocks_with_activation("cpu", act, torch.float64, 1e-10)
 
 
-@pytest.mark.parametrize("tag", ["vae_sym", "vae_nosym"])
+@pytest.mark.parametrize("tag", ["vae_sym", "vae_nosym", "vae_noneq"])
 @pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-9), (torch.float32, 5e-5)])
 def test_cgvae_model(tag, dtype, tol):
     pc.cgvae_model("cpu", tag, dtype, tol)
