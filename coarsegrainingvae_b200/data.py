@@ -35,8 +35,21 @@ def get_neighbor_list_batch(xyz, num_atoms, cutoff, undirected=True):
     return ops.radius_graph(xyz, cutoff, undirected=undirected, frame_ptr=frame_ptr.to(xyz.device), use_cells=use_cells)
 
 
+def bond_cg_graph(bond_edge_list, mapping, n_cgs):
+    """CG graph derived from the bond graph (data.py:227-248): beads I != J are neighbours iff some bond joins an atom of
+    I to an atom of J.  The reference forms assign^T . adj . assign as dense float matrices and takes ``nonzero()``; this
+    is the same set in the same (row-major, both directions) order from integer keys -- dataset-preparation time, on the
+    device the lists live on (the reference keeps them on the CPU)."""
+    bond = torch.as_tensor(bond_edge_list, dtype=torch.int64)
+    mapping = torch.as_tensor(mapping, dtype=torch.int64)
+    a, b = mapping[bond[:, 0]], mapping[bond[:, 1]]
+    keys = torch.cat([a * n_cgs + b, b * n_cgs + a])
+    keys = torch.unique(keys[torch.cat([a != b, a != b])])          # sorted: row-major order of nonzero()
+    return torch.stack([keys // n_cgs, keys % n_cgs], 1)
+
+
 class CGDataset(TorchDataset):
-    """data.py:186-252 (the radius-graph part; the bond-derived CG graph of :227-248 stays host-side)."""
+    """data.py:186-252."""
 
     def __init__(self, props, check_props=True):
         self.props = props
@@ -56,9 +69,10 @@ class CGDataset(TorchDataset):
         else:
             nbr_list = self._batched(self.props['nxyz'], atom_cutoff, device, undirected)
         if cg_cutoff is None:
-            raise NotImplementedError("cg_cutoff=None (bond-derived CG graph, data.py:227-248) is host-side preprocessing, "
-                                      "out of the hot-path scope")
-        cg_nbr_list = self._batched(self.props['CG_nxyz'], cg_cutoff, device, undirected)
+            cg_nbr_list = [bond_cg_graph(bond, self.props['CG_mapping'][i], int(self.props['num_CGs'][i]))
+                           for i, bond in enumerate(self.props['bond_edge_list'])]
+        else:
+            cg_nbr_list = self._batched(self.props['CG_nxyz'], cg_cutoff, device, undirected)
         self.props['nbr_list'] = nbr_list
         self.props['CG_nbr_list'] = cg_nbr_list
 
