@@ -141,6 +141,53 @@ def blocks(ref_conv):
     _save("blocks_small.npz", store)
 
 
+def blocks_activations(ref_conv):
+    """blocks_act.npz: the K=3 message block and the UpdateBlock built by the REAL reference with every other entry of its
+    layer_types registry (modules.py:32-42) -- pins the oracle's activation table, which the CUDA epilogue codes 2..7 are
+    then tested against."""
+    gen = torch.Generator().manual_seed(77)
+    F, R, N, cutoff = 16, 4, 11, 4.0
+    store = {"meta/F": F, "meta/R": R, "meta/N": N, "meta/cutoff": cutoff}
+    xyz = torch.randn(N, 3, generator=gen) * 1.5
+    half = _sym_edges(N, 0.6, gen)
+    nbrs, _ = ref_conv.make_directed(half)
+    r = xyz[nbrs[:, 1]] - xyz[nbrs[:, 0]]
+    store["in/nbrs"], store["in/r"] = _np(nbrs), _np(r)
+
+    def rnd(*shape):
+        return torch.randn(*shape, generator=gen)
+
+    torch.manual_seed(12)
+    for act in ("ReLU", "Tanh", "sigmoid", "shifted_softplus", "LeakyReLU", "ELU"):
+        blk = ref_conv.EquiMessageBlock(feat_dim=F, activation=act, n_rbf=R, cutoff=cutoff, dropout=0.0)
+        for p in blk.parameters():
+            if p.dim() == 1:
+                p.data.normal_(0, 0.3, generator=gen)
+        s, v = rnd(N, F).requires_grad_(), rnd(N, F, 3).requires_grad_()
+        ds, dv = blk(s, v, r, nbrs)
+        gs, gv = rnd(N, F), rnd(N, F, 3)
+        ((ds * gs).sum() + (dv * gv).sum()).backward()
+        tag = "msg_" + act
+        _state(tag, blk, store)
+        _grads(tag, blk, store)
+        for k, t in (("s", s), ("v", v), ("ds", ds), ("dv", dv), ("gs", gs), ("gv", gv), ("grad_s", s.grad), ("grad_v", v.grad)):
+            store["%s/%s" % (tag, k)] = _np(t)
+        blk = ref_conv.UpdateBlock(feat_dim=F, activation=act, dropout=0.0)
+        for p in blk.parameters():
+            if p.dim() == 1:
+                p.data.normal_(0, 0.3, generator=gen)
+        s, v = rnd(N, F).requires_grad_(), rnd(N, F, 3).requires_grad_()
+        ds, dv = blk(s, v)
+        gs, gv = rnd(N, F), rnd(N, F, 3)
+        ((ds * gs).sum() + (dv * gv).sum()).backward()
+        tag = "upd_" + act
+        _state(tag, blk, store)
+        _grads(tag, blk, store)
+        for k, t in (("s", s), ("v", v), ("ds", ds), ("dv", dv), ("gs", gs), ("gv", gv), ("grad_s", s.grad), ("grad_v", v.grad)):
+            store["%s/%s" % (tag, k)] = _np(t)
+    _save("blocks_act.npz", store)
+
+
 def _molecule_batch(ref_data, gen, n_conf, n_atoms, mapping, atom_cutoff, cg_cutoff, spread):
     samples = []
     n_cg = int(mapping.max()) + 1
@@ -278,6 +325,7 @@ def main():
     torch.set_num_threads(1)
     ref_modules, ref_conv, ref_cgvae, ref_data = ref_shim.import_reference()
     blocks(ref_conv)
+    blocks_activations(ref_conv)
     cgvae_small(ref_cgvae, ref_data)
     cgvae_small(ref_cgvae, ref_data, fname="cgvae_noneq.npz", cases=(("vae_noneq", True, False),), seed=22)
     pcn_small(ref_cgvae, ref_data)
