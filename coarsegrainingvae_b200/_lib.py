@@ -25,6 +25,7 @@ SIGNATURES = {
     "cgvae_abi_version": (_INT, []),
     "cgvae_last_error": (ctypes.c_char_p, []),
     "cgvae_launch_count": (ctypes.c_ulonglong, []),
+    "cgvae_set_error_flags": (_INT, [_INT, _P]),
     "cgvae_radius_graph_ws_bytes": (_SZ, [_I64, _I64]),
     "cgvae_radius_graph_count": (_INT, [_P, _I64, _P, _I64, _F32, _INT, _INT, _P, _P, _SZ, _P]),
     "cgvae_radius_graph_fill": (_INT, [_P, _I64, _P, _I64, _F32, _INT, _INT, _P, _P, _P, _SZ, _P]),
@@ -54,11 +55,12 @@ SIGNATURES = {
     "cgvae_update_norm_bwd": (_INT, [_P, _P, _P, _P, _I64, _INT, _INT, _P, _P, _P]),
     "cgvae_segment_reduce_fwd": (_INT, [_P, _P, _P, _I64, _I64, _INT, _P, _P]),
     "cgvae_segment_reduce_bwd": (_INT, [_P, _P, _P, _I64, _I64, _INT, _P, _P]),
-    "cgvae_gather_rows": (_INT, [_P, _P, _I64, _I64, _P, _P]),
+    "cgvae_gather_rows": (_INT, [_P, _P, _I64, _I64, _I64, _P, _P]),
     "cgvae_lift_fwd": (_INT, [_P, _P, _P, _P, _P, _P, _P, _I64, _I64, _INT, _INT, _P, _P]),
     "cgvae_lift_bwd": (_INT, [_P, _P, _P, _P, _P, _P, _I64, _I64, _INT, _INT, _P, _P]),
     "cgvae_adam_ws_bytes": (_SZ, []),
-    "cgvae_adam_clip_step": (_INT, [_P, _P, _P, _P, _I64, _F32, _F32, _F32, _F32, _F32, _F32, _P, _P, _P, _SZ, _P]),
+    "cgvae_adam_clip_step": (_INT, [_P, _P, _P, _P, _I64, _F32, _F32, _F32, _F32, _F32, _F32, _P, _P, _P, _F32, _F32, _P,
+                                    _P, _SZ, _P]),
     "cgvae_vec_to_planar": (_INT, [_P, _I64, _INT, _P, _P]),
     "cgvae_vec_from_planar": (_INT, [_P, _I64, _INT, _P, _P]),
 }

@@ -18,7 +18,7 @@ class BatchGraphs(object):
     """CSR graphs and segment tables of one batch, built once and shared by encoder / prior / decoder
     (the reference re-runs make_directed in each of them: cgvae.py:270-271,378,87,165)."""
 
-    def __init__(self, nbr_count=None, cg_nbr_count=None):
+    def __init__(self, nbr_count=None, cg_nbr_count=None, nbr_symmetrize=True, cg_nbr_symmetrize=True):
         self.atom = None      # ops.Graph over atoms (directed)
         self.cg = None        # ops.Graph over beads (directed)
         self.seg = None       # ops.Segments (mapping)
@@ -28,11 +28,22 @@ class BatchGraphs(object):
         # capacity and these int64 device scalars hold the live row counts; the flipped half of make_directed is
         # generated inside the CSR kernels and no host read happens.
         self.counts = {"atom": nbr_count, "cg": cg_nbr_count}
+        # make_directed (conv.py:10-20) appends the flipped list only when the list is one-directional; its two
+        # ``.any().item()`` reads are taken on the host when the static batch is prepared (train.to_static_batch) and
+        # arrive here as plain bools: a bidirectional list (dir_mp=True, or the bond-derived CG graph of
+        # cg_cutoff=None) must NOT be doubled.
+        self.symmetrize = {"atom": bool(nbr_symmetrize), "cg": bool(cg_nbr_symmetrize)}
+
+    @classmethod
+    def for_batch(cls, batch):
+        return cls(batch.get('nbr_count'), batch.get('CG_nbr_count'), batch.get('nbr_symmetrize', True),
+                   batch.get('CG_nbr_symmetrize', True))
 
     def directed_graph(self, which, nbr_list, n_nodes, already_directed=False):
         count = self.counts.get(which)
         if count is not None:
-            return ops.build_graph(nbr_list, n_nodes, symmetrize=True, n_edges_dev=count)
+            sym = self.symmetrize.get(which, True) and not already_directed
+            return ops.build_graph(nbr_list, n_nodes, symmetrize=sym, n_edges_dev=count)
         pairs = nbr_list if already_directed else make_directed(nbr_list)[0]
         return ops.build_graph(pairs, n_nodes)
 
@@ -262,7 +273,7 @@ class CGequiVAE(nn.Module):
     def forward(self, batch, eps=None):
         atomic_nums, cg_z, xyz, cg_xyz, nbr_list, CG_nbr_list, mapping, num_CGs = self.get_inputs(batch)
         xyz, cg_xyz = xyz.contiguous(), cg_xyz.contiguous()
-        g = batch.get('_graphs') or BatchGraphs(batch.get('nbr_count'), batch.get('CG_nbr_count'))
+        g = batch.get('_graphs') or BatchGraphs.for_batch(batch)
         S_I, s_i = self.encoder(atomic_nums, xyz, cg_xyz, mapping, nbr_list, CG_nbr_list, graphs=g,
                                 num_beads=cg_xyz.shape[0])
         if self.prior_net:
@@ -275,6 +286,7 @@ class CGequiVAE(nn.Module):
         sigma = 1e-12 + torch.exp(logvar / 2)
         z_sample = self.reparametrize(mu, sigma, eps) if not self.det else z
         xyz_recon = self.decoder(cg_xyz, CG_nbr_list, z_sample, s_i, mapping, num_CGs, graphs=g)
+        ops.check_device_errors(xyz_recon.device)      # IndexError where the reference raises one (cgvae.py:473)
         return mu, sigma, H_prior_mu, H_prior_sigma, xyz, xyz_recon
 
 
@@ -318,5 +330,7 @@ class PCN(nn.Module):
         cg_z, xyz, cg_xyz, nbr_list, CG_nbr_list, mapping, num_CGs = self.get_inputs(batch)
         S_I = _embed(self.embedding, cg_z)
         xyz_recon = self.decoder(cg_xyz.contiguous(), CG_nbr_list, S_I, batch['ca_idx'], mapping, num_CGs,
-                                 graphs=batch.get('_graphs') or BatchGraphs(None, batch.get('CG_nbr_count')))
+                                 graphs=batch.get('_graphs') or BatchGraphs(None, batch.get('CG_nbr_count'), True,
+                                                                            batch.get('CG_nbr_symmetrize', True)))
+        ops.check_device_errors(xyz_recon.device)
         return None, None, None, None, xyz, xyz_recon

@@ -131,8 +131,7 @@ class EquiMessagePsuedo(nn.Module):
         return fn.Message9Block.apply(geom, True, self.inv_message.act, s, sbar, v, vbar, *self.inv_message.params())
 
     def forward(self, s_j, sbar_j, v_j, vbar_j, r_ij, nbrs, edge_wgt=None):
-        if edge_wgt is not None:
-            raise NotImplementedError("EquiMessagePsuedo ignores edge_wgt in the reference as well (conv.py:187)")
+        # edge_wgt is accepted and ignored, exactly like the reference (conv.py:180-187 never reads it)
         geom = _geometry_from_edges(nbrs, r_ij, s_j.shape[0], self.inv_message.n_rbf, self.inv_message.cutoff)
         ds, dsbar, dv, dvbar = fn.Message9Block.apply(geom, False, self.inv_message.act, s_j, sbar_j, _Planar.apply(v_j), _Planar.apply(vbar_j),
                                                       *self.inv_message.params())

@@ -17,6 +17,22 @@ constexpr int kNumSM = 148;  // B200: 2 dies x 74 SMs
 extern thread_local char g_err[512];
 extern std::atomic<unsigned long long> g_launches;
 
+// Device-side index validation.  The raw-pointer kernels cannot raise, so an out-of-range index (atoms of a bead >= F
+// at the lifting gather, an embedding id >= table rows, a bead / node index outside its range) is SKIPPED (never read
+// or written out of bounds) and recorded as a bit in a caller-owned int32 word registered per device with
+// cgvae_set_error_flags(); the host turns it into the IndexError the reference raises (cgvae.py:473, nn.Embedding).
+enum { CGVAE_ERR_LIFT_RANK = 1, CGVAE_ERR_EMBED_INDEX = 2, CGVAE_ERR_BEAD_INDEX = 4, CGVAE_ERR_NODE_INDEX = 8 };
+constexpr int kMaxDevices = 64;
+extern std::atomic<int32_t*> g_err_flags[kMaxDevices];
+inline int32_t* err_flags() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= kMaxDevices) return nullptr;
+  return g_err_flags[d].load(std::memory_order_relaxed);
+}
+__device__ __forceinline__ void raise_flag(int32_t* flags, int bit) {
+  if (flags != nullptr) atomicOr(flags, bit);
+}
+
 inline int fail(int code, const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);

@@ -7,6 +7,7 @@ namespace cgvae {
 
 thread_local char g_err[512] = {0};
 std::atomic<unsigned long long> g_launches{0};
+std::atomic<int32_t*> g_err_flags[kMaxDevices];
 
 bool pdl_enabled() {
   static const bool on = [] {
@@ -394,11 +395,13 @@ __device__ __forceinline__ bool directed_edge(const int64_t* __restrict__ pairs,
 }
 
 __global__ void csr_count_kernel(const int64_t* __restrict__ pairs, int64_t E, const int64_t* __restrict__ n_dev, int symmetrize,
-                                 int32_t* __restrict__ deg_r, int32_t* __restrict__ deg_s) {
+                                 int64_t n_recv, int64_t n_send, int32_t* __restrict__ deg_r, int32_t* __restrict__ deg_s,
+                                 int32_t* __restrict__ err) {
   CGVAE_KERNEL_PROLOGUE();
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t i, j;
   if (!directed_edge(pairs, e, E, n_dev, symmetrize, i, j)) return;
+  if (i < 0 || i >= n_recv || j < 0 || j >= n_send) { raise_flag(err, CGVAE_ERR_NODE_INDEX); return; }
   atomicAdd(&deg_r[i], 1);
   atomicAdd(&deg_s[j], 1);
 }
@@ -407,11 +410,12 @@ __global__ void csr_count_kernel(const int64_t* __restrict__ pairs, int64_t E, c
 __global__ void csr_place_kernel(const int64_t* __restrict__ pairs, int64_t E, const int64_t* __restrict__ n_dev, int symmetrize,
                                  const int32_t* __restrict__ rowptr_r, const int32_t* __restrict__ rowptr_s,
                                  int32_t* __restrict__ cursor_r, int32_t* __restrict__ cursor_s,
-                                 int32_t* __restrict__ eid_r, int32_t* __restrict__ eid_s) {
+                                 int32_t* __restrict__ eid_r, int32_t* __restrict__ eid_s, int64_t n_recv, int64_t n_send) {
   CGVAE_KERNEL_PROLOGUE();
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t i, j;
   if (!directed_edge(pairs, e, E, n_dev, symmetrize, i, j)) return;
+  if (i < 0 || i >= n_recv || j < 0 || j >= n_send) return;   // flagged by csr_count_kernel
   eid_r[rowptr_r[i] + atomicAdd(&cursor_r[i], 1)] = (int32_t)e;
   eid_s[rowptr_s[j] + atomicAdd(&cursor_s[j], 1)] = (int32_t)e;
 }
@@ -447,24 +451,30 @@ __global__ void csr_finish_s_kernel(const int64_t* __restrict__ pairs, int64_t E
 // ------------------------------------------------------------------------------------------
 // segment ranks (CG2ChannelIdx)
 // ------------------------------------------------------------------------------------------
-__global__ void segment_count_kernel(const int64_t* __restrict__ mapping, int64_t n, int32_t* __restrict__ deg) {
-  CGVAE_KERNEL_PROLOGUE();
-  const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (a < n) atomicAdd(&deg[mapping[a]], 1);
-}
-__global__ void segment_place_kernel(const int64_t* __restrict__ mapping, int64_t n, const int32_t* __restrict__ rowptr_b,
-                                     int32_t* __restrict__ cursor, int32_t* __restrict__ atoms) {
+__global__ void segment_count_kernel(const int64_t* __restrict__ mapping, int64_t n, int64_t n_beads, int32_t* __restrict__ deg,
+                                     int32_t* __restrict__ err) {
   CGVAE_KERNEL_PROLOGUE();
   const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= n) return;
   const int64_t b = mapping[a];
+  if (b < 0 || b >= n_beads) { raise_flag(err, CGVAE_ERR_BEAD_INDEX); return; }
+  atomicAdd(&deg[b], 1);
+}
+__global__ void segment_place_kernel(const int64_t* __restrict__ mapping, int64_t n, int64_t n_beads,
+                                     const int32_t* __restrict__ rowptr_b, int32_t* __restrict__ cursor, int32_t* __restrict__ atoms) {
+  CGVAE_KERNEL_PROLOGUE();
+  const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n) return;
+  const int64_t b = mapping[a];
+  if (b < 0 || b >= n_beads) return;                           // flagged by segment_count_kernel
   atoms[rowptr_b[b] + atomicAdd(&cursor[b], 1)] = (int32_t)a;
 }
-__global__ void segment_rank_kernel(const int64_t* __restrict__ mapping, int64_t n, const int32_t* __restrict__ rowptr_b,
-                                    const int32_t* __restrict__ atoms, int32_t* __restrict__ slot_of_atom, int64_t* __restrict__ rank) {
+__global__ void segment_rank_kernel(const int64_t* __restrict__ mapping, int64_t n, int64_t n_beads,
+                                    const int32_t* __restrict__ rowptr_b, const int32_t* __restrict__ atoms,
+                                    int32_t* __restrict__ slot_of_atom, int64_t* __restrict__ rank) {
   CGVAE_KERNEL_PROLOGUE();
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n) return;
+  if (t >= n || t >= rowptr_b[n_beads]) return;                 // fewer live slots only when indices were rejected
   const int a = atoms[t];
   slot_of_atom[a] = (int32_t)t;
   rank[a] = t - rowptr_b[mapping[a]];
@@ -479,6 +489,11 @@ extern "C" {
 int cgvae_abi_version(void) { return CGVAE_ABI_VERSION; }
 const char* cgvae_last_error(void) { return g_err; }
 unsigned long long cgvae_launch_count(void) { return g_launches.load(); }
+int cgvae_set_error_flags(int device, int32_t* flags) {
+  CGVAE_REQUIRE(device >= 0 && device < kMaxDevices, "set_error_flags: bad device %d", device);
+  g_err_flags[device].store(flags);
+  return 0;
+}
 
 size_t cgvae_radius_graph_ws_bytes(int64_t n, int64_t n_frames) {
   return radius_ws_layout(n > 0 ? n : 1, n_frames > 0 ? n_frames : 1, nullptr, nullptr) + 256;
@@ -569,7 +584,8 @@ int cgvae_csr_count(const int64_t* pairs, int64_t n_edges, const int64_t* n_edge
   CGVAE_ZERO(deg_r, sizeof(int32_t) * (size_t)n_recv, st);
   CGVAE_ZERO(deg_s, sizeof(int32_t) * (size_t)n_send, st);
   if (cap == 0) return 0;
-  launch_kernel(csr_count_kernel, dim3((unsigned)ceil_div(cap, 256)), dim3(256), 0, st, pairs, n_edges, n_edges_dev, symmetrize, deg_r, deg_s);
+  launch_kernel(csr_count_kernel, dim3((unsigned)ceil_div(cap, 256)), dim3(256), 0, st, pairs, n_edges, n_edges_dev, symmetrize, n_recv, n_send, deg_r, deg_s,
+                err_flags());
   return launched("csr_count");
 }
 
@@ -587,7 +603,8 @@ int cgvae_csr_fill(const int64_t* pairs, int64_t n_edges_in, const int64_t* n_ed
   int32_t* slot_of_edge = eid_s + n_edges;
   CGVAE_ZERO(cursor_r, sizeof(int32_t) * (size_t)(n_recv + n_send), st);
   const unsigned gb = (unsigned)ceil_div(n_edges, 256);
-  launch_kernel(csr_place_kernel, dim3(gb), dim3(256), 0, st, pairs, n_edges_in, n_edges_dev, symmetrize, rowptr_r, rowptr_s, cursor_r, cursor_s, eid, eid_s);
+  launch_kernel(csr_place_kernel, dim3(gb), dim3(256), 0, st, pairs, n_edges_in, n_edges_dev, symmetrize, rowptr_r, rowptr_s, cursor_r, cursor_s, eid, eid_s,
+                n_recv, n_send);
   if (int rc = launched("csr_place")) return rc;
   // rows were filled in atomic (arbitrary) order: sorting by edge id makes the layout deterministic and
   // keeps the reference's edge-list order inside every row
@@ -608,7 +625,7 @@ int cgvae_segment_count(const int64_t* mapping, int64_t n, int64_t n_beads, int3
   CGVAE_REQUIRE(deg && n >= 0 && n < INT_MAX, "segment_count: bad arguments");
   CGVAE_ZERO(deg, sizeof(int32_t) * (size_t)n_beads, st);
   if (n == 0) return 0;
-  launch_kernel(segment_count_kernel, dim3((unsigned)ceil_div(n, 256)), dim3(256), 0, st, mapping, n, deg);
+  launch_kernel(segment_count_kernel, dim3((unsigned)ceil_div(n, 256)), dim3(256), 0, st, mapping, n, n_beads, deg, err_flags());
   return launched("segment_count");
 }
 
@@ -619,11 +636,11 @@ int cgvae_segment_rank(const int64_t* mapping, int64_t n, int64_t n_beads, const
   CGVAE_REQUIRE(mapping && rowptr_b && scratch && atoms && slot_of_atom && rank, "segment_rank: null pointer");
   CGVAE_ZERO(scratch, sizeof(int32_t) * (size_t)n_beads, st);
   const unsigned gb = (unsigned)ceil_div(n, 256);
-  launch_kernel(segment_place_kernel, dim3(gb), dim3(256), 0, st, mapping, n, rowptr_b, scratch, atoms);
+  launch_kernel(segment_place_kernel, dim3(gb), dim3(256), 0, st, mapping, n, n_beads, rowptr_b, scratch, atoms);
   if (int rc = launched("segment_place")) return rc;
   launch_kernel(sort_rows_kernel, dim3((unsigned)ceil_div(n_beads, kSortWarps)), dim3(kSortWarps * 32), 0, st, rowptr_b, n_beads, atoms);
   if (int rc = launched("segment_sort")) return rc;
-  launch_kernel(segment_rank_kernel, dim3(gb), dim3(256), 0, st, mapping, n, rowptr_b, atoms, slot_of_atom, rank);
+  launch_kernel(segment_rank_kernel, dim3(gb), dim3(256), 0, st, mapping, n, n_beads, rowptr_b, atoms, slot_of_atom, rank);
   return launched("segment_rank");
 }
 

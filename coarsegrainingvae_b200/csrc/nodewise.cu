@@ -114,19 +114,26 @@ __global__ void __launch_bounds__(256) segment_reduce_bwd_kernel(const float* __
 }
 
 __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ table, const int64_t* __restrict__ idx, int64_t W,
-                                                          float* __restrict__ out) {
+                                                          int64_t n_rows, float* __restrict__ out, int32_t* __restrict__ err) {
   CGVAE_KERNEL_PROLOGUE();
   const int64_t n = blockIdx.x;
   const int64_t w = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
   if (w >= W) return;
-  out[n * W + w] = table[idx[n] * W + w];
+  const int64_t r = idx[n];
+  if (n_rows > 0 && (r < 0 || r >= n_rows)) {                  // nn.Embedding raises IndexError here
+    if (w == 0) raise_flag(err, CGVAE_ERR_EMBED_INDEX);
+    out[n * W + w] = __int_as_float(0x7fc00000);
+    return;
+  }
+  out[n * W + w] = table[r * W + w];
 }
 
 // warp per bead.  mode 0: plain gather; 1: subtract the bead mean; 2: zero pinned atoms
 __global__ void __launch_bounds__(128) lift_fwd_kernel(const float* __restrict__ V, const float* __restrict__ cg_xyz,
                                                        const int64_t* __restrict__ rank, const int32_t* __restrict__ rowptr_b,
                                                        const int32_t* __restrict__ atoms, const uint8_t* __restrict__ pin,
-                                                       int64_t n_beads, int F, int mode, float* __restrict__ xyz_out) {
+                                                       int64_t n_beads, int F, int mode, float* __restrict__ xyz_out,
+                                                       int32_t* __restrict__ err) {
   CGVAE_KERNEL_PROLOGUE();
   const int lane = threadIdx.x & 31;
   const int64_t b = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
@@ -137,6 +144,7 @@ __global__ void __launch_bounds__(128) lift_fwd_kernel(const float* __restrict__
   if (mode == 1) {
     for (int t = beg + lane; t < end; t += 32) {
       const int64_t ch = rank[atoms[t]];
+      if (ch >= F) continue;                                   // more atoms in the bead than channels: flagged below
 #pragma unroll
       for (int c = 0; c < 3; ++c) mean[c] += Vb[(int64_t)c * F + ch];
     }
@@ -148,6 +156,13 @@ __global__ void __launch_bounds__(128) lift_fwd_kernel(const float* __restrict__
     const int a = atoms[t];
     const int64_t ch = rank[a];
     const bool pinned = (mode == 2) && pin != nullptr && pin[a] != 0;
+    if (ch >= F) {
+      // the reference raises IndexError at cg_v[mapping, CG2atomChannel] (cgvae.py:473): no read, NaN out, flag
+      raise_flag(err, CGVAE_ERR_LIFT_RANK);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) xyz_out[(int64_t)a * 3 + c] = __int_as_float(0x7fc00000);
+      continue;
+    }
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       const float rel = pinned ? 0.f : Vb[(int64_t)c * F + ch] - mean[c];
@@ -180,6 +195,7 @@ __global__ void __launch_bounds__(128) lift_bwd_kernel(const float* __restrict__
     const int a = atoms[t];
     const int64_t ch = rank[a];
     const bool pinned = (mode == 2) && pin != nullptr && pin[a] != 0;
+    if (ch >= F) continue;                                     // flagged by lift_fwd_kernel; never write past the bead row
 #pragma unroll
     for (int c = 0; c < 3; ++c) gVb[(int64_t)c * F + ch] = pinned ? 0.f : g_xyz[(int64_t)a * 3 + c] - mean[c];
   }
@@ -236,11 +252,12 @@ int cgvae_segment_reduce_bwd(const float* g_out, const int64_t* mapping, const i
   launch_kernel(segment_reduce_bwd_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, g_out, mapping, rowptr_b, W, mean, g_X);
   return launched("segment_reduce_bwd");
 }
-int cgvae_gather_rows(const float* table, const int64_t* idx, int64_t N, int64_t W, float* out, cgvae_stream_t stream) {
+int cgvae_gather_rows(const float* table, const int64_t* idx, int64_t N, int64_t W, int64_t n_rows, float* out,
+                      cgvae_stream_t stream) {
   if (N == 0 || W == 0) return 0;
   CGVAE_REQUIRE(table && idx && out, "gather_rows: null pointer");
   dim3 grid((unsigned)N, (unsigned)ceil_div(W, 256));
-  launch_kernel(gather_rows_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, table, idx, W, out);
+  launch_kernel(gather_rows_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, table, idx, W, n_rows, out, err_flags());
   return launched("gather_rows");
 }
 
@@ -252,7 +269,7 @@ int cgvae_lift_fwd(const float* V, const float* cg_xyz, const int64_t* mapping, 
   CGVAE_REQUIRE(V && cg_xyz && rank && rowptr_b && atoms && xyz_out, "lift_fwd: null pointer");
   CGVAE_REQUIRE(mode >= 0 && mode <= 2, "lift_fwd: bad mode %d", mode);
   launch_kernel(lift_fwd_kernel, dim3((unsigned)ceil_div(n_beads, 4)), dim3(128), 0, (cudaStream_t)stream, V, cg_xyz, rank, rowptr_b, atoms, pin, n_beads, F,
-                                                                                   mode, xyz_out);
+                                                                                   mode, xyz_out, err_flags());
   return launched("lift_fwd");
 }
 int cgvae_lift_bwd(const float* g_xyz, const int64_t* mapping, const int64_t* rank, const int32_t* rowptr_b, const int32_t* atoms,

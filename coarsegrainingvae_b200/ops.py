@@ -47,6 +47,39 @@ def launch_count():
     return _lib.launch_count()
 
 
+# Device-side index validation (cgvae_set_error_flags): one int32 word per device, owned here.  Kernels skip an
+# out-of-range index and OR a bit into it; check_device_errors() reads it (one host sync) and raises what the
+# reference raises.  The model forwards call it in eager mode (VALIDATE) -- never while a CUDA graph is being captured;
+# static-capacity batches are validated on the host instead (train.validate_batch).
+VALIDATE = True
+_ERR_FLAGS = {}
+_ERR_TEXT = {1: "a bead holds more atoms than feature channels (cg_v[mapping, CG2atomChannel], cgvae.py:473)",
+             2: "embedding index out of range (nn.Embedding, cgvae.py:273,380,591)",
+             4: "CG_mapping entry outside [0, n_beads)",
+             8: "edge-list entry outside [0, n_nodes)"}
+
+
+def error_flags(device):
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    t = _ERR_FLAGS.get(idx)
+    if t is None:
+        t = torch.zeros(1, dtype=torch.int32, device=torch.device("cuda", idx))
+        _ERR_FLAGS[idx] = t
+        _lib.check(_lib.load().cgvae_set_error_flags(idx, t.data_ptr()), "set_error_flags")
+    return t
+
+
+def check_device_errors(device, force=False):
+    """raise IndexError if a kernel rejected an index since the last check (synchronises the device)."""
+    if not (VALIDATE or force) or device.type != "cuda" or torch.cuda.is_current_stream_capturing():
+        return
+    t = error_flags(device)
+    bits = int(t.item())
+    if bits:
+        t.zero_()
+        raise IndexError("; ".join(msg for bit, msg in _ERR_TEXT.items() if bits & bit))
+
+
 class KernelTimer(object):
     """Optional CUDA-event timing of individual kernel launches on the launching stream (bench.py uses it for the
     live roofline figure).  ``records[name]`` = list of (start_event, end_event, meta)."""
@@ -278,6 +311,7 @@ def build_graph(pairs, n_recv, n_send=None, symmetrize=False, n_edges_dev=None):
     dev = pairs.device
     st = _stream()
     sym = int(bool(symmetrize))
+    error_flags(dev)
     deg_r = torch.empty(n_recv, dtype=torch.int32, device=dev)
     deg_s = torch.empty(n_send, dtype=torch.int32, device=dev)
     _lib.check(lib.cgvae_csr_count(_p(pairs), E_in, _p(n_edges_dev), sym, n_recv, n_send, _p(deg_r), _p(deg_s), st), "csr_count")
@@ -301,6 +335,7 @@ def build_segments(mapping, n_beads):
     n = mapping.shape[0]
     dev = mapping.device
     st = _stream()
+    error_flags(dev)
     deg = torch.empty(n_beads, dtype=torch.int32, device=dev)
     _lib.check(lib.cgvae_segment_count(_p(mapping), n, n_beads, _p(deg), st), "segment_count")
     rowptr = exclusive_scan(deg, torch.int32)
@@ -735,7 +770,8 @@ def gather_rows(table, idx):
     idx = idx.to(torch.int64).contiguous()
     W = table.shape[1]
     out = torch.empty((idx.shape[0], W), dtype=torch.float32, device=table.device)
-    _lib.check(lib.cgvae_gather_rows(_p(table), _p(idx), idx.shape[0], W, _p(out), _stream()), "gather_rows")
+    error_flags(table.device)
+    _lib.check(lib.cgvae_gather_rows(_p(table), _p(idx), idx.shape[0], W, table.shape[0], _p(out), _stream()), "gather_rows")
     return out
 
 
@@ -744,6 +780,7 @@ def lift_fwd(V, cg_xyz, seg, mode, pin):
     lib = _lib.load()
     F = V.shape[-1]
     out = torch.empty((seg.n, 3), dtype=torch.float32, device=V.device)
+    error_flags(V.device)
     _lib.check(lib.cgvae_lift_fwd(_p(V), _p(_f32(cg_xyz)), _p(seg.mapping), _p(seg.rank), _p(seg.rowptr), _p(seg.atoms), _p(pin),
                                   seg.n, seg.n_beads, F, mode, _p(out), _stream()), "lift_fwd")
     return out
@@ -778,16 +815,20 @@ def vec_from_planar(v_n3f):
     return out
 
 
-def adam_clip_step(p, g, m, v, step, max_norm, lr, betas=(0.9, 0.999), eps=1e-8, norm_out=None, grad_scale=1.0):
+def adam_clip_step(p, g, m, v, step, max_norm, lr, betas=(0.9, 0.999), eps=1e-8, norm_out=None, grad_scale=1.0,
+                   loss=None, loss_scale=1.0, loss_limit=float("inf"), skipped=None):
     """fused clip_grad_norm_ + Adam on flat buffers (cgvae_adam_clip_step); all tensors flat fp32 CUDA, `step` float [1];
-    the gradients are taken as grad_scale * g (1/world after an all-reduce(sum))."""
+    the gradients are taken as grad_scale * g (1/world after an all-reduce(sum)).  loss (device float [1], optional):
+    the reference's skip guard (scripts/utils.py:145-148) -- the step is a no-op when loss*loss_scale is NaN or >=
+    loss_limit (or the gradient norm is not finite); skipped (device float [1], optional) counts such steps."""
     _need_cuda(p, g, m, v, step)
     lib = _lib.load()
     ws_bytes = int(lib.cgvae_adam_ws_bytes())
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=p.device)
     t0 = TIMER.begin("adam_clip") if TIMER is not None else None
     _lib.check(lib.cgvae_adam_clip_step(_p(p), _p(g), _p(m), _p(v), p.numel(), float(max_norm), float(grad_scale), float(lr), float(betas[0]),
-                                        float(betas[1]), float(eps), _p(step), _p(norm_out), _p(ws), ws_bytes, _stream()),
+                                        float(betas[1]), float(eps), _p(step), _p(norm_out), _p(loss), float(loss_scale),
+                                        float(min(loss_limit, 3.0e38)), _p(skipped), _p(ws), ws_bytes, _stream()),
                "adam_clip_step")
     if t0 is not None:
         TIMER.end("adam_clip", t0, dict(n=p.numel()))

@@ -12,27 +12,40 @@ EPS = 1e-6          # scripts/utils.py:27
 
 
 def kl_divergence(mu1, std1, mu2, std2):
-    """scripts/utils.py:81-86 -- note the reference divides (mu1-mu2)^2 by std2, not std2^2; kept."""
+    """scripts/utils.py:81-86 -- note the reference divides (mu1-mu2)^2 by std2, not std2^2; kept.  Without a prior
+    network (``mu2 is None``) the reference falls back to the KL against the standard normal (:82-83)."""
+    if mu2 is None:
+        return -0.5 * torch.sum(1 + torch.log(std1.pow(2)) - mu1.pow(2) - std1.pow(2), dim=-1).mean()
     return 0.5 * ((std1.pow(2) / std2.pow(2)).sum(-1) + ((mu1 - mu2).pow(2) / std2).sum(-1)
                   + torch.log(std2.pow(2)).sum(-1) - torch.log(std1.pow(2)).sum(-1) - std1.shape[-1]).mean()
 
 
-def training_loss(outputs, xyz, bond_edge_list, beta, gamma, bond_count=None):
+def training_loss(outputs, xyz, bond_edge_list, beta, gamma, bond_count=None, norms=None):
     """scripts/utils.py:117-141: MSE + beta*KL + gamma*bond-graph loss, all on the device (the reference moves the
     edge list and the target coordinates to the CPU first: utils.py:127-128).  ``bond_count`` (device scalar): number of
-    live rows of a zero-padded static-capacity ``bond_edge_list`` -- padded (0, 0) rows contribute exactly 0 to the sum."""
+    live rows of a zero-padded static-capacity ``bond_edge_list`` -- padded (0, 0) rows contribute exactly 0 to the sum.
+    ``norms`` (device float [3], data-parallel training): the denominators (atoms, beads, bonds) of the three means as
+    GLOBAL count / world, so that the mean over ranks of the local losses (and gradients) equals the single-process
+    ``mean()`` over the global batch even when the ranks hold different numbers of atoms / bonds."""
     mu, sigma, pmu, pstd, _, xyz_recon = outputs
-    recon = (xyz_recon - xyz).pow(2).mean()
+    if norms is None:
+        recon = (xyz_recon - xyz).pow(2).mean()
+    else:
+        recon = (xyz_recon - xyz).pow(2).sum() / (3.0 * norms[0])
     loss = recon
     kl = graph = None
     if mu is not None:
         kl = kl_divergence(mu, sigma, pmu, pstd)
+        if norms is not None:
+            kl = kl * (mu.shape[0] / norms[1])
         loss = loss + kl * beta
     if gamma != 0.0:
         a, b = bond_edge_list[:, 0], bond_edge_list[:, 1]
         gen = ((xyz_recon[a] - xyz_recon[b]).pow(2).sum(-1) + EPS).sqrt()
         dat = ((xyz[a] - xyz[b]).pow(2).sum(-1) + EPS).sqrt()
-        if bond_count is None:
+        if norms is not None:
+            graph = (gen - dat).pow(2).sum() / norms[2]
+        elif bond_count is None:
             graph = (gen - dat).pow(2).mean()
         else:
             graph = (gen - dat).pow(2).sum() / bond_count.to(gen.dtype).reshape(())
@@ -53,7 +66,13 @@ class FlatGrads(object):
         n = sum(p.numel() for p in self.params)
         dev = self.params[0].device if self.params else "cpu"
         dtype = self.params[0].dtype if self.params else torch.float32
-        self.flat = torch.zeros(n, dtype=dtype, device=dev)
+        # storage = [ gradients (n) | pad to 16 bytes | loss slot ]: the loss of the step rides at the tail so that the
+        # data-parallel all-reduce of ``buffer`` also sums the per-rank losses -- the skip guard of the reference loop
+        # (scripts/utils.py:145-148) is then decided on the SAME all-reduced value on every rank
+        pad = (-n) % 4
+        self.buffer = torch.zeros(n + pad + 4, dtype=dtype, device=dev)
+        self.flat = self.buffer[:n]
+        self.loss_slot = self.buffer[n + pad:n + pad + 1]
         self.sink = self.flat.is_cuda
         self.views = []
         off = 0
@@ -97,9 +116,9 @@ class FlatGrads(object):
         world = dist.get_world_size(group)
         if world == 1:
             return
-        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(self.buffer, op=dist.ReduceOp.SUM, group=group)      # gradients + the loss slot
         if not scale_in_optimizer:
-            self.flat.mul_(1.0 / world)
+            self.buffer.mul_(1.0 / world)
 
     def clip_(self, max_norm):
         """torch.nn.utils.clip_grad_norm_ semantics (scripts/utils.py:156) on the flat buffer; returns the norm."""
@@ -121,11 +140,17 @@ class TrainStep(object):
     """one optimisation step of scripts/utils.py::loop (train=True branch): forward, loss, backward, [all-reduce],
     clip_grad_norm_(0.01), Adam."""
 
-    def __init__(self, model, beta, gamma, lr=1e-4, max_norm=0.01, group=None, capturable=False, optimizer="fused"):
+    def __init__(self, model, beta, gamma, lr=1e-4, max_norm=0.01, group=None, capturable=False, optimizer="fused",
+                 loss_limit="reference"):
         """optimizer: "fused" = cgvae_adam_clip_step on flat parameter / gradient / moment buffers (CUDA only; the used
         parameters are re-pointed at views of one contiguous buffer), "torch" = clip on the flat gradients +
-        torch.optim.Adam (always used for CPU tensors)."""
+        torch.optim.Adam (always used for CPU tensors).
+        loss_limit: the skip guard of the reference loop -- a batch whose loss is NaN or >= loss_limit takes no optimiser
+        step (scripts/utils.py:145-148); "reference" = gamma * 200, None disables it.  With the fused optimiser the
+        decision is taken on the device (no host read, graph-capturable); ``skipped`` counts such steps."""
         self.model, self.beta, self.gamma = model, beta, gamma
+        self.loss_limit = (gamma * 200.0) if loss_limit == "reference" else loss_limit
+        self.skipped = None
         self.max_norm, self.group = max_norm, group
         self.lr = lr
         self.capturable = capturable
@@ -150,7 +175,29 @@ class TrainStep(object):
     def _loss(self, batch, eps):
         out = self.model(batch, eps=eps) if eps is not None else self.model(batch)
         xyz = out[4]
-        return training_loss(out, xyz, batch["bond_edge_list"], self.beta, self.gamma, batch.get("bond_count"))[0]
+        return training_loss(out, xyz, batch["bond_edge_list"], self.beta, self.gamma, batch.get("bond_count"),
+                             batch.get("dp_norms"))[0]
+
+    def update_dp_norms(self, batch):
+        """data parallel: (atoms, beads, bonds) of the GLOBAL batch divided by the world size, all-reduced into
+        ``batch['dp_norms']`` (a device float [3], updated in place when present so that a captured graph sees it)."""
+        import torch.distributed as dist
+        world = self._world()
+        if world == 1:
+            return batch
+        xyz = batch["nxyz"] if "nxyz" in batch else batch["xyz"]
+        beads = batch["CG_nxyz"] if "CG_nxyz" in batch else batch["ca_xyz"]
+        dev = xyz.device
+        bonds = batch["bond_count"].to(torch.float32).reshape(1) if "bond_count" in batch else \
+            torch.full((1,), float(batch["bond_edge_list"].shape[0]), device=dev)
+        counts = torch.cat([torch.tensor([float(xyz.shape[0]), float(beads.shape[0])], device=dev), bonds.to(dev)])
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=self.group)
+        counts = (counts / world).clamp_min(1.0)
+        if "dp_norms" in batch:
+            batch["dp_norms"].copy_(counts)
+        else:
+            batch["dp_norms"] = counts
+        return batch
 
     def prepare(self, batch, eps=None):
         """discover the used parameters with one dry backward and lay their gradients out in one flat buffer."""
@@ -176,6 +223,7 @@ class TrainStep(object):
             self.exp_avg = torch.zeros_like(self.flat_p)
             self.exp_avg_sq = torch.zeros_like(self.flat_p)
             self.step_count = torch.zeros(1, dtype=torch.float32, device=params[0].device)
+            self.skipped = torch.zeros(1, dtype=torch.float32, device=params[0].device)
         self.flat = FlatGrads(params)
         fused = self.flat.flat.is_cuda
         if self.flat_p is None:
@@ -225,6 +273,8 @@ class TrainStep(object):
                     loss.backward()
         else:
             loss.backward()
+        with torch.no_grad():
+            self.flat.loss_slot.copy_(loss.detach().reshape(1))     # read by the skip guard (after the all-reduce)
         return loss
 
     def _pack_factors(self, pending):
@@ -285,6 +335,7 @@ class TrainStep(object):
             import torch.distributed as dist
             if self.n_reduce:
                 dist.all_reduce(self.flat.flat[:self.n_reduce], op=dist.ReduceOp.SUM, group=self.group)
+            dist.all_reduce(self.flat.loss_slot, op=dist.ReduceOp.SUM, group=self.group)
             dist.all_gather_into_tensor(self._gathered, self._arena, group=self.group)
             return
         self.flat.allreduce_mean_(self.group, scale_in_optimizer=self.flat_p is not None)
@@ -294,16 +345,38 @@ class TrainStep(object):
             from . import ops
             if self.gather_factors:        # every rank forms the SUM over ranks of the deferred gradients itself
                 ops.wgrad_grouped_table(self._factor_table, self._factor_out_floats)
+            guard = self.loss_limit is not None
             ops.adam_clip_step(self.flat_p, self.flat.flat, self.exp_avg, self.exp_avg_sq, self.step_count, self.max_norm, self.lr,
-                               grad_scale=1.0 / self._world())
+                               grad_scale=1.0 / self._world(), loss=self.flat.loss_slot if guard else None,
+                               loss_scale=1.0 / self._world(), loss_limit=self.loss_limit if guard else float("inf"),
+                               skipped=self.skipped)
         else:
+            # torch optimiser path (CPU tensors / optimizer="torch"): the guard is the reference's host read
+            # (allreduce_mean_ has already turned the slot into the mean over ranks)
+            if self.loss_limit is not None:
+                l = float(self.flat.loss_slot.item())
+                if l != l or l >= self.loss_limit:
+                    self.n_skipped_host = getattr(self, "n_skipped_host", 0) + 1
+                    return
             self.flat.clip_(self.max_norm)
             self.opt.step()
 
-    def step(self, batch, eps=None):
+    def skipped_steps(self):
+        """number of optimiser steps the skip guard suppressed so far (one host read)."""
+        n = getattr(self, "n_skipped_host", 0)
+        if self.skipped is not None:
+            n += int(self.skipped.item())
+        return n
+
+    def step(self, batch, eps=None, train=True):
+        """train=False: the validation branch of the reference loop (scripts/utils.py:159-160) -- forward, loss and
+        backward (the reference calls loss.backward() there too), no gradient exchange and no optimiser step."""
+        if self._world() > 1 and "dp_norms" not in batch and not torch.cuda.is_current_stream_capturing():
+            batch = self.update_dp_norms(dict(batch))
         loss = self.forward_backward(batch, eps)
-        self.exchange_gradients()
-        self.apply_gradients()
+        if train:
+            self.exchange_gradients()
+            self.apply_gradients()
         return loss
 
 
@@ -326,7 +399,41 @@ def to_static_batch(batch, capacities):
         padded[:n] = t
         out[key] = padded
         out[count_key] = torch.tensor([n], dtype=torch.int64)
+        if key != "bond_edge_list":
+            # the two host reads of make_directed (conv.py:12-13), taken here once per batch: the flipped half is only
+            # generated for one-directional lists
+            up = bool((t[:, 0] > t[:, 1]).any()) if n else False
+            down = bool((t[:, 1] > t[:, 0]).any()) if n else False
+            out[key.replace("_list", "_symmetrize")] = not (up and down)
     return out
+
+
+def validate_batch(batch, n_basis=None):
+    """Host-side index validation of a (static) batch -- what the device kernels would flag (ops.check_device_errors)
+    and the reference raises as IndexError: mapping / edge-list ranges, atomic numbers inside the embedding table, and
+    no bead with more atoms than feature channels (cgvae.py:473)."""
+    def _cpu(t):
+        return t.detach().cpu() if torch.is_tensor(t) else torch.as_tensor(t)
+    if "CG_mapping" in batch:
+        mapping = _cpu(batch["CG_mapping"]).long()
+        n_beads = int(batch["CG_nxyz"].shape[0])
+        n_atoms = int(batch["nxyz"].shape[0])
+        if mapping.numel() and (int(mapping.min()) < 0 or int(mapping.max()) >= n_beads):
+            raise IndexError("CG_mapping entry outside [0, %d)" % n_beads)
+        if n_basis is not None and mapping.numel() and int(torch.bincount(mapping, minlength=n_beads).max()) > n_basis:
+            raise IndexError("a bead holds more atoms than feature channels (%d) -- cg_v[mapping, CG2atomChannel], "
+                             "cgvae.py:473" % n_basis)
+        z = _cpu(batch["nxyz"])[:, 0]
+        if z.numel() and (float(z.min()) < 0 or float(z.max()) >= 100):
+            raise IndexError("atomic number outside the embedding table (nn.Embedding(100, F), cgvae.py:273)")
+        for key, count_key, n in (("nbr_list", "nbr_count", n_atoms), ("CG_nbr_list", "CG_nbr_count", n_beads),
+                                  ("bond_edge_list", "bond_count", n_atoms)):
+            if key in batch:
+                t = _cpu(batch[key])
+                if count_key in batch:
+                    t = t[:int(_cpu(batch[count_key]).reshape(-1)[0])]
+                if t.numel() and (int(t.min()) < 0 or int(t.max()) >= n):
+                    raise IndexError("%s entry outside [0, %d)" % (key, n))
 
 
 class GraphedTrainStep(object):
@@ -339,6 +446,8 @@ class GraphedTrainStep(object):
         if not trainer.capturable:
             raise ValueError("TrainStep(capturable=True) required")
         self.trainer = trainer
+        if trainer._world() > 1 and "dp_norms" not in example_batch:
+            example_batch = trainer.update_dp_norms(dict(example_batch))
         # all input tensors live in ONE byte buffer (256-byte aligned slots): a batch packed on the host the same way
         # (``pack``) is loaded with a single copy instead of one launch per key (11 copies, ~10 us of host latency each)
         self.layout, off = [], 0
@@ -384,9 +493,14 @@ class GraphedTrainStep(object):
 
     def pack(self, batch, pin=False, device=None):
         """the batch as one uint8 tensor in the layout of the static input buffer (host-side, once per batch)."""
+        for k, v in batch.items():
+            if k.endswith("_symmetrize") and bool(v) != bool(self.static.get(k, True)):
+                raise ValueError("%s differs from the captured graph (one-directional vs bidirectional edge list)" % k)
         out = torch.zeros(self.packed.numel(), dtype=torch.uint8, pin_memory=pin) if device is None else \
             torch.zeros(self.packed.numel(), dtype=torch.uint8, device=device)
         for k, o, nbytes, dtype, shape in self.layout:
+            if k == "dp_norms" and k not in batch:      # filled on the device by update_dp_norms before every replay
+                continue
             v = batch[k]
             if tuple(v.shape) != shape or v.dtype != dtype:
                 raise ValueError("%s: expected %s %s, got %s %s" % (k, dtype, shape, v.dtype, tuple(v.shape)))
@@ -404,6 +518,8 @@ class GraphedTrainStep(object):
     def step(self, batch):
         """batch: a dict from ``to_static_batch`` (one copy per key) or its ``pack``ed form (one copy)."""
         self.load(batch)
+        if self.opt_graph is not None:
+            self.trainer.update_dp_norms(self.static)          # tiny all-reduce of the (atoms, beads, bonds) counts
         self.graph.replay()
         if self.opt_graph is not None:
             self.trainer.exchange_gradients()
@@ -416,6 +532,55 @@ def sample_ensemble_member(model, cg_xyz, CG_nbr_list, mapping, num_CGs, H_prior
     """scripts/sampling.py:276-279: H = mu + eps*sigma, then the decoder."""
     H = H_prior_mu + eps * H_prior_sigma
     return model.decoder(cg_xyz, CG_nbr_list, H, H, mapping, num_CGs, graphs=graphs)
+
+
+@torch.no_grad()
+def sample_single(model, batch, n_ensemble, eps_members=None, eps_recon=None, reconstruct=True):
+    """``sample_single`` scripts/sampling.py:252-293 without its ASE bookkeeping: the prior once (:268), ``n_ensemble``
+    members ``H = eps*sigma + mu`` -> ``model.decoder`` (:276-279), then one reconstruction forward ``model(batch)`` (:293).
+    The noise is drawn with ``torch.randn_like`` in the reference's call order unless given (``eps_members
+    [n_ensemble, Nc, F]``, ``eps_recon [Nc, F]``).  Returns (members [n_ensemble, N, 3], xyz_recon or None, mu, sigma)."""
+    from .cgvae import BatchGraphs
+    z, cg_z, xyz, cg_xyz, nbr, cg_nbr, mapping, num = model.get_inputs(batch)
+    cg_xyz = cg_xyz.contiguous()
+    graphs = BatchGraphs.for_batch(batch)
+    mu, sigma = model.prior_net(cg_z, cg_xyz, cg_nbr, graphs=graphs)
+    members = []
+    for m in range(int(n_ensemble)):
+        eps = torch.randn_like(sigma) if eps_members is None else eps_members[m]
+        members.append(sample_ensemble_member(model, cg_xyz, cg_nbr, mapping, num, mu, sigma, eps, graphs=graphs))
+    xyz_recon = None
+    if reconstruct:
+        batch2 = dict(batch)
+        batch2["_graphs"] = graphs
+        xyz_recon = model(batch2, eps=eps_recon)[5]
+    return torch.stack(members), xyz_recon, mu, sigma
+
+
+def sample_ensemble_sharded(model, batch, n_ensemble, eps_members, group=None):
+    """Ensemble members sharded over the ranks of a process group (BASELINE config 3: 8 members on 8
+    GPUs): member m runs on rank m % world, the prior is recomputed on every rank (cheaper than a broadcast), and the
+    geometries ``[n_atoms, 3]`` are exchanged with ONE all_gather.  ``eps_members [n_ensemble, Nc, F]`` must be the same on
+    every rank (rank 0's generator, replayed or broadcast by the caller): the result is then identical to
+    ``sample_single`` on one device, member by member.  Returns xyz [n_ensemble, N, 3] on every rank."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return sample_single(model, batch, n_ensemble, eps_members, reconstruct=False)[0]
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    n_ensemble = int(n_ensemble)
+    per = (n_ensemble + world - 1) // world
+    mine = [m for m in range(n_ensemble) if m % world == rank]
+    n_atoms = int(batch["nxyz"].shape[0])
+    local = torch.zeros((per, n_atoms, 3), dtype=torch.float32, device=batch["nxyz"].device)
+    if mine:
+        out = sample_single(model, batch, len(mine), eps_members[mine], reconstruct=False)[0]
+        local[:len(mine)] = out
+    gathered = torch.empty((world, per, n_atoms, 3), dtype=torch.float32, device=local.device)
+    dist.all_gather_into_tensor(gathered, local, group=group)
+    # member m = slot m // world of rank m % world
+    idx_rank = torch.arange(n_ensemble, device=local.device) % world
+    idx_slot = torch.arange(n_ensemble, device=local.device) // world
+    return gathered[idx_rank, idx_slot]
 
 
 class GraphedSampler(object):
@@ -452,7 +617,7 @@ class GraphedSampler(object):
         m = self.model
         z, cg_z, xyz, cg_xyz, nbr, cg_nbr, mapping, num = m.get_inputs(self.static)
         cg_xyz = cg_xyz.contiguous()
-        graphs = BatchGraphs(None, self.static.get("CG_nbr_count"))
+        graphs = BatchGraphs(None, self.static.get("CG_nbr_count"), True, self.static.get("CG_nbr_symmetrize", True))
         mu, sigma = m.prior_net(cg_z, cg_xyz, cg_nbr, graphs=graphs)
         outs = [sample_ensemble_member(m, cg_xyz, cg_nbr, mapping, num, mu, sigma, self.eps[k], graphs=graphs)
                 for k in range(self.n_ensemble)]

@@ -54,6 +54,14 @@ int cgvae_abi_version(void);
 const char* cgvae_last_error(void);
 /* number of kernels launched by this library in the calling process (bench.py `gpu_launches`) */
 unsigned long long cgvae_launch_count(void);
+/* Index validation without host round trips: the kernels SKIP an out-of-range index (no out-of-bounds access) and
+ * OR a bit into the caller-owned device word registered here for `device` (NULL unregisters); the host reads it when
+ * it synchronises anyway and raises what the reference raises (IndexError at cgvae.py:473 / nn.Embedding). */
+enum { CGVAE_ERR_LIFT_RANK_BIT = 1,   /* a bead holds more atoms than channels F (cgvae.py:473) */
+       CGVAE_ERR_EMBED_INDEX_BIT = 2, /* embedding id outside the table (cgvae.py:273,380,591) */
+       CGVAE_ERR_BEAD_INDEX_BIT = 4,  /* CG_mapping entry outside [0, n_beads) */
+       CGVAE_ERR_NODE_INDEX_BIT = 8   /* edge-list entry outside [0, n_nodes) */ };
+int cgvae_set_error_flags(int device, int32_t* flags);
 
 /* ------------------------------------------------------------------ graph builders (integer) */
 
@@ -233,8 +241,9 @@ int cgvae_segment_reduce_fwd(const float* X, const int32_t* rowptr_b, const int3
                              int64_t W, int mean, float* out, cgvae_stream_t stream);
 int cgvae_segment_reduce_bwd(const float* g_out, const int64_t* mapping, const int32_t* rowptr_b, int64_t N,
                              int64_t W, int mean, float* g_X, cgvae_stream_t stream);
-/* Embedding gather (cgvae.py:273,380,591): out[n] = table[idx[n]] ; idx int64. */
-int cgvae_gather_rows(const float* table, const int64_t* idx, int64_t N, int64_t W, float* out,
+/* Embedding gather (cgvae.py:273,380,591): out[n] = table[idx[n]] ; idx int64.  n_rows > 0: ids outside
+ * [0, n_rows) give a NaN row and set CGVAE_ERR_EMBED_INDEX (nn.Embedding raises IndexError). */
+int cgvae_gather_rows(const float* table, const int64_t* idx, int64_t N, int64_t W, int64_t n_rows, float* out,
                       cgvae_stream_t stream);
 
 /* Bead -> atom lifting, CGequiVAE.decoder cgvae.py:466-482 / PCN.decoder cgvae.py:556-576:
@@ -255,10 +264,15 @@ int cgvae_lift_bwd(const float* g_xyz, const int64_t* mapping, const int64_t* ra
  * float holding the number of steps taken so far (incremented by the call: graph-replay safe); norm_out (nullable)
  * receives the unclipped gradient norm.  The gradient buffer itself is left unscaled.  grad_scale: the gradients
  * are taken as grad_scale * g (1/world after a data-parallel all-reduce(sum): saves the separate scaling pass; 1.0f
- * otherwise).  ws: cgvae_adam_ws_bytes(). */
+ * otherwise).  ws: cgvae_adam_ws_bytes().
+ * Skip guard of the reference loop (scripts/utils.py:145-148: `if loss.item() >= gamma*200 or isnan(loss): continue`),
+ * decided on the device: with loss != NULL the step is a no-op (p / m / v / step untouched, skipped[0] += 1 when
+ * skipped != NULL) if loss[0]*loss_scale is NaN or >= loss_limit; a non-finite gradient norm is skipped too (it would
+ * otherwise be written into the moments and parameters).  loss_scale = 1/world when loss[0] is an all-reduced sum. */
 size_t cgvae_adam_ws_bytes(void);
 int cgvae_adam_clip_step(float* p, const float* g, float* m, float* v, int64_t n, float max_norm, float grad_scale,
-                         float lr, float beta1, float beta2, float eps, float* step, float* norm_out, void* ws,
+                         float lr, float beta1, float beta2, float eps, float* step, float* norm_out,
+                         const float* loss, float loss_scale, float loss_limit, float* skipped, void* ws,
                          size_t ws_bytes, cgvae_stream_t stream);
 
 /* layout conversion at the module boundary: reference v[N][F][3] <-> planar v[N][3][F] */

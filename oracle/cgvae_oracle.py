@@ -319,6 +319,38 @@ def cgvae_forward(P, spec, batch, eps=None):
     return mu, sigma, pmu, pstd, xyz, xyz_recon
 
 
+def cgvae_decode(P, spec, cg_xyz, cg_nbr_list, S, mapping):
+    """``CGequiVAE.decoder`` cgvae.py:462-484: decoder stack + lifting."""
+    S2, V = decoder_stack_forward(P, "equivaraintconv", spec, cg_xyz, cg_nbr_list, S)
+    if spec.get("equivariant", True) is False:
+        V = affine(P, "euclidean", S2).reshape(S2.shape[0], S2.shape[1], 3)
+    return lift(V, cg_xyz, mapping, offset=spec.get("offset", True))
+
+
+def sample_ensemble(P, spec, batch, eps_members):
+    """The ensemble loop of ``sample_single`` scripts/sampling.py:265-284: the prior once (:268), then per member
+    ``H = eps*sigma + mu`` (``sample_normal`` :247-250) and ``model.decoder(cg_xyz, CG_nbr_list, H, H, mapping, num_CGs)``
+    (:277-279).  ``eps_members [n_ensemble, Nc, F]`` replaces the ``torch.randn_like`` draws.
+    Returns (prior_mu, prior_sigma, xyz [n_ensemble, N, 3])."""
+    cg_nxyz = batch["CG_nxyz"]
+    cg_z, cg_xyz = cg_nxyz[:, 0], cg_nxyz[:, 1:]
+    mu, sigma = prior_forward(P, "prior_net", spec, cg_z, cg_xyz, batch["CG_nbr_list"])
+    out = []
+    for eps in eps_members:
+        H = eps * sigma + mu
+        out.append(cgvae_decode(P, spec, cg_xyz, batch["CG_nbr_list"], H, batch["CG_mapping"]))
+    return mu, sigma, torch.stack(out)
+
+
+def train_loop_step(loss, gamma, train=True):
+    """The control flow of one iteration of ``loop`` scripts/utils.py:145-160 as data: returns (backward, optimiser_step).
+    ``loss >= gamma*200`` or NaN -> ``continue`` (no backward, no step); validation still runs ``loss.backward()``."""
+    l = float(loss)
+    if l >= gamma * 200.0 or l != l:
+        return False, False
+    return True, bool(train)
+
+
 def pcn_forward(P, spec, batch):
     """``PCN.forward`` cgvae.py:588-594."""
     S = torch.nn.functional.embedding(batch["res"].long(), P["embedding.weight"], padding_idx=0)
@@ -333,7 +365,10 @@ def pcn_forward(P, spec, batch):
 # ----------------------------------------------------------------------------
 
 def kl_divergence(mu1, std1, mu2, std2):
-    """scripts/utils.py:81-86 (the ``/ std2`` -- not ``std2**2`` -- quirk is kept)."""
+    """scripts/utils.py:81-86 (the ``/ std2`` -- not ``std2**2`` -- quirk is kept); ``mu2 is None``: KL against the
+    standard normal (:82-83)."""
+    if mu2 is None:
+        return -0.5 * torch.sum(1 + torch.log(std1.pow(2)) - mu1.pow(2) - std1.pow(2), dim=-1).mean()
     return 0.5 * ((std1.pow(2) / std2.pow(2)).sum(-1) + ((mu1 - mu2).pow(2) / std2).sum(-1)
                   + torch.log(std2.pow(2)).sum(-1) - torch.log(std1.pow(2)).sum(-1)
                   - std1.shape[-1]).mean()

@@ -321,6 +321,92 @@ def graphs(ref_data, ref_cgvae):
     _save("graphs.npz", store)
 
 
+def sampling(ref_cgvae, ref_data):
+    """sampling_small.npz: the ensemble loop of scripts/sampling.py:252-293 (``sample_single``) driven on the REAL reference
+    model.  scripts/sampling.py itself does not import here (ase / mdshare / pyemma are absent), so its three model calls
+    are issued verbatim -- ``model.prior_net`` once (:268), then per member ``sample_normal`` (:247-250: ``eps =
+    torch.randn_like(sigma); z = eps.mul(sigma).add_(mu)``) and ``model.decoder(cg_xyz, CG_nbr_list, H, H, mapping,
+    num_CGs)`` (:277-279), then the reconstruction forward ``model(batch)`` (:293) -- under one fixed torch seed; the noise
+    of every draw is recovered by replaying the generator in the same call order."""
+    from torch import nn
+    gen = torch.Generator().manual_seed(41)
+    F, R, enc, dec = 24, 5, 2, 3
+    atom_cutoff, cg_cutoff = 3.5, 6.0
+    n_ens = 5
+    mapping = torch.tensor([0, 0, 0, 1, 1, 2, 2, 2, 2, 3, 3, 3])
+    store = {}
+    for tag, breaksym in (("sym", True), ("nosym", False)):
+        batch = _molecule_batch(ref_data, gen, 1, 12, mapping, atom_cutoff, cg_cutoff, 1.6)   # batch_size 1 (sampling.py:335)
+        torch.manual_seed(321)
+        dec_net = ref_cgvae.EquivariantPsuedoDecoder(n_atom_basis=F, n_rbf=R, cutoff=atom_cutoff,
+                                                     num_conv=dec, activation="swish", breaksym=breaksym)
+        enc_net = ref_cgvae.EquiEncoder(n_conv=enc, n_atom_basis=F, n_rbf=R, cutoff=cg_cutoff,
+                                        activation="swish", cg_mp=False, dir_mp=False)
+        prior = ref_cgvae.CGprior(n_conv=enc, n_atom_basis=F, n_rbf=R, cutoff=cg_cutoff,
+                                  activation="swish", dir_mp=False)
+        mu_net = nn.Sequential(nn.Linear(F, F), nn.ReLU(), nn.Linear(F, F))
+        sg_net = nn.Sequential(nn.Linear(F, F), nn.ReLU(), nn.Linear(F, F))
+        model = ref_cgvae.CGequiVAE(enc_net, dec_net, mu_net, sg_net, 4, feature_dim=F, prior_net=prior,
+                                    det=False, equivariant=True)
+        for p in model.parameters():         # default-initialised biases are zero: make them matter
+            if p.dim() == 1:
+                p.data.normal_(0, 0.2, generator=gen)
+        torch.manual_seed(2024)
+        z, cg_z, xyz, cg_xyz, nbr_list, CG_nbr_list, mp, num_CGs = model.get_inputs(batch)
+        H_prior_mu, H_prior_sigma = model.prior_net(cg_z, cg_xyz, CG_nbr_list)
+        members = []
+        for _ in range(n_ens):
+            eps = torch.randn_like(H_prior_sigma)                       # sample_normal, sampling.py:247-250
+            H = eps.mul(H_prior_sigma).add_(H_prior_mu)
+            members.append(model.decoder(cg_xyz, CG_nbr_list, H, H, mp, num_CGs).detach())
+        S_mu, S_sigma, pm, ps, xyz_out, xyz_recon = model(batch)        # sampling.py:293
+        # replay the generator: same seed, same shapes, same order
+        torch.manual_seed(2024)
+        eps_members = torch.stack([torch.randn_like(H_prior_sigma) for _ in range(n_ens)])
+        eps_recon = torch.randn_like(S_sigma)
+        _state(tag, model, store)
+        for k, t in batch.items():
+            store["%s/batch/%s" % (tag, k)] = _np(t)
+        for k, t in (("prior_mu", H_prior_mu), ("prior_sigma", H_prior_sigma), ("eps_members", eps_members),
+                     ("members", torch.stack(members)), ("eps_recon", eps_recon), ("xyz_recon", xyz_recon),
+                     ("mu", S_mu), ("sigma", S_sigma)):
+            store["%s/%s" % (tag, k)] = _np(t)
+        store["%s/meta" % tag] = np.array([F, R, enc, dec, atom_cutoff, cg_cutoff, int(breaksym), n_ens])
+    _save("sampling_small.npz", store)
+
+
+def dataset_lists(ref_data):
+    """dataset_lists.npz: CGDataset.generate_neighbor_list (data.py:207-252) of the REAL reference on ragged frames: the
+    radius branch (atom and CG graphs) and the bond-derived CG graph of ``cg_cutoff=None`` (:227-248)."""
+    gen = torch.Generator().manual_seed(63)
+    sizes = [9, 14, 5, 11]
+    props = {"nxyz": [], "CG_nxyz": [], "CG_mapping": [], "num_atoms": [], "num_CGs": [], "bond_edge_list": []}
+    for n in sizes:
+        xyz = torch.randn(n, 3, generator=gen) * 1.7
+        n_cg = max(2, n // 4)
+        mapping = (torch.arange(n) * n_cg) // n
+        cg_xyz = torch.stack([xyz[mapping == b].mean(0) for b in range(n_cg)])
+        props["nxyz"].append(torch.cat([torch.ones(n, 1), xyz], 1))
+        props["CG_nxyz"].append(torch.cat([torch.arange(n_cg).float()[:, None], cg_xyz], 1))
+        props["CG_mapping"].append(mapping)
+        props["num_atoms"].append(torch.tensor(n))
+        props["num_CGs"].append(torch.tensor(n_cg))
+        chain = torch.stack([torch.arange(n - 1), torch.arange(1, n)], 1)
+        extra = torch.stack([torch.arange(n - 3), torch.arange(3, n)], 1)[::2]
+        props["bond_edge_list"].append(torch.cat([chain, extra], 0))
+    store = {"meta/sizes": np.array(sizes), "meta/atom_cutoff": 2.5, "meta/cg_cutoff": 4.0}
+    for i in range(len(sizes)):
+        for k in ("nxyz", "CG_nxyz", "CG_mapping", "num_atoms", "num_CGs", "bond_edge_list"):
+            store["props/%d/%s" % (i, k)] = _np(props[k][i])
+    for tag, cg_cut, und in (("radius", 4.0, True), ("radius_dir", 4.0, False), ("bond", None, True)):
+        ds = ref_data.CGDataset({k: list(v) for k, v in props.items()})
+        ds.generate_neighbor_list(atom_cutoff=2.5, cg_cutoff=cg_cut, device="cpu", undirected=und)
+        for i in range(len(sizes)):
+            store["%s/%d/nbr_list" % (tag, i)] = _np(ds.props["nbr_list"][i])
+            store["%s/%d/CG_nbr_list" % (tag, i)] = _np(ds.props["CG_nbr_list"][i])
+    _save("dataset_lists.npz", store)
+
+
 def main():
     torch.set_num_threads(1)
     ref_modules, ref_conv, ref_cgvae, ref_data = ref_shim.import_reference()
@@ -330,6 +416,8 @@ def main():
     cgvae_small(ref_cgvae, ref_data, fname="cgvae_noneq.npz", cases=(("vae_noneq", True, False),), seed=22)
     pcn_small(ref_cgvae, ref_data)
     graphs(ref_data, ref_cgvae)
+    sampling(ref_cgvae, ref_data)
+    dataset_lists(ref_data)
 
 
 if __name__ == "__main__":

@@ -324,3 +324,36 @@ def blocks_with_activation(dev, act, dtype, tol):
     assert rel_err(dS, odS) < tol and rel_err(dV, odV) < tol
     assert rel_err(s.grad, so.grad) < tol and rel_err(v.grad, vo.grad) < tol
     _check_grads(blk, P, tol, "blk.")
+
+
+def sampling_case(dev, tag, dtype, tol, gold_tol=5e-5, graphed=False):
+    """train.sample_single (and train.GraphedSampler when ``graphed``) against the loop of scripts/sampling.py:265-293
+    run on the REAL reference (tests/golden/sampling_small.npz, fixed noise) and against oracle.sample_ensemble."""
+    from coarsegrainingvae_b200 import train
+    sec = section(load("sampling_small.npz"), tag)
+    F, R, enc, dec, acut, ccut, breaksym, n_ens = [float(x) for x in sec["meta"]]
+    model = build_vae(int(F), int(R), int(enc), int(dec), acut, ccut, bool(breaksym), n_cgs=4)
+    _load_params(model, sec, dtype, dev)
+    batch = {k[len("batch/"):]: v for k, v in sec.items() if k.startswith("batch/")}
+    cpu_batch, dev_batch = _batch_to(batch, dtype, "cpu"), _batch_to(batch, dtype, dev)
+    eps_m, eps_r = sec["eps_members"].to(dtype), sec["eps_recon"].to(dtype)
+    members, xyz_recon, mu, sigma = train.sample_single(model, dev_batch, int(n_ens), eps_m.to(dev), eps_r.to(dev))
+    spec = dict(n_basis=int(F), n_rbf=int(R), enc_nconv=int(enc), dec_nconv=int(dec), atom_cutoff=acut, cg_cutoff=ccut,
+                decoder="pseudo", breaksym=bool(breaksym), activation="swish")
+    with torch.no_grad():
+        P = _oracle_params(model)
+        omu, osig, oxyz = orc.sample_ensemble(P, spec, cpu_batch, eps_m)
+        orecon = orc.cgvae_forward(P, spec, cpu_batch, eps=eps_r)[5]
+    assert rel_err(mu, omu) < tol and rel_err(sigma, osig) < tol
+    assert rel_err(members, oxyz) < tol, rel_err(members, oxyz)
+    assert rel_err(xyz_recon, orecon) < tol
+    # the frozen geometries of the real reference, member by member
+    assert rel_err(members, sec["members"]) < gold_tol and rel_err(xyz_recon, sec["xyz_recon"]) < gold_tol
+    assert rel_err(mu, sec["prior_mu"]) < gold_tol and rel_err(sigma, sec["prior_sigma"]) < gold_tol
+    if graphed:
+        caps = {"nbr_list": batch["nbr_list"].shape[0] + 5, "CG_nbr_list": batch["CG_nbr_list"].shape[0] + 3,
+                "bond_edge_list": batch["bond_edge_list"].shape[0] + 2}
+        static = _batch_to(train.to_static_batch(batch, caps), dtype, dev)
+        sampler = train.GraphedSampler(model, static, int(n_ens))
+        got = sampler.sample(static, eps_m.to(dev))
+        assert rel_err(got, oxyz) < tol and rel_err(got, sec["members"]) < gold_tol

@@ -59,6 +59,70 @@ def test_pcn_model(tag, dtype, tol):
     pc.pcn_model("cpu", tag, dtype, tol)
 
 
+@pytest.mark.parametrize("tag", ["sym", "nosym"])
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-9), (torch.float32, 5e-5)])
+def test_sampling_loop(tag, dtype, tol):
+    """train.sample_single on the emulator vs the real reference's sampling loop (frozen) and the oracle"""
+    pc.sampling_case("cpu", tag, dtype, tol, gold_tol=5e-5 if dtype == torch.float32 else 5e-6)
+
+
+def test_static_batch_keeps_bidirectional_lists_single():
+    """to_static_batch takes make_directed's two host reads (conv.py:12-13): a list that already holds both directions (the
+    bond-derived CG graph of cg_cutoff=None, or dir_mp=True) must not get the flipped half appended in static mode."""
+    from coarsegrainingvae_b200.train import to_static_batch, validate_batch
+    from coarsegrainingvae_b200.cgvae import BatchGraphs
+    one_way = torch.tensor([[0, 1], [0, 2], [1, 2]])
+    both = torch.cat([one_way, one_way.flip(1)])
+    base = {"nbr_list": one_way, "CG_nbr_list": both, "bond_edge_list": one_way}
+    sb = to_static_batch(base, {"nbr_list": 8, "CG_nbr_list": 8, "bond_edge_list": 8})
+    assert sb["nbr_symmetrize"] is True and sb["CG_nbr_symmetrize"] is False
+    g = BatchGraphs.for_batch(sb)
+    atom = g.directed_graph("atom", sb["nbr_list"], 3)
+    cgg = g.directed_graph("cg", sb["CG_nbr_list"], 3)
+    assert int(atom.rowptr[-1]) == 6 and int(cgg.rowptr[-1]) == 6          # 3 undirected edges -> 6 directed, both ways
+    assert torch.equal(cgg.rowptr, atom.rowptr)
+    # dir_mp=True: already_directed wins even for a one-directional list
+    assert int(g.directed_graph("atom", sb["nbr_list"], 3, already_directed=True).rowptr[-1]) == 3
+    full = {"nxyz": torch.tensor([[1., 0, 0, 0], [6., 1, 0, 0], [8., 0, 1, 0]]), "CG_nxyz": torch.zeros(3, 4),
+            "CG_mapping": torch.tensor([0, 0, 1]), **sb}
+    validate_batch(full, n_basis=2)
+    with pytest.raises(IndexError):
+        validate_batch(full, n_basis=1)                 # bead 0 holds 2 atoms > 1 channel (cgvae.py:473)
+    bad = dict(full, CG_mapping=torch.tensor([0, 0, 3]))
+    with pytest.raises(IndexError):
+        validate_batch(bad, n_basis=8)
+    bad = dict(full, nxyz=torch.tensor([[1., 0, 0, 0], [6., 1, 0, 0], [108., 0, 1, 0]]))
+    with pytest.raises(IndexError):
+        validate_batch(bad, n_basis=8)
+
+
+def test_train_step_skip_guard_and_validation_mode_cpu():
+    """TrainStep on the torch-optimiser path (CPU): the reference loop's control flow (scripts/utils.py:145-160) -- no
+    optimiser step for loss >= 200*gamma or NaN, validation mode runs backward without a step."""
+    from coarsegrainingvae_b200.train import TrainStep
+    from oracle import cgvae_oracle as orc
+    z = load("cgvae_small.npz")
+    sec = section(z, "vae_sym")
+    F, R, enc, dec, acut, ccut, breaksym, beta, gamma = [float(x) for x in sec["meta"]]
+    model = pc.build_vae(int(F), int(R), int(enc), int(dec), acut, ccut, bool(breaksym))
+    pc._load_params(model, sec, torch.float32, "cpu")
+    batch = {k[len("batch/"):]: v for k, v in sec.items() if k.startswith("batch/")}
+    eps = sec["eps"]
+    tr = TrainStep(model, beta, gamma, lr=1e-3, optimizer="torch")
+    tr.prepare(batch, eps)
+    before = [p.detach().clone() for p in tr.flat.params]
+    loss = tr.step(batch, eps, train=False)                      # validation: backward, no step
+    assert orc.train_loop_step(loss, gamma, train=False) == (True, False)
+    assert all(torch.equal(a, p) for a, p in zip(before, tr.flat.params)) and float(tr.flat.flat.abs().max()) > 0
+    tr.loss_limit = float(loss) * 0.5                            # pretend the loss is past the guard
+    tr.step(batch, eps)
+    assert all(torch.equal(a, p) for a, p in zip(before, tr.flat.params)) and tr.skipped_steps() == 1
+    tr.loss_limit = gamma * 200.0
+    loss = tr.step(batch, eps)
+    assert orc.train_loop_step(loss, gamma) == (True, True)
+    assert any(not torch.equal(a, p) for a, p in zip(before, tr.flat.params)) and tr.skipped_steps() == 1
+
+
 def test_product_refuses_cpu_tensors(monkeypatch):
     monkeypatch.undo()                                 # drop the emulator: this is the shipped behaviour
     blk = cg.UpdateBlock(feat_dim=8, activation="swish", dropout=0.0)
