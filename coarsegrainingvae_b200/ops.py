@@ -603,9 +603,112 @@ def colsum(X, param=None):
 # message layers
 # --------------------------------------------------------------------------------------------------
 
+class MessageTiles(object):
+    """column tiles of a CSR for the tensor-core message kernels (cgvae_msg_tiles_build): bptr[n_chunks+1] batch offsets,
+    ngroups[n_chunks], rec = batch records (uint8), rc = rows per chunk."""
+
+    def __init__(self, rc, bptr, ngroups, rec, n_batches_cap, n_edges):
+        self.rc, self.bptr, self.ngroups, self.rec = int(rc), bptr, ngroups, rec
+        self.n_batches_cap, self.n_edges = int(n_batches_cap), int(n_edges)
+        self.fill = None              # live edges / columns, measured once in eager mode (one host read)
+
+
+# Tensor-core message path policy.  CGVAE_MSG_TC=0 disables it; =1 forces it wherever it applies (homogeneous graph,
+# R <= 15).  Default "auto": graphs with at least MSG_TC_MIN_EDGES directed edge slots and a mean degree of at least
+# MSG_TC_MIN_DEGREE, and -- measured once per graph SHAPE outside CUDA-graph capture -- a column fill (edges / columns
+# of the tiles) of at least MSG_TC_MIN_FILL: below that the zero columns cost more than the register re-use of the
+# gathered sender rows saves and the SIMT kernel of message.cu (L1 re-use across 4 receivers) is the better path.
+import os as _os
+MSG_TC = _os.environ.get("CGVAE_MSG_TC", "auto")
+MSG_TC_RC = int(_os.environ.get("CGVAE_MSG_TC_RC", "8"))
+MSG_TC_MIN_EDGES = 4096
+MSG_TC_MIN_DEGREE = 12.0
+MSG_TC_MIN_FILL = float(_os.environ.get("CGVAE_MSG_TC_MIN_FILL", "0.35"))
+_TC_DECISIONS = {}
+
+
+def message_tiles(geom, transposed=False, rc=None):
+    """forward (receiver-chunk) or backward (sender-chunk) column tiles of a Geometry, built once and cached on it."""
+    rc = int(rc or MSG_TC_RC)
+    cache = geom.__dict__.setdefault("_tiles", {})
+    key = (rc, bool(transposed))
+    hit = cache.get(key)
+    if hit is not None:
+        return hit
+    lib = _lib.load()
+    g = geom.graph
+    if transposed:
+        rowptr, col, slot_map, n_rows, n_part = g.rowptr_t, g.col_t, g.perm_t, g.n_send, g.n_recv
+    else:
+        rowptr, col, slot_map, n_rows, n_part = g.rowptr, g.col, None, g.n_recv, g.n_send
+    dev = geom.basis.device
+    n_chunks = (n_rows + rc - 1) // rc
+    cap = int(lib.cgvae_msg_tiles_batches_cap(n_rows, n_part, g.n_edges, rc))
+    rec_bytes = int(lib.cgvae_msg_tiles_rec_bytes())
+    nbatch = torch.empty(max(n_chunks, 1), dtype=torch.int32, device=dev)
+    bptr = torch.empty(n_chunks + 1, dtype=torch.int32, device=dev)
+    ngroups = torch.empty(max(n_chunks, 1), dtype=torch.int32, device=dev)
+    rec = torch.empty(cap * rec_bytes, dtype=torch.uint8, device=dev)
+    _lib.check(lib.cgvae_msg_tiles_build(_p(rowptr), _p(col), _p(slot_map), n_rows, n_part, g.n_edges, _p(geom.basis),
+                                         _p(geom.unit), geom.rb, rc, _p(nbatch), _p(bptr), _p(ngroups), _p(rec), cap, _stream()),
+               "msg_tiles_build")
+    tiles = MessageTiles(rc, bptr, ngroups, rec, cap, g.n_edges)
+    cache[key] = tiles
+    return tiles
+
+
+def _tc_applies(geom, n_split):
+    """policy decision (see MSG_TC above); returns the forward tiles or None."""
+    if MSG_TC == "0":
+        return False
+    g = geom.graph
+    if g.n_recv != g.n_send or g.n_recv == 0 or geom.n_rbf > 15 or g.n_recv > 262144:
+        return False
+    if MSG_TC == "1":
+        return True
+    if g.n_edges < MSG_TC_MIN_EDGES or g.n_edges < MSG_TC_MIN_DEGREE * g.n_recv:
+        return False
+    key = (g.n_recv, (g.n_edges // g.n_recv) // 4, MSG_TC_RC)     # per graph shape: nodes, degree bucket
+    hit = _TC_DECISIONS.get(key)
+    if hit is None:
+        if torch.cuda.is_current_stream_capturing():
+            return True                     # no host read inside a capture: the warm-up steps normally decide first
+        tiles = message_tiles(geom, False)
+        if tiles.fill is None:
+            live_edges = int(g.rowptr[-1].item())
+            n_batches = int(tiles.bptr[-1].item())
+            tiles.fill = live_edges / max(1.0, 32.0 * n_batches)
+        hit = tiles.fill >= MSG_TC_MIN_FILL
+        _TC_DECISIONS[key] = hit
+    return hit
+
+
+def message_tc_fwd(n_split, phi, v_send, v_recv, geom, Wf, bf, res_s, res_v, want_q=False):
+    """cgvae_message_tc_fwd: the fused message layer with the filter contraction on the tensor cores."""
+    lib = _lib.load()
+    g = geom.graph
+    F = phi.shape[-1]
+    dev = phi.device
+    rc = MSG_TC_RC if not (n_split == 4 and MSG_TC_RC == 16) else 8
+    tiles = message_tiles(geom, False, rc)
+    out_s = torch.empty((g.n_recv, F), dtype=torch.float32, device=dev)
+    out_v = torch.empty((g.n_recv, 3, F), dtype=torch.float32, device=dev)
+    q = torch.empty((g.n_recv, 3, F), dtype=torch.float32, device=dev) if (want_q and n_split == 4) else None
+    t0 = TIMER.begin("message_fwd") if TIMER is not None else None
+    _lib.check(lib.cgvae_message_tc_fwd(n_split, _p(phi), _p(v_send), _p(v_recv), _p(tiles.bptr), _p(tiles.ngroups), _p(tiles.rec),
+                                        tiles.rc, _p(Wf), _p(bf), g.n_recv, F, geom.n_rbf, _p(res_s), _p(res_v), int(v_send is None),
+                                        _p(out_s), _p(out_v), _p(q), _stream()), "message_tc_fwd")
+    if t0 is not None:
+        TIMER.end("message_fwd", t0, dict(n_split=n_split, E=g.n_edges, n_recv=g.n_recv, n_send=g.n_send, F=F,
+                                          R=geom.n_rbf, v_zero=v_send is None, tc=True))
+    return out_s, out_v, q
+
+
 def message_fwd(n_split, phi, v_send, v_recv, geom, Wf, bf, res_s, res_v, want_q=False):
     """returns (out_s [n_recv,F], out_v [n_recv,3,F], q or None).  v_send None == all-zero vectors."""
     _need_cuda(phi)
+    if _tc_applies(geom, n_split):
+        return message_tc_fwd(n_split, phi, v_send, v_recv, geom, Wf, bf, res_s, res_v, want_q)
     lib = _lib.load()
     g = geom.graph
     F = phi.shape[-1]

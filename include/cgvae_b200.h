@@ -201,6 +201,27 @@ int cgvae_message_bwd(int n_split, const float* phi, const float* v_send, const 
                       float* g_phi, float* g_v_send, float* dWf, float* dbf,
                       void* ws, size_t ws_bytes, cgvae_stream_t stream);
 
+/* ---- the same layers on the 5th-generation tensor cores (csrc/message_tc.cu) ----
+ * Column tiles of a CSR: rows are taken RC (4, 8 or 16) at a time; the columns of a chunk are (sorted union of the partner
+ * nodes of its rows) x (the RC rows), 32 columns per batch record (both tf32 halves of the basis tile in the tensor core's
+ * canonical K-major layout, unit vectors, partner ids; non-edges keep an all-zero basis row).  Built once per graph and
+ * shared by all layers on it: forward tiles from the receiver CSR (rowptr, col, slot_map = NULL), backward tiles from the
+ * sender CSR (rowptr_t, col_t, slot_map = perm_t: CSR slot whose basis / unit row the edge uses).
+ *   nbatch[n_chunks] scratch, bptr[n_chunks+1] batch offsets, ngroups[n_chunks], rec[n_batches_cap * rec_bytes]. */
+int64_t cgvae_msg_tiles_batches_cap(int64_t n_rows, int64_t n_partners, int64_t n_edge_slots, int RC);
+size_t cgvae_msg_tiles_rec_bytes(void);
+int cgvae_msg_tiles_build(const int32_t* rowptr, const int32_t* col, const int32_t* slot_map, int64_t n_rows,
+                          int64_t n_partners, int64_t n_edge_slots, const float* basis, const float* unit, int RB, int RC,
+                          int32_t* nbatch, int32_t* bptr, int32_t* ngroups, void* rec, int64_t n_batches_cap,
+                          cgvae_stream_t stream);
+/* cgvae_message_fwd on forward tiles: the filter rbf @ W_filter (modules.py:192-197) is a 3xTF32 tcgen05.mma per batch
+ * (accumulators in TMEM, channels on the TMEM lanes), the sender rows are gathered once per (chunk, sender) and re-used
+ * from registers for the RC receivers of the chunk.  Same outputs, same arguments as cgvae_message_fwd. */
+int cgvae_message_tc_fwd(int n_split, const float* phi, const float* v_send, const float* v_recv, const int32_t* bptr,
+                         const int32_t* ngroups, const void* rec, int RC, const float* Wf, const float* bf,
+                         int64_t n_recv, int F, int R, const float* res_s, const float* res_v, int v_is_zero,
+                         float* out_s, float* out_v, float* q, cgvae_stream_t stream);
+
 /* EquiMessagePsuedo.forward conv.py:180-242 (9 splits) and its backward.  State (s, sbar, v, vbar)
  * on one node set; residual adds fused (cgvae.py:108-111).  The backward also needs the receiver CSR
  * (receiver-side gradient terms) and writes gw[E][9][F] (per-edge filter gradient, original CSR slot

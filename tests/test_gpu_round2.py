@@ -164,7 +164,8 @@ def test_bead_with_more_atoms_than_channels_raises_like_the_reference():
     torch.manual_seed(1)
     model = build_cgvae(8, 4, 1, 1, cfg["atom_cutoff"], cfg["cg_cutoff"], 3).to(DEV)
     batch = _to(synthetic.cgvae_batch(cfg, 0, _gpu_radius, cg.CG_collate), DEV)
-    out = model(batch)
+    eps = torch.randn(6, 8, device=DEV)
+    out = model(batch, eps=eps)
     assert bool(torch.isfinite(out[5]).all())
     bad = dict(batch)
     bad["CG_mapping"] = batch["CG_mapping"].clone()
@@ -176,7 +177,7 @@ def test_bead_with_more_atoms_than_channels_raises_like_the_reference():
     bad["nxyz"][0, 0] = 250.0                                               # atomic number outside nn.Embedding(100, F)
     with pytest.raises(IndexError):
         model(bad)
-    out2 = model(batch)                                                     # the flag is cleared: good batches still run
+    out2 = model(batch, eps=eps)                                            # the flag is cleared: good batches still run
     assert torch.equal(out2[5], out[5])
 
 
@@ -218,3 +219,162 @@ def test_graphed_step_with_bond_derived_cg_graph_matches_eager():
         assert rel_err(lb, la) < 1e-5, (i, float(la), float(lb))
     gtr.flat.release()
     eager.flat.release()
+
+
+# ------------------------------------------------------------------------------------------ tensor-core message kernels
+
+def _tile_reference(rowptr, col, basis, unit, rc):
+    """numpy restatement of the column-tile layout (cgvae_msg_tiles_build): per chunk of rc rows, the sorted union of the
+    partner nodes; column (g, rr) = edge (row chunk*rc+rr <- partner union[g]); 32 columns per batch."""
+    n_rows = len(rowptr) - 1
+    gb = 32 // rc
+    batches = []          # per batch: (gcol list, dense [32, RB] basis, dense [32, 3] unit)
+    bptr = [0]
+    ngroups = []
+    for c0 in range(0, n_rows, rc):
+        rows = range(c0, min(n_rows, c0 + rc))
+        union = sorted({int(col[e]) for i in rows for e in range(rowptr[i], rowptr[i + 1])})
+        rank = {j: g for g, j in enumerate(union)}
+        nb = (len(union) + gb - 1) // gb
+        local = [([0] * gb, np.zeros((32, basis.shape[1]), np.float32), np.zeros((32, 3), np.float32)) for _ in range(nb)]
+        for g, j in enumerate(union):
+            local[g // gb][0][g % gb] = j
+        for i in rows:
+            for e in range(rowptr[i], rowptr[i + 1]):
+                g = rank[int(col[e])]
+                c = (g % gb) * rc + (i - c0)
+                local[g // gb][1][c] = basis[e]
+                local[g // gb][2][c] = unit[e, :3]
+        batches += local
+        bptr.append(bptr[-1] + nb)
+        ngroups.append(len(union))
+    return bptr, ngroups, batches
+
+
+@pytest.mark.parametrize("rc", [4, 8, 16])
+def test_message_tiles_layout_exact(rc):
+    """the column tiles the tensor-core kernels consume: partner ids, batch offsets and group counts bit-exact, tf32 hi + lo
+    == the fp32 basis to 2^-21, zero rows for non-edges, unit vectors exact -- forward (receiver chunks) and backward
+    (sender chunks through perm_t) tiles of a ragged, non-symmetric graph."""
+    n, R, cutoff = 70, 10, 6.0
+    g = torch.Generator().manual_seed(5 + rc)
+    xyz = torch.rand(n, 3, generator=g) * 6.0
+    pairs = torch.randint(0, n, (900, 2), generator=g)
+    pairs = pairs[pairs[:, 0] != pairs[:, 1]]
+    pairs = torch.unique(pairs, dim=0)
+    pairs = pairs[torch.randperm(pairs.shape[0], generator=g)]             # arbitrary edge-list order
+    pairs = pairs[(pairs[:, 0] < 50) | (pairs[:, 0] > 58)]                   # a run of receivers without edges
+    graph = ops.build_graph(pairs.to(DEV), n)
+    geom = ops.edge_geometry(graph, xyz.to(DEV), xyz.to(DEV), R, cutoff)
+    basis, unit = geom.basis.cpu().numpy(), geom.unit.cpu().numpy()
+    for transposed in (False, True):
+        tiles = ops.message_tiles(geom, transposed, rc)
+        if transposed:
+            rowptr, col = graph.rowptr_t.cpu().numpy(), graph.col_t.cpu().numpy()
+            perm = graph.perm_t.cpu().numpy()
+            b_src, u_src = basis[perm], unit[perm]
+        else:
+            rowptr, col, b_src, u_src = graph.rowptr.cpu().numpy(), graph.col.cpu().numpy(), basis, unit
+        bptr, ngroups, batches = _tile_reference(rowptr, col, b_src, u_src, rc)
+        assert tiles.bptr.cpu().tolist() == bptr and tiles.ngroups.cpu().tolist() == ngroups
+        rec = tiles.rec.cpu().numpy().reshape(-1, 4608)
+        gb = 32 // rc
+        for b, (gcol, bb, uu) in enumerate(batches):
+            r = rec[b]
+            hi = r[0:2048].view(np.float32).reshape(4, 4, 8, 4)      # [row group][k chunk][row in group][k in chunk]
+            lo = r[2048:4096].view(np.float32).reshape(4, 4, 8, 4)
+            hi = hi.transpose(0, 2, 1, 3).reshape(32, 16)
+            lo = lo.transpose(0, 2, 1, 3).reshape(32, 16)
+            want = np.zeros((32, 16), np.float32)
+            want[:, :bb.shape[1]] = bb
+            assert np.all((hi.view(np.uint32) & 0x1FFF) == 0) and np.all((lo.view(np.uint32) & 0x1FFF) == 0)   # tf32 values
+            assert np.abs((hi.astype(np.float64) + lo) - want).max() <= 2.0 ** -21 * max(1e-30, np.abs(want).max())
+            assert np.all(hi[np.all(want == 0, axis=1)] == 0)
+            un = r[4096:4096 + 384].view(np.float32).reshape(3, 32).T
+            assert np.array_equal(un, uu)
+            got_gcol = r[4480:4480 + 4 * gb].view(np.int32).tolist()
+            assert got_gcol == gcol, (b, got_gcol, gcol)
+
+
+def _tc_vs_simt_case(n_split, rc, n, F, R, cutoff, seed, v_zero=False, residual=True, sym=True):
+    g = torch.Generator().manual_seed(seed)
+    xyz = synthetic.lattice_points(n, 2.2, np.random.default_rng(seed), rotate=False)
+    half = ops.radius_graph(torch.as_tensor(xyz, device=DEV), cutoff, True)
+    pairs = torch.cat([half, half.flip(1)], 0) if sym else half
+    graph = ops.build_graph(pairs, n)
+    x = torch.as_tensor(xyz, device=DEV)
+    geom = ops.edge_geometry(graph, x, x, R, cutoff)
+    phi = torch.randn(n, n_split, F, generator=g).to(DEV)
+    v = None if v_zero else torch.randn(n, 3, F, generator=g).to(DEV)
+    Wf = (torch.randn(n_split * F, R, generator=g) * 0.5).to(DEV)
+    bf = (torch.randn(n_split * F, generator=g) * 0.5).to(DEV)
+    res_s = torch.randn(n, F, generator=g).to(DEV) if residual else None
+    res_v = torch.randn(n, 3, F, generator=g).to(DEV) if residual else None
+    old_tc, old_rc = ops.MSG_TC, ops.MSG_TC_RC
+    try:
+        ops.MSG_TC = "0"
+        want = ops.message_fwd(n_split, phi, v, v if n_split == 4 else None, geom, Wf, bf, res_s, res_v, want_q=n_split == 4)
+        ops.MSG_TC, ops.MSG_TC_RC = "1", rc
+        got = ops.message_fwd(n_split, phi, v, v if n_split == 4 else None, geom, Wf, bf, res_s, res_v, want_q=n_split == 4)
+        again = ops.message_fwd(n_split, phi, v, v if n_split == 4 else None, geom, Wf, bf, res_s, res_v, want_q=n_split == 4)
+    finally:
+        ops.MSG_TC, ops.MSG_TC_RC = old_tc, old_rc
+    # float64 ground truth of the layer from the SAME per-edge records (basis, unit): conv.py:505-563 / 358-402
+    col = graph.col.long()
+    recv = torch.repeat_interleave(torch.arange(n, device=DEV), (graph.rowptr[1:] - graph.rowptr[:-1]).long())
+    E = int(graph.rowptr[-1])
+    col, recv = col[:E], recv[:E]
+    B = geom.basis[:E].double()
+    Wfull = torch.zeros(n_split * F, geom.rb, dtype=torch.float64, device=DEV)
+    Wfull[:, :R] = Wf.double()
+    Wfull[:, R] = bf.double()
+    w = (B @ Wfull.t()).view(E, n_split, F)
+    m = phi.double()[col] * w
+    u = geom.unit[:E, :3].double()
+    ds = torch.zeros(n, F, dtype=torch.float64, device=DEV).index_add_(0, recv, m[:, 1])
+    dv_e = m[:, 2, None, :] * u[:, :, None]
+    if v is not None:
+        dv_e = dv_e + m[:, 0, None, :] * v.double()[col]
+        if n_split == 4:
+            dv_e = dv_e + m[:, 3, None, :] * torch.linalg.cross(v.double()[recv], v.double()[col], dim=1)
+    dv = torch.zeros(n, 3, F, dtype=torch.float64, device=DEV).index_add_(0, recv, dv_e)
+    if residual:
+        ds, dv = ds + res_s.double(), dv + res_v.double()
+    for a, b, name in ((got[0], ds, "s"), (got[1], dv, "v")):
+        assert rel_err(a, b) < TOL, (name, rel_err(a, b))
+    assert rel_err(got[0], want[0]) < TOL and rel_err(got[1], want[1]) < TOL
+    if n_split == 4 and v is not None:
+        assert rel_err(got[2], want[2]) < TOL
+    assert all(torch.equal(a, b) for a, b in zip(got[:2], again[:2]))       # deterministic
+    return E
+
+
+@pytest.mark.parametrize("n_split,rc,n,F,R,cutoff", [
+    (3, 8, 350, 600, 10, 12.0),      # chignolin-like density, F not a multiple of 128
+    (3, 4, 300, 128, 8, 5.0),
+    (3, 16, 200, 64, 8, 7.0),        # F < 128: partial channel slice
+    (4, 8, 250, 512, 8, 7.0),        # cross block at the PCN width
+    (4, 4, 97, 96, 4, 4.0),          # node count not a multiple of the chunk
+])
+def test_message_tc_forward_matches_simt_and_float64(n_split, rc, n, F, R, cutoff):
+    """cgvae_message_tc_fwd (filter on tcgen05, column tiles) == cgvae_message_fwd (fp32 SIMT) == float64 ground truth within
+    1e-5 scale-relative, bitwise repeatable."""
+    E = _tc_vs_simt_case(n_split, rc, n, F, R, cutoff, seed=3 + n_split + rc)
+    assert E > 0
+
+
+def test_message_tc_forward_first_layer_and_delta_modes():
+    _tc_vs_simt_case(3, 8, 180, 192, 10, 9.0, seed=11, v_zero=True, residual=True)
+    _tc_vs_simt_case(4, 8, 180, 192, 8, 9.0, seed=12, v_zero=True, residual=False)
+    _tc_vs_simt_case(3, 8, 180, 192, 8, 9.0, seed=13, v_zero=False, residual=False, sym=False)   # one-directional list
+
+
+@pytest.mark.parametrize("tag,cls", [("k3", "EquiMessageBlock"), ("k4", "EquiMessageCross")])
+def test_message_block_api_on_tensor_cores(tag, cls):
+    """the frozen reference block outputs / gradients (tests/golden/blocks_small.npz) with the tensor-core path forced"""
+    old = ops.MSG_TC
+    try:
+        ops.MSG_TC = "1"
+        pc.message_block_api(DEV, tag, cls, torch.float32, TOL)
+    finally:
+        ops.MSG_TC = old
