@@ -102,6 +102,19 @@ __device__ __forceinline__ void bar_wait(uint64_t* bar, uint32_t parity) {
   }
   asm volatile("trap;");
 }
+// one elected lane of a converged warp: bulk copies issued under a divergent `if (tid == 0)` are each wrapped by ptxas in an
+// ELECT / R2UR / BRA.U.ANY serialisation loop (~200 cycles per copy, measured for tcgen05.mma with tools/tc_latency.cu)
+__device__ __forceinline__ bool elect_lane() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 // 1-D bulk copy global -> shared (UBLKCP): 16-byte aligned addresses, size a multiple of 16
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sm_u32(dst)),
@@ -143,7 +156,7 @@ __global__ void __launch_bounds__(MR > 16 ? 256 : 512) gemm_nt_stream_kernel(
   for (int idx = tid; idx < (MR - M) * (K / 4); idx += blockDim.x)
     reinterpret_cast<float4*>(Xs + (size_t)M * K)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();
-  if (tid == 0) {
+  if (warp == 0 && elect_lane()) {
     const uint32_t row_bytes = (uint32_t)K * 4u;
     bar_expect_tx(bar, (uint32_t)(M + rows) * row_bytes);
     if (ldw == K) {
@@ -244,6 +257,9 @@ __global__ void __launch_bounds__(NW * 32) gemm_nn_stream_kernel(
   if (tid == 0) {
     for (int b = 0; b < nbox; ++b) bar_init(bars + b, 1);
     bar_fence_init();
+  }
+  __syncwarp();
+  if (warp == 0 && elect_lane()) {
     // rows beyond K (and columns beyond N) are zero-filled by the TMA unit; the byte count is that of the full box
     for (int b = 0; b < nbox; ++b) {
       if (b * box_rows < cnt) {

@@ -74,6 +74,18 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate)
       : "memory");
 }
+// one elected lane of a converged warp (see csrc/tc_common.cuh::elect_one)
+__device__ __forceinline__ bool elect_one_lane() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -247,30 +259,36 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) gemm_tc_kernel(const float* __
       __syncwarp();
       if (lane == 0) mbar_arrive(&full_bar[s]);
     }
-  } else if (lane == 0) {
-    // ---------------- MMA issuer: one thread drives the tensor core ----------------
+  } else {
+    // ---------------- MMA issuer: the whole warp stays in the loop, ONE ELECTED lane drives the tensor core ----------------
+    // (issued under a divergent `if (lane == 0)` every tcgen05.mma is wrapped by ptxas in an ELECT / R2UR / BRA.U.ANY
+    // serialisation loop: ~205 cycles per instruction whatever its shape, measured with tools/tc_latency.cu; under
+    // elect.sync in warp-uniform control flow a 128x64x8 tf32 MMA issues every ~85 cycles)
     for (int kt = 0; kt < num_kt; ++kt) {
       const int s = kt % STAGES;
       const uint32_t round = (uint32_t)(kt / STAGES);
       mbar_wait(&full_bar[s], round & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t a_hi = smem_u32(smem + (uint32_t)s * STAGE_BYTES), a_lo = a_hi + A_TILE_BYTES;
-      const uint32_t b_hi = a_hi + 2 * A_TILE_BYTES, b_lo = b_hi + B_TILE_BYTES;
-      constexpr uint32_t idesc = IDESC_BASE;                 // both smem tiles are K-major (the producers transpose)
-      // one MMA consumes K = 8: two 16-byte chunks of a K-major tile
-      constexpr uint32_t a_step = 2 * LBO, a_lbo = LBO, a_sbo = SBO;
-      constexpr uint32_t b_step = 2 * LBO, b_lbo = LBO, b_sbo = SBO;
+      if (elect_one_lane()) {
+        const uint32_t a_hi = smem_u32(smem + (uint32_t)s * STAGE_BYTES), a_lo = a_hi + A_TILE_BYTES;
+        const uint32_t b_hi = a_hi + 2 * A_TILE_BYTES, b_lo = b_hi + B_TILE_BYTES;
+        constexpr uint32_t idesc = IDESC_BASE;                 // both smem tiles are K-major (the producers transpose)
+        // one MMA consumes K = 8: two 16-byte chunks of a K-major tile
+        constexpr uint32_t a_step = 2 * LBO, a_lbo = LBO, a_sbo = SBO;
+        constexpr uint32_t b_step = 2 * LBO, b_lbo = LBO, b_sbo = SBO;
 #pragma unroll
-      for (int ks = 0; ks < BK / 8; ++ks) {
-        const uint32_t ao = (uint32_t)ks * a_step, bo = (uint32_t)ks * b_step;
-        const uint32_t acc = (kt > 0 || ks > 0) ? 1u : 0u;
-        umma_tf32(tmem_base, make_desc(a_lo + ao, a_lbo, a_sbo), make_desc(b_hi + bo, b_lbo, b_sbo), acc, idesc);   // small terms first
-        umma_tf32(tmem_base, make_desc(a_hi + ao, a_lbo, a_sbo), make_desc(b_lo + bo, b_lbo, b_sbo), 1u, idesc);
-        umma_tf32(tmem_base, make_desc(a_hi + ao, a_lbo, a_sbo), make_desc(b_hi + bo, b_lbo, b_sbo), 1u, idesc);
+        for (int ks = 0; ks < BK / 8; ++ks) {
+          const uint32_t ao = (uint32_t)ks * a_step, bo = (uint32_t)ks * b_step;
+          const uint32_t acc = (kt > 0 || ks > 0) ? 1u : 0u;
+          umma_tf32(tmem_base, make_desc(a_lo + ao, a_lbo, a_sbo), make_desc(b_hi + bo, b_lbo, b_sbo), acc, idesc);   // small terms first
+          umma_tf32(tmem_base, make_desc(a_hi + ao, a_lbo, a_sbo), make_desc(b_lo + bo, b_lbo, b_sbo), 1u, idesc);
+          umma_tf32(tmem_base, make_desc(a_hi + ao, a_lbo, a_sbo), make_desc(b_hi + bo, b_lbo, b_sbo), 1u, idesc);
+        }
+        umma_commit(&empty_bar[s]);          // smem slot reusable once these MMAs have read it
+        if (kt == num_kt - 1) umma_commit(acc_bar);   // accumulator complete
       }
-      umma_commit(&empty_bar[s]);          // smem slot reusable once these MMAs have read it
+      __syncwarp();
     }
-    umma_commit(acc_bar);                  // accumulator complete
   }
 
   if (warp < NUM_PRODUCER_WARPS) {

@@ -41,10 +41,6 @@ constexpr int REC_BLO = 2048;          // [32 x 16] tf32 lo
 constexpr int REC_UNIT = 4096;         // unit vectors, component-major: ux[32] uy[32] uz[32]
 constexpr int REC_GCOL = 4480;         // partner (sender) index of each group of the batch: NB / RC <= 8 ints
 constexpr int REC_BYTES = 4608;        // 36 x 128
-constexpr int NSTAGE = 4;
-constexpr int NTHREADS = 192;
-constexpr int A_TILE_BYTES = 128 * KT * 4;       // 8 KB per (split, half)
-constexpr int TMEM_COLS = 256;
 
 // ------------------------------------------------------------------------------------------------------------------
 // tile builder (integer work, exact, deterministic)
@@ -173,262 +169,372 @@ __global__ void __launch_bounds__(kTileThreads) tile_fill_kernel(const int32_t* 
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// shared pieces of the forward / backward kernels
+// forward
 // ------------------------------------------------------------------------------------------------------------------
-struct Smem {
-  char* a_tiles;        // [KS][hi | lo][8 KB]
-  char* stages;         // [NSTAGE][REC_BYTES]
-  uint64_t* stage_full;
-  uint64_t* stage_empty;
-  uint64_t* tmem_full;
-  uint64_t* tmem_empty;
-  uint32_t* tmem_ptr;
+// One persistent CTA per SM.  Work items = (128-channel slice, receiver chunk), slice-major; CTA b owns the contiguous
+// item range [b * n_items / G, (b + 1) * n_items / G).  Warps: 4 lane quarters x NSUB consumer warps (thread = channel,
+// the NSUB warps of a quarter take the groups of a batch round-robin and merge their partial receiver sums through shared
+// memory in a fixed order), + 1 bulk-copy producer warp, + 1 MMA / TMEM-allocator warp.
+// TMEM (512 columns): filter operand A = Wf' of the slice, both tf32 halves [KS][2][16 columns] (written by the channel
+// threads with tcgen05.st: the MMA reads it from TMEM, so the only shared-memory operand traffic is the 1 KB basis tile per
+// MMA -- with A in shared memory every N = 32 MMA re-read 4 KB of it and the kernel was shared-memory bound);
+// accumulators D[buf][k][32 columns], double buffered.
+constexpr int NSTAGE = 8;
+constexpr int TMEM_COLS = 512;
+
+template <int KS>
+struct Cols {
+  static constexpr uint32_t A = 0;                       // [KS][hi | lo][KT]
+  static constexpr uint32_t D = KS * 2 * KT;             // [2][KS][NB]
+  static_assert(D + 2 * KS * NB <= TMEM_COLS, "TMEM budget");
 };
 
-template <int KS>
-__device__ __forceinline__ Smem carve(char* smem) {
-  Smem s;
-  s.a_tiles = smem;
-  s.stages = smem + KS * 2 * A_TILE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s.stages + NSTAGE * REC_BYTES);
-  s.stage_full = bars;
-  s.stage_empty = bars + NSTAGE;
-  s.tmem_full = bars + 2 * NSTAGE;
-  s.tmem_empty = bars + 2 * NSTAGE + 2;
-  s.tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 4);
-  return s;
-}
-template <int KS>
-constexpr size_t smem_bytes() { return (size_t)KS * 2 * A_TILE_BYTES + NSTAGE * REC_BYTES + (2 * NSTAGE + 4) * 8 + 64; }
+struct Ring {
+  char* stages;
+  uint64_t* stage_full;   // [NSTAGE]  bulk copy landed
+  uint64_t* stage_empty;  // [NSTAGE]  every consumer warp is done with the record
+  uint64_t* d_full;       // [2]       filter MMAs of the batch complete
+  uint64_t* d_empty;      // [2]       every consumer warp has read its columns of the buffer
+  uint64_t* a_full;       // filter operand of the current slice staged in TMEM
+  uint32_t* tmem_ptr;
+  float* xchg;            // [NSUB - 1][n_acc][128] partial sums of the sub-warps
+};
 
-// Wf'[k][f0 + row][0..15] = [Wf[(k*F + f)*R + r] (r < R) | bf[k*F + f] | 0 ...], both tf32 halves, canonical K-major tiles
+template <int NSUB, int NACC>
+__device__ __forceinline__ Ring carve(char* smem) {
+  Ring r;
+  r.stages = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NSTAGE * REC_BYTES);
+  r.stage_full = bars;
+  r.stage_empty = bars + NSTAGE;
+  r.d_full = bars + 2 * NSTAGE;
+  r.d_empty = bars + 2 * NSTAGE + 2;
+  r.a_full = bars + 2 * NSTAGE + 4;
+  r.tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 5);
+  r.xchg = reinterpret_cast<float*>(bars + 2 * NSTAGE + 6);
+  return r;
+}
+template <int NSUB, int NACC>
+constexpr size_t fwd_smem_bytes() {
+  return (size_t)NSTAGE * REC_BYTES + (2 * NSTAGE + 6) * 8 + sizeof(float) * (size_t)(NSUB - 1) * NACC * 128 + 64;
+}
+
+// filter MMAs of one batch: D_k = A_k[tmem] * B^T[smem] for every split, 3xTF32 (small terms first), K = 16 in two steps
 template <int KS>
-__device__ __forceinline__ void stage_filter_tiles(char* a_tiles, const float* __restrict__ Wf, const float* __restrict__ bf, int F,
-                                                   int R, int f0) {
-  for (int idx = threadIdx.x; idx < KS * 128 * (KT / 4); idx += NTHREADS) {
-    const int c4 = idx & 3, row = (idx >> 2) & 127, k = idx >> 9;
-    const int ch = f0 + row;
-    float x[4];
+__device__ __forceinline__ void issue_filter_mmas(const char* stage, uint32_t tmem_base, uint32_t d_col) {
+  constexpr uint32_t idesc = idesc_tf32(128, NB);
+  const uint32_t b_hi = smem_u32(stage + REC_BHI), b_lo = b_hi + (REC_BLO - REC_BHI);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int r = 4 * c4 + j;
+  for (int k = 0; k < KS; ++k) {
+    const uint32_t a_hi = tmem_base + Cols<KS>::A + (uint32_t)(k * 2 * KT), a_lo = a_hi + KT;
+    const uint32_t d = tmem_base + d_col + (uint32_t)(k * NB);
+#pragma unroll
+    for (int ks = 0; ks < KT / 8; ++ks) {
+      const uint32_t ao = (uint32_t)ks * 8, bo = (uint32_t)ks * 2 * kLBO;
+      umma_tf32_ts(d, a_lo + ao, make_desc(b_hi + bo, kLBO, TILE_SBO), ks > 0 ? 1u : 0u, idesc);
+      umma_tf32_ts(d, a_hi + ao, make_desc(b_lo + bo, kLBO, TILE_SBO), 1u, idesc);
+      umma_tf32_ts(d, a_hi + ao, make_desc(b_hi + bo, kLBO, TILE_SBO), 1u, idesc);
+    }
+  }
+}
+
+// the thread that owns channel f0 + row writes its rows of Wf'_k = [Wf[(k*F + f)*R + r] (r < R) | bf[k*F + f] | 0 ...] into
+// the TMEM operand region, both tf32 halves
+template <int KS>
+__device__ __forceinline__ void stage_filter_tmem(uint32_t t_lane, const float* __restrict__ Wf, const float* __restrict__ bf, int F,
+                                                  int R, int ch) {
+#pragma unroll
+  for (int k = 0; k < KS; ++k) {
+    uint32_t hi[KT], lo[KT];
+#pragma unroll
+    for (int r = 0; r < KT; ++r) {
       float val = 0.f;
       if (ch < F) {
         if (r < R) val = __ldg(Wf + ((int64_t)k * F + ch) * R + r);
         else if (r == R) val = __ldg(bf + (int64_t)k * F + ch);
       }
-      x[j] = val;
+      float h, l;
+      split_tf32(val, h, l);
+      hi[r] = __float_as_uint(h);
+      lo[r] = __float_as_uint(l);
     }
-    float4 h, l;
-    split_tf32(x[0], h.x, l.x);
-    split_tf32(x[1], h.y, l.y);
-    split_tf32(x[2], h.z, l.z);
-    split_tf32(x[3], h.w, l.w);
-    const uint32_t off = tile_off(row, 4 * c4, TILE_SBO);
-    *reinterpret_cast<float4*>(a_tiles + (2 * k) * A_TILE_BYTES + off) = h;
-    *reinterpret_cast<float4*>(a_tiles + (2 * k + 1) * A_TILE_BYTES + off) = l;
+    tmem_st16(t_lane + Cols<KS>::A + (uint32_t)(k * 2 * KT), hi);
+    tmem_st16(t_lane + Cols<KS>::A + (uint32_t)(k * 2 * KT + KT), lo);
   }
+  tmem_wait_st();
 }
 
-// bulk-copy producer: one thread, NSTAGE-deep ring of batch records
-__device__ __forceinline__ void producer_loop(const Smem& sm, const char* __restrict__ rec, int64_t b0, int nb) {
-  const char* src = rec + b0 * REC_BYTES;
-  for (int b = 0; b < nb; ++b) {
-    const int s = b % NSTAGE;
-    mbar_wait(&sm.stage_empty[s], (((uint32_t)(b / NSTAGE)) & 1u) ^ 1u);
-    mbar_expect_tx(&sm.stage_full[s], REC_BYTES);
-    bulk_g2s(sm.stages + s * REC_BYTES, src + (int64_t)b * REC_BYTES, REC_BYTES, &sm.stage_full[s]);
-  }
-}
-
-// filter MMAs of one batch: D_k = A_k * B^T for every split, 3xTF32 (small terms first), K = 16 in two steps
-template <int KS>
-__device__ __forceinline__ void issue_filter_mmas(const Smem& sm, int s, uint32_t tmem_d) {
-  constexpr uint32_t idesc = idesc_tf32(128, NB);
-  const uint32_t b_hi = smem_u32(sm.stages + s * REC_BYTES + REC_BHI), b_lo = b_hi + (REC_BLO - REC_BHI);
-#pragma unroll
-  for (int k = 0; k < KS; ++k) {
-    const uint32_t a_hi = smem_u32(sm.a_tiles + (2 * k) * A_TILE_BYTES), a_lo = a_hi + A_TILE_BYTES;
-    const uint32_t d = tmem_d + (uint32_t)(k * NB);
-#pragma unroll
-    for (int ks = 0; ks < KT / 8; ++ks) {
-      const uint32_t o = (uint32_t)ks * 2 * kLBO;
-      umma_tf32_ss(d, make_desc(a_lo + o, kLBO, TILE_SBO), make_desc(b_hi + o, kLBO, TILE_SBO), ks > 0 ? 1u : 0u, idesc);
-      umma_tf32_ss(d, make_desc(a_hi + o, kLBO, TILE_SBO), make_desc(b_lo + o, kLBO, TILE_SBO), 1u, idesc);
-      umma_tf32_ss(d, make_desc(a_hi + o, kLBO, TILE_SBO), make_desc(b_hi + o, kLBO, TILE_SBO), 1u, idesc);
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// forward
-// ------------------------------------------------------------------------------------------------------------------
-template <int KS, int RC>
-__global__ void __launch_bounds__(NTHREADS, 2) message_tc_fwd_kernel(
+template <int KS, int RC, int NSUB>
+__global__ void __launch_bounds__((4 * NSUB + 2) * 32, 1) message_tc_fwd_kernel(
     const float* __restrict__ phi, const float* __restrict__ v_send, const float* __restrict__ v_recv,
     const int32_t* __restrict__ bptr, const int32_t* __restrict__ ngroups, const char* __restrict__ rec,
     const float* __restrict__ Wf, const float* __restrict__ bf, int64_t n_recv, int F, int R,
     const float* __restrict__ res_s, const float* __restrict__ res_v, int v_is_zero, float* __restrict__ out_s,
-    float* __restrict__ out_v, float* __restrict__ q_out) {
+    float* __restrict__ out_v, float* __restrict__ q_out, int n_chunks, int n_items) {
   CGVAE_KERNEL_PROLOGUE();
-  constexpr int GB = NB / RC;
+  constexpr int GB = NB / RC;                  // groups per batch
+  constexpr int GPW = GB / NSUB;               // groups per consumer warp and batch
+  static_assert(GB % NSUB == 0 && GPW >= 1, "groups of a batch must divide over the sub-warps");
+  constexpr int NQ = (KS == 4) ? 3 : 0;
+  constexpr int NACC = RC * (4 + NQ);          // per-thread accumulators: s, v[3] (, q[3]) per receiver of the chunk
+  constexpr int NCONS = 4 * NSUB;              // consumer warps
   extern __shared__ __align__(1024) char smem_raw[];
-  const Smem sm = carve<KS>(smem_raw);
+  const Ring sm = carve<NSUB, NACC>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int chunk = blockIdx.x, f0 = blockIdx.y * 128;
-  const int64_t b0 = bptr[chunk];
-  const int nb = bptr[chunk + 1] - bptr[chunk];
-  const int ng = ngroups[chunk];
+  const int item0 = (int)(((int64_t)blockIdx.x * n_items) / gridDim.x);
+  const int item1 = (int)(((int64_t)(blockIdx.x + 1) * n_items) / gridDim.x);
 
-  if (nb > 0) {
-    if (tid == 0) {
-      for (int s = 0; s < NSTAGE; ++s) {
-        mbar_init(&sm.stage_full[s], 1);
-        mbar_init(&sm.stage_empty[s], 4);
-      }
-      for (int b = 0; b < 2; ++b) {
-        mbar_init(&sm.tmem_full[b], 1);
-        mbar_init(&sm.tmem_empty[b], 4);
-      }
-      mbar_fence_init();
+  if (tid == 0) {
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(&sm.stage_full[s], 1);
+      mbar_init(&sm.stage_empty[s], NCONS);
     }
-    if (warp == 5) tmem_alloc<TMEM_COLS>(sm.tmem_ptr);
-    stage_filter_tiles<KS>(sm.a_tiles, Wf, bf, F, R, f0);
-    fence_async_smem();                      // generic-proxy tile writes -> visible to the tensor core
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&sm.d_full[b], 1);
+      mbar_init(&sm.d_empty[b], NCONS);
+    }
+    mbar_init(sm.a_full, 4);
+    mbar_fence_init();
   }
-  const uint32_t tmem_base = nb > 0 ? *sm.tmem_ptr : 0u;
+  if (warp == NCONS + 1) tmem_alloc<TMEM_COLS>(sm.tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *sm.tmem_ptr;
 
-  if (warp == 4) {
-    if (lane == 0 && nb > 0) producer_loop(sm, rec, b0, nb);
-  } else if (warp == 5) {
-    if (lane == 0) {
-      for (int b = 0; b < nb; ++b) {
-        const int s = b % NSTAGE, buf = b & 1;
-        mbar_wait(&sm.stage_full[s], ((uint32_t)(b / NSTAGE)) & 1u);
-        mbar_wait(&sm.tmem_empty[buf], (((uint32_t)(b >> 1)) & 1u) ^ 1u);
+  if (warp == NCONS) {
+    // ---------------- bulk-copy producer (whole warp in the loop, one elected lane issues: see elect_one) ----------------
+    uint32_t bc = 0;
+    for (int item = item0; item < item1; ++item) {
+      const int chunk = item % n_chunks;
+      const int64_t b0 = bptr[chunk];
+      const int nb = bptr[chunk + 1] - bptr[chunk];
+      const char* src = rec + b0 * REC_BYTES;
+      for (int b = 0; b < nb; ++b, ++bc) {
+        const uint32_t s = bc % NSTAGE;
+        mbar_wait(&sm.stage_empty[s], ((bc / NSTAGE) & 1u) ^ 1u);
+        if (elect_one()) {
+          mbar_expect_tx(&sm.stage_full[s], REC_BYTES);
+          bulk_g2s(sm.stages + s * REC_BYTES, src + (int64_t)b * REC_BYTES, REC_BYTES, &sm.stage_full[s]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == NCONS + 1) {
+    // ---------------- MMA issuer (whole warp in the loop, one elected lane issues) ----------------
+    uint32_t bc = 0, ac = 0;
+    int staged_slice = -1;
+    for (int item = item0; item < item1; ++item) {
+      const int chunk = item % n_chunks, slice = item / n_chunks;
+      const int nb = bptr[chunk + 1] - bptr[chunk];
+      if (nb > 0 && slice != staged_slice) {
+        mbar_wait(sm.a_full, ac & 1u);          // the channel threads have re-staged Wf' of the new slice
+        ++ac;
+        staged_slice = slice;
+      }
+      for (int b = 0; b < nb; ++b, ++bc) {
+        const uint32_t s = bc % NSTAGE, buf = bc & 1u;
+        mbar_wait(&sm.stage_full[s], (bc / NSTAGE) & 1u);
+        mbar_wait(&sm.d_empty[buf], ((bc >> 1) & 1u) ^ 1u);
         tc_fence_after();
-        issue_filter_mmas<KS>(sm, s, tmem_base + (uint32_t)(buf * KS * NB));
-        umma_commit(&sm.tmem_full[buf]);
+        if (elect_one()) {
+          issue_filter_mmas<KS>(sm.stages + s * REC_BYTES, tmem_base, Cols<KS>::D + buf * (KS * NB));
+          umma_commit(&sm.d_full[buf]);
+        }
+        __syncwarp();
       }
     }
   } else {
     // ---------------- channel threads ----------------
-    const int f = f0 + tid;
-    const bool active = f < F;
-    const int fc = active ? f : F - 1;       // inactive lanes compute on a valid channel, never store
-    float acc_s[RC], acc_v[3][RC], acc_q[KS == 4 ? 3 : 1][RC];
-#pragma unroll
-    for (int rr = 0; rr < RC; ++rr) {
-      acc_s[rr] = 0.f;
-      acc_v[0][rr] = acc_v[1][rr] = acc_v[2][rr] = 0.f;
-#pragma unroll
-      for (int c = 0; c < (KS == 4 ? 3 : 1); ++c) acc_q[c][rr] = 0.f;
-    }
-    const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
-    for (int b = 0; b < nb; ++b) {
-      const int s = b % NSTAGE, buf = b & 1;
-      mbar_wait(&sm.stage_full[s], ((uint32_t)(b / NSTAGE)) & 1u);
-      const char* st = sm.stages + s * REC_BYTES;
-      const int32_t* gcol = reinterpret_cast<const int32_t*>(st + REC_GCOL);
-      const float* un = reinterpret_cast<const float*>(st + REC_UNIT);
-      const int n_live = min(GB, ng - b * GB);
-      // gathers of every live group of the batch: in flight while the tensor core finishes the batch
-      float ph[GB][KS], vv[GB][3];
-#pragma unroll
-      for (int g = 0; g < GB; ++g) {
-        const int j = (g < n_live) ? gcol[g] : 0;
-        const float* pj = phi + (int64_t)j * KS * F + fc;
-#pragma unroll
-        for (int k = 0; k < KS; ++k) ph[g][k] = (g < n_live) ? __ldg(pj + (int64_t)k * F) : 0.f;
-        if (!v_is_zero && g < n_live) {
-          const float* vj = v_send + (int64_t)j * 3 * F + fc;
-          vv[g][0] = __ldg(vj); vv[g][1] = __ldg(vj + F); vv[g][2] = __ldg(vj + 2 * (int64_t)F);
-        } else {
-          vv[g][0] = vv[g][1] = vv[g][2] = 0.f;
+    const int quarter = warp & 3, sub = warp >> 2;
+    const int row = quarter * 32 + lane;                     // TMEM lane = channel inside the slice
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    uint32_t bc = 0;
+    int staged_slice = -1;
+    for (int item = item0; item < item1; ++item) {
+      const int chunk = item % n_chunks, slice = item / n_chunks;
+      const int nb = bptr[chunk + 1] - bptr[chunk];
+      const int ng = ngroups[chunk];
+      const int f = slice * 128 + row;
+      const bool active = f < F;
+      const int fc = active ? f : F - 1;           // inactive lanes compute on a valid channel, never store
+      if (nb > 0 && slice != staged_slice) {
+        // all MMAs that read the previous operand are complete: this thread has consumed every batch of the last item
+        if (sub == 0) {
+          stage_filter_tmem<KS>(t_lane, Wf, bf, F, R, f);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(sm.a_full);
         }
+        staged_slice = slice;
       }
-      mbar_wait(&sm.tmem_full[buf], ((uint32_t)(b >> 1)) & 1u);
-      tc_fence_after();
-      const uint32_t t_buf = t_lane + (uint32_t)(buf * KS * NB);
-#pragma unroll
-      for (int g = 0; g < GB; ++g) {
-        if (g < n_live) {
-          uint32_t w[KS][RC];
-#pragma unroll
-          for (int k = 0; k < KS; ++k) tmem_ld<RC>(t_buf + (uint32_t)(k * NB + g * RC), w[k]);
-          tmem_wait_ld();
-          const float p0 = ph[g][0] * vv[g][0], p1 = ph[g][0] * vv[g][1], p2 = ph[g][0] * vv[g][2];
-          float x0 = 0.f, x1 = 0.f, x2 = 0.f;
-          if constexpr (KS == 4) {
-            x0 = ph[g][3] * vv[g][0]; x1 = ph[g][3] * vv[g][1]; x2 = ph[g][3] * vv[g][2];
-          }
-#pragma unroll
-          for (int rr = 0; rr < RC; ++rr) {
-            const int c = g * RC + rr;
-            const float w0 = __uint_as_float(w[0][rr]), w1 = __uint_as_float(w[1][rr]), w2 = __uint_as_float(w[2][rr]);
-            acc_s[rr] = fmaf(ph[g][1], w1, acc_s[rr]);                     // dS_i += m1            (conv.py:526,558)
-            const float t = ph[g][2] * w2;                                  // m2
-            acc_v[0][rr] = fmaf(t, un[c], acc_v[0][rr]);                    // dV_i += m2 * u_ij     (conv.py:524)
-            acc_v[1][rr] = fmaf(t, un[NB + c], acc_v[1][rr]);
-            acc_v[2][rr] = fmaf(t, un[2 * NB + c], acc_v[2][rr]);
-            acc_v[0][rr] = fmaf(w0, p0, acc_v[0][rr]);                      //        + m0 * v_j     (conv.py:525)
-            acc_v[1][rr] = fmaf(w0, p1, acc_v[1][rr]);
-            acc_v[2][rr] = fmaf(w0, p2, acc_v[2][rr]);
-            if constexpr (KS == 4) {
-              const float w3 = __uint_as_float(w[3][rr]);                   // q_i = sum m3 * v_j    (conv.py:379)
-              acc_q[0][rr] = fmaf(w3, x0, acc_q[0][rr]);
-              acc_q[1][rr] = fmaf(w3, x1, acc_q[1][rr]);
-              acc_q[2][rr] = fmaf(w3, x2, acc_q[2][rr]);
-            }
-          }
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&sm.tmem_empty[buf]);
-        mbar_arrive(&sm.stage_empty[s]);
-      }
-    }
-    // ---------------- receiver epilogue: single store per output element, residual fused ----------------
-    if (active) {
+      float acc_s[RC], acc_v[3][RC], acc_q[KS == 4 ? 3 : 1][RC];
 #pragma unroll
       for (int rr = 0; rr < RC; ++rr) {
-        const int64_t i = (int64_t)chunk * RC + rr;
-        if (i < n_recv) {
-          const int64_t so = i * F + f, vo = i * 3 * F + f;
-          float a0 = acc_v[0][rr], a1 = acc_v[1][rr], a2 = acc_v[2][rr];
+        acc_s[rr] = 0.f;
+        acc_v[0][rr] = acc_v[1][rr] = acc_v[2][rr] = 0.f;
+#pragma unroll
+        for (int c = 0; c < (KS == 4 ? 3 : 1); ++c) acc_q[c][rr] = 0.f;
+      }
+      // gathers of this warp's groups of a batch: issued one batch ahead of their use
+      float ph[GPW][KS], vv[GPW][3];
+      auto gather = [&](uint32_t bcx, int b) {
+        const uint32_t s = bcx % NSTAGE;
+        mbar_wait(&sm.stage_full[s], (bcx / NSTAGE) & 1u);
+        const int32_t* gcol = reinterpret_cast<const int32_t*>(sm.stages + s * REC_BYTES + REC_GCOL);
+#pragma unroll
+        for (int t = 0; t < GPW; ++t) {
+          const int g = sub + t * NSUB;
+          const bool live = b * GB + g < ng;
+          const int j = live ? gcol[g] : 0;
+          const float* pj = phi + (int64_t)j * KS * F + fc;
+#pragma unroll
+          for (int k = 0; k < KS; ++k) ph[t][k] = live ? __ldg(pj + (int64_t)k * F) : 0.f;
+          if (!v_is_zero && live) {
+            const float* vj = v_send + (int64_t)j * 3 * F + fc;
+            vv[t][0] = __ldg(vj); vv[t][1] = __ldg(vj + F); vv[t][2] = __ldg(vj + 2 * (int64_t)F);
+          } else {
+            vv[t][0] = vv[t][1] = vv[t][2] = 0.f;
+          }
+        }
+      };
+      if (nb > 0) gather(bc, 0);
+      for (int b = 0; b < nb; ++b, ++bc) {
+        const uint32_t s = bc % NSTAGE, buf = bc & 1u;
+        float cph[GPW][KS], cvv[GPW][3];
+#pragma unroll
+        for (int t = 0; t < GPW; ++t) {
+#pragma unroll
+          for (int k = 0; k < KS; ++k) cph[t][k] = ph[t][k];
+          cvv[t][0] = vv[t][0]; cvv[t][1] = vv[t][1]; cvv[t][2] = vv[t][2];
+        }
+        if (b + 1 < nb) gather(bc + 1, b + 1);       // next batch's sender rows: in flight during this batch's math
+        const float* un = reinterpret_cast<const float*>(sm.stages + s * REC_BYTES + REC_UNIT);
+        mbar_wait(&sm.d_full[buf], (bc >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t t_buf = t_lane + Cols<KS>::D + buf * (KS * NB);
+        // four columns (= four receivers of the chunk) at a time: filter values from TMEM, unit vectors from the record
+#pragma unroll
+        for (int t = 0; t < GPW; ++t) {
+          const int g = sub + t * NSUB;
+          const bool live = b * GB + g < ng;
+          const float p0 = cph[t][0] * cvv[t][0], p1 = cph[t][0] * cvv[t][1], p2 = cph[t][0] * cvv[t][2];
+          float x0 = 0.f, x1 = 0.f, x2 = 0.f;
           if constexpr (KS == 4) {
-            // sum_e m3 (v_i x v_j) = v_i x q_i
-            float vi0 = 0.f, vi1 = 0.f, vi2 = 0.f;
-            if (!v_is_zero) {
-              vi0 = v_recv[vo]; vi1 = v_recv[vo + F]; vi2 = v_recv[vo + 2 * (int64_t)F];
+            x0 = cph[t][3] * cvv[t][0]; x1 = cph[t][3] * cvv[t][1]; x2 = cph[t][3] * cvv[t][2];
+          }
+#pragma unroll
+          for (int q4 = 0; q4 < RC / 4; ++q4) {
+            const int c0 = g * RC + 4 * q4;
+            uint32_t w[KS][4];
+#pragma unroll
+            for (int k = 0; k < KS; ++k) tmem_ld4(t_buf + (uint32_t)(k * NB + c0), w[k]);
+            const float4 ux = *reinterpret_cast<const float4*>(un + c0);
+            const float4 uy = *reinterpret_cast<const float4*>(un + NB + c0);
+            const float4 uz = *reinterpret_cast<const float4*>(un + 2 * NB + c0);
+            tmem_wait_ld();
+            if (t == GPW - 1 && q4 == RC / 4 - 1) {
+              // this warp's columns of the accumulator buffer and its part of the record are in registers: release both
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) {
+                mbar_arrive(&sm.d_empty[buf]);
+                mbar_arrive(&sm.stage_empty[s]);
+              }
             }
-            a0 += vi1 * acc_q[2][rr] - vi2 * acc_q[1][rr];
-            a1 += vi2 * acc_q[0][rr] - vi0 * acc_q[2][rr];
-            a2 += vi0 * acc_q[1][rr] - vi1 * acc_q[0][rr];
-            if (q_out) {
-              q_out[vo] = acc_q[0][rr]; q_out[vo + F] = acc_q[1][rr]; q_out[vo + 2 * (int64_t)F] = acc_q[2][rr];
+            if (live) {
+              const float uxa[4] = {ux.x, ux.y, ux.z, ux.w}, uya[4] = {uy.x, uy.y, uy.z, uy.w}, uza[4] = {uz.x, uz.y, uz.z, uz.w};
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const int rr = 4 * q4 + c;
+                const float w0 = __uint_as_float(w[0][c]), w1 = __uint_as_float(w[1][c]), w2 = __uint_as_float(w[2][c]);
+                acc_s[rr] = fmaf(cph[t][1], w1, acc_s[rr]);                    // dS_i += m1            (conv.py:526,558)
+                const float m2 = cph[t][2] * w2;
+                acc_v[0][rr] = fmaf(m2, uxa[c], acc_v[0][rr]);                 // dV_i += m2 * u_ij     (conv.py:524)
+                acc_v[1][rr] = fmaf(m2, uya[c], acc_v[1][rr]);
+                acc_v[2][rr] = fmaf(m2, uza[c], acc_v[2][rr]);
+                acc_v[0][rr] = fmaf(w0, p0, acc_v[0][rr]);                     //        + m0 * v_j     (conv.py:525)
+                acc_v[1][rr] = fmaf(w0, p1, acc_v[1][rr]);
+                acc_v[2][rr] = fmaf(w0, p2, acc_v[2][rr]);
+                if constexpr (KS == 4) {
+                  const float w3 = __uint_as_float(w[3][c]);                   // q_i = sum m3 * v_j    (conv.py:379)
+                  acc_q[0][rr] = fmaf(w3, x0, acc_q[0][rr]);
+                  acc_q[1][rr] = fmaf(w3, x1, acc_q[1][rr]);
+                  acc_q[2][rr] = fmaf(w3, x2, acc_q[2][rr]);
+                }
+              }
             }
           }
-          out_s[so] = (res_s ? res_s[so] : 0.f) + acc_s[rr];
-          out_v[vo] = (res_v ? res_v[vo] : 0.f) + a0;
-          out_v[vo + F] = (res_v ? res_v[vo + F] : 0.f) + a1;
-          out_v[vo + 2 * (int64_t)F] = (res_v ? res_v[vo + 2 * (int64_t)F] : 0.f) + a2;
         }
       }
+      // ---------------- merge the sub-warps (fixed order) and store: single store per output element ----------------
+      if constexpr (NSUB > 1) {
+        if (sub > 0) {
+          float* dst = sm.xchg + (size_t)(sub - 1) * NACC * 128 + row;
+#pragma unroll
+          for (int rr = 0; rr < RC; ++rr) {
+            dst[(rr * (4 + NQ) + 0) * 128] = acc_s[rr];
+            dst[(rr * (4 + NQ) + 1) * 128] = acc_v[0][rr];
+            dst[(rr * (4 + NQ) + 2) * 128] = acc_v[1][rr];
+            dst[(rr * (4 + NQ) + 3) * 128] = acc_v[2][rr];
+            if constexpr (KS == 4) {
+              dst[(rr * 7 + 4) * 128] = acc_q[0][rr];
+              dst[(rr * 7 + 5) * 128] = acc_q[1][rr];
+              dst[(rr * 7 + 6) * 128] = acc_q[2][rr];
+            }
+          }
+        }
+        named_bar_sync(1, NCONS * 32);
+      }
+      if (sub == 0) {
+#pragma unroll
+        for (int rr = 0; rr < RC; ++rr) {
+          float a_s = acc_s[rr], a0 = acc_v[0][rr], a1 = acc_v[1][rr], a2 = acc_v[2][rr];
+          float q0 = (KS == 4) ? acc_q[0][rr] : 0.f, q1 = (KS == 4) ? acc_q[1][rr] : 0.f, q2 = (KS == 4) ? acc_q[2][rr] : 0.f;
+#pragma unroll
+          for (int o = 0; o < NSUB - 1; ++o) {
+            const float* src = sm.xchg + (size_t)o * NACC * 128 + row;
+            a_s += src[(rr * (4 + NQ) + 0) * 128];
+            a0 += src[(rr * (4 + NQ) + 1) * 128];
+            a1 += src[(rr * (4 + NQ) + 2) * 128];
+            a2 += src[(rr * (4 + NQ) + 3) * 128];
+            if constexpr (KS == 4) {
+              q0 += src[(rr * 7 + 4) * 128];
+              q1 += src[(rr * 7 + 5) * 128];
+              q2 += src[(rr * 7 + 6) * 128];
+            }
+          }
+          const int64_t i = (int64_t)chunk * RC + rr;
+          if (active && i < n_recv) {
+            const int64_t so = i * F + f, vo = i * 3 * F + f;
+            if constexpr (KS == 4) {
+              // sum_e m3 (v_i x v_j) = v_i x q_i
+              float vi0 = 0.f, vi1 = 0.f, vi2 = 0.f;
+              if (!v_is_zero) {
+                vi0 = v_recv[vo]; vi1 = v_recv[vo + F]; vi2 = v_recv[vo + 2 * (int64_t)F];
+              }
+              a0 += vi1 * q2 - vi2 * q1;
+              a1 += vi2 * q0 - vi0 * q2;
+              a2 += vi0 * q1 - vi1 * q0;
+              if (q_out) {
+                q_out[vo] = q0; q_out[vo + F] = q1; q_out[vo + 2 * (int64_t)F] = q2;
+              }
+            }
+            out_s[so] = (res_s ? res_s[so] : 0.f) + a_s;
+            out_v[vo] = (res_v ? res_v[vo] : 0.f) + a0;
+            out_v[vo + F] = (res_v ? res_v[vo + F] : 0.f) + a1;
+            out_v[vo + 2 * (int64_t)F] = (res_v ? res_v[vo + 2 * (int64_t)F] : 0.f) + a2;
+          }
+        }
+      }
+      if constexpr (NSUB > 1) named_bar_sync(1, NCONS * 32);      // the exchange buffer is free again
     }
   }
-  if (nb > 0) {
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 5) {
-      tc_fence_after();
-      tmem_dealloc<TMEM_COLS>(tmem_base);
-    }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == NCONS + 1) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
   }
 }
 
@@ -484,6 +590,7 @@ int cgvae_message_tc_fwd(int n_split, const float* phi, const float* v_send, con
                          cgvae_stream_t stream) {
   CGVAE_REQUIRE(n_split == 3 || n_split == 4, "message_tc_fwd: n_split must be 3 or 4 (got %d)", n_split);
   CGVAE_REQUIRE(RC == 4 || RC == 8 || RC == 16, "message_tc_fwd: RC must be 4, 8 or 16 (got %d)", RC);
+  CGVAE_REQUIRE(n_split == 3 || RC == 4, "message_tc_fwd: the cross block runs with RC = 4 (register budget)");
   CGVAE_REQUIRE(R >= 1 && R + 1 <= mtc::KT && F >= 1, "message_tc_fwd: need 1 <= R <= 15");
   if (n_recv == 0) return 0;
   CGVAE_REQUIRE(phi && bptr && ngroups && rec && Wf && bf && out_s && out_v, "message_tc_fwd: null pointer");
@@ -491,23 +598,25 @@ int cgvae_message_tc_fwd(int n_split, const float* phi, const float* v_send, con
   CGVAE_REQUIRE(n_split != 4 || v_is_zero || v_recv, "message_tc_fwd: v_recv missing for the cross block");
   CGVAE_REQUIRE(aligned16(rec), "message_tc_fwd: records must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
-  dim3 grid((unsigned)ceil_div(n_recv, RC), (unsigned)ceil_div(F, 128));
+  const int64_t n_chunks = ceil_div(n_recv, RC), n_items = n_chunks * ceil_div(F, 128);
+  CGVAE_REQUIRE(n_items < INT_MAX, "message_tc_fwd: too many work items");
+  dim3 grid((unsigned)std::min<int64_t>(n_items, kNumSM));
   const char* recp = reinterpret_cast<const char*>(rec);
-#define LAUNCH_TC_FWD(KS, RCV)                                                                                                   \
+#define LAUNCH_TC_FWD(KS, RCV, NSUB)                                                                                             \
   do {                                                                                                                           \
     static bool attr_done = false;                                                                                               \
-    constexpr size_t smb = mtc::smem_bytes<KS>();                                                                                \
+    constexpr size_t smb = mtc::fwd_smem_bytes<NSUB, RCV*(KS == 4 ? 7 : 4)>();                                                   \
     if (!attr_done) {                                                                                                            \
-      CGVAE_CUDA(cudaFuncSetAttribute(mtc::message_tc_fwd_kernel<KS, RCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb)); \
+      CGVAE_CUDA(cudaFuncSetAttribute(mtc::message_tc_fwd_kernel<KS, RCV, NSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb)); \
       attr_done = true;                                                                                                          \
     }                                                                                                                            \
-    launch_kernel(mtc::message_tc_fwd_kernel<KS, RCV>, grid, dim3(mtc::NTHREADS), smb, st, phi, v_send, v_recv, bptr, ngroups, recp, Wf, \
-                  bf, n_recv, F, R, res_s, res_v, v_is_zero, out_s, out_v, q);                                                   \
+    launch_kernel(mtc::message_tc_fwd_kernel<KS, RCV, NSUB>, grid, dim3((4 * NSUB + 2) * 32), smb, st, phi, v_send, v_recv, bptr, ngroups, \
+                  recp, Wf, bf, n_recv, F, R, res_s, res_v, v_is_zero, out_s, out_v, q, (int)n_chunks, (int)n_items);            \
   } while (0)
   if (n_split == 3) {
-    if (RC == 4) LAUNCH_TC_FWD(3, 4); else if (RC == 8) LAUNCH_TC_FWD(3, 8); else LAUNCH_TC_FWD(3, 16);
+    if (RC == 4) LAUNCH_TC_FWD(3, 4, 4); else if (RC == 8) LAUNCH_TC_FWD(3, 8, 4); else LAUNCH_TC_FWD(3, 16, 2);
   } else {
-    if (RC == 4) LAUNCH_TC_FWD(4, 4); else if (RC == 8) LAUNCH_TC_FWD(4, 8); else LAUNCH_TC_FWD(4, 16);
+    LAUNCH_TC_FWD(4, 4, 4);
   }
 #undef LAUNCH_TC_FWD
   return launched("message_tc_fwd");

@@ -689,7 +689,7 @@ def message_tc_fwd(n_split, phi, v_send, v_recv, geom, Wf, bf, res_s, res_v, wan
     g = geom.graph
     F = phi.shape[-1]
     dev = phi.device
-    rc = MSG_TC_RC if not (n_split == 4 and MSG_TC_RC == 16) else 8
+    rc = MSG_TC_RC if n_split == 3 else 4       # the cross block's extra accumulators only fit the register budget at RC = 4
     tiles = message_tiles(geom, False, rc)
     out_s = torch.empty((g.n_recv, F), dtype=torch.float32, device=dev)
     out_v = torch.empty((g.n_recv, 3, F), dtype=torch.float32, device=dev)
