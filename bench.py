@@ -173,13 +173,85 @@ def _oracle_step_fn(cfg, pool_size, threads):
     return step
 
 
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+
+
+def _reference_step_fn(cfg, pool_size, threads):
+    """The UNMODIFIED reference (pip-installed into the git-ignored baseline/_ref by tools/install_reference.sh; it travels
+    to the GPU box with the snapshot) driven through its own public API on the host CPU: model construction as in
+    scripts/run_ala.py:184-209, batches from the reference's get_neighbor_list (data.py:65-82) + CG_collate (data.py:255-289),
+    and one iteration of the training loop of scripts/utils.py:112-157 per step (scripts/ itself needs ase / mdtraj, which
+    are absent, so the dozen lines of that loop are restated here around the reference's model call).  Returns None when
+    baseline/_ref is missing (then the oracle port is timed and reported as kind "port")."""
+    if not os.path.isdir(os.path.join(REF_DIR, "CoarseGrainingVAE")):
+        return None
+    os.environ["CGVAE_REFERENCE_ROOT"] = REF_DIR
+    import torch
+    from torch import nn
+    from coarsegrainingvae_b200 import synthetic
+    from oracle import ref_shim
+    ref_shim.REFERENCE_ROOT = REF_DIR
+    try:
+        _, _, ref_cgvae, ref_data = ref_shim.import_reference()
+    except Exception:
+        return None
+    torch.set_num_threads(threads)
+    torch.manual_seed(123)
+    F, R, act = cfg["n_basis"], cfg["n_rbf"], "swish"
+    decoder = ref_cgvae.EquivariantPsuedoDecoder(n_atom_basis=F, n_rbf=R, cutoff=cfg["atom_cutoff"], num_conv=cfg["dec_nconv"],
+                                                 activation=act, breaksym=cfg["n_cgs"] == 3)
+    encoder = ref_cgvae.EquiEncoder(n_conv=cfg["enc_nconv"], n_atom_basis=F, n_rbf=R, cutoff=cfg["cg_cutoff"], activation=act,
+                                    cg_mp=False, dir_mp=False)
+    prior = ref_cgvae.CGprior(n_conv=cfg["enc_nconv"], n_atom_basis=F, n_rbf=R, cutoff=cfg["cg_cutoff"], activation=act, dir_mp=False)
+    atom_mu = nn.Sequential(nn.Linear(F, F), nn.ReLU(), nn.Linear(F, F))
+    atom_sigma = nn.Sequential(nn.Linear(F, F), nn.ReLU(), nn.Linear(F, F))
+    model = ref_cgvae.CGequiVAE(encoder, decoder, atom_mu, atom_sigma, cfg["n_cgs"], feature_dim=F, prior_net=prior, det=False,
+                                equivariant=True)
+    model.train()
+    optimizer = torch.optim.Adam(model.parameters(), lr=1e-4)            # scripts/run_ala.py:211
+
+    def ref_radius(xyz, cutoff):
+        return ref_data.get_neighbor_list(torch.as_tensor(xyz), "cpu", cutoff, True).numpy()
+
+    batches = [synthetic.cgvae_batch(cfg, i, ref_radius, ref_data.CG_collate) for i in range(pool_size)]
+    beta, gamma, EPS = cfg["beta"], cfg["gamma"], 1e-6
+
+    def step(i):
+        batch = batches[i % pool_size]
+        S_mu, S_sigma, H_prior_mu, H_prior_sigma, xyz, xyz_recon = model(batch)                     # utils.py:114
+        loss_kl = 0.5 * ((S_sigma.pow(2) / H_prior_sigma.pow(2)).sum(-1) + ((S_mu - H_prior_mu).pow(2) / H_prior_sigma).sum(-1)
+                         + torch.log(H_prior_sigma.pow(2)).sum(-1) - torch.log(S_sigma.pow(2)).sum(-1) - S_sigma.shape[-1]).mean()
+        loss_recon = (xyz_recon - xyz).pow(2).mean()                                                # utils.py:124
+        edge_list = batch["bond_edge_list"]
+        gen = ((xyz_recon[edge_list[:, 0]] - xyz_recon[edge_list[:, 1]]).pow(2).sum(-1) + EPS).sqrt()
+        dat = ((xyz[edge_list[:, 0]] - xyz[edge_list[:, 1]]).pow(2).sum(-1) + EPS).sqrt()
+        loss = loss_recon + loss_kl * beta + (gen - dat).pow(2).mean() * gamma                       # utils.py:141
+        if loss.item() >= gamma * 200.0 or torch.isnan(loss):                                       # utils.py:145-148
+            return float(loss)
+        optimizer.zero_grad()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 0.01)
+        optimizer.step()
+        return float(loss)
+
+    return step
+
+
+def _cpu_step_fn(cfg, pool_size, threads):
+    """(step, kind): the unmodified reference when baseline/_ref is present, else the oracle port."""
+    step = _reference_step_fn(cfg, pool_size, threads)
+    if step is not None:
+        return step, "reference"
+    return _oracle_step_fn(cfg, pool_size, threads), "port"
+
+
 def run_reference(args, cfg):
     import torch
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    step = _oracle_step_fn(cfg, args.pool, threads)
+    step, kind = _cpu_step_fn(cfg, args.pool, threads)
     for i in range(args.warmup):
         step(i)
     t0 = time.perf_counter()
@@ -193,9 +265,11 @@ def run_reference(args, cfg):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": _config_json(args.workload, cfg, 1, {"note": "reference algorithm on host CPU cores (oracle port; the "
-                                                           "reference is pure PyTorch), torch %s" % torch.__version__}),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "config": _config_json(args.workload, cfg, args.gpus),
+            "reference_impl": ("unmodified wwang2/CoarseGrainingVAE from baseline/_ref on the host CPU cores, torch %s"
+                               if kind == "reference" else "oracle port of the reference (baseline/_ref missing), torch %s")
+                              % torch.__version__,
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -430,10 +504,11 @@ def run_cuda(args, cfg):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": _config_json(args.workload, cfg, n_gpus, {
+            "config": _config_json(args.workload, cfg, n_gpus),
+            "workload_details": {
                 "directed_atom_edges_per_batch": edges, "used_gradient_floats": n_used, "used_parameters": len(used),
                 "launch_mode": ("one CUDA graph per step over static-capacity input buffers (edge counts read on the device)"
-                                if use_graph else "eager launches")}),
+                                if use_graph else "eager launches")},
             "clocks": clock_info,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": 4, "last_loss": last},
@@ -443,7 +518,7 @@ def run_cuda(args, cfg):
 
     if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        step = _oracle_step_fn(cfg, 2, threads)
+        step, kind = _cpu_step_fn(cfg, 2, threads)
         step(0)
         t0 = time.perf_counter()
         n = 0
@@ -451,9 +526,10 @@ def run_cuda(args, cfg):
             step(n + 1)
             n += 1
         dt = (time.perf_counter() - t0) / n
-        line["cpu_baseline"] = {"value": cfg["batch"] / dt, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": "%d full train steps of the same %s batch on the host CPU (oracle port of the "
-                                          "reference, torch %s), after 1 warm-up" % (n, args.workload, torch.__version__)}
+        line["cpu_baseline"] = {"value": cfg["batch"] / dt, "unit": UNIT, "cores": threads, "kind": kind,
+                                "sample": "%d full train steps of the same %s batch on the host CPU (%s, torch %s), after 1 "
+                                          "warm-up" % (n, args.workload, "the unmodified reference from baseline/_ref"
+                                                       if kind == "reference" else "oracle port of the reference", torch.__version__)}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

@@ -49,7 +49,9 @@ SIGNATURES = {
     "cgvae_msg_tiles_batches_cap": (_I64, [_I64, _I64, _I64, _INT]),
     "cgvae_msg_tiles_rec_bytes": (_SZ, []),
     "cgvae_msg_tiles_build": (_INT, [_P, _P, _P, _I64, _I64, _I64, _P, _P, _INT, _INT, _P, _P, _P, _P, _I64, _P]),
-    "cgvae_message_tc_fwd": (_INT, [_INT, _P, _P, _P, _P, _P, _P, _INT, _P, _P, _I64, _INT, _INT, _P, _P, _INT, _P, _P, _P, _P]),
+    "cgvae_message_tc_ws_bytes": (_SZ, [_INT, _INT, _I64, _INT]),
+    "cgvae_message_tc_fwd": (_INT, [_INT, _P, _P, _P, _P, _P, _P, _I64, _INT, _P, _P, _I64, _INT, _INT, _P, _P, _INT, _P, _P, _P,
+                                    _P, _SZ, _P]),
     "cgvae_message9_fwd": (_INT, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _INT, _INT, _INT, _INT, _P, _P, _P, _P, _P]),
     "cgvae_message9_bwd": (_INT, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _INT, _INT, _INT, _INT,
                                   _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

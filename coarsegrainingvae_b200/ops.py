@@ -677,7 +677,7 @@ def _tc_applies(geom, n_split):
         if tiles.fill is None:
             live_edges = int(g.rowptr[-1].item())
             n_batches = int(tiles.bptr[-1].item())
-            tiles.fill = live_edges / max(1.0, 32.0 * n_batches)
+            tiles.fill = live_edges / max(1.0, 64.0 * n_batches)
         hit = tiles.fill >= MSG_TC_MIN_FILL
         _TC_DECISIONS[key] = hit
     return hit
@@ -694,10 +694,13 @@ def message_tc_fwd(n_split, phi, v_send, v_recv, geom, Wf, bf, res_s, res_v, wan
     out_s = torch.empty((g.n_recv, F), dtype=torch.float32, device=dev)
     out_v = torch.empty((g.n_recv, 3, F), dtype=torch.float32, device=dev)
     q = torch.empty((g.n_recv, 3, F), dtype=torch.float32, device=dev) if (want_q and n_split == 4) else None
+    ws_bytes = int(lib.cgvae_message_tc_ws_bytes(n_split, tiles.rc, g.n_recv, F))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     t0 = TIMER.begin("message_fwd") if TIMER is not None else None
     _lib.check(lib.cgvae_message_tc_fwd(n_split, _p(phi), _p(v_send), _p(v_recv), _p(tiles.bptr), _p(tiles.ngroups), _p(tiles.rec),
-                                        tiles.rc, _p(Wf), _p(bf), g.n_recv, F, geom.n_rbf, _p(res_s), _p(res_v), int(v_send is None),
-                                        _p(out_s), _p(out_v), _p(q), _stream()), "message_tc_fwd")
+                                        tiles.n_batches_cap, tiles.rc, _p(Wf), _p(bf), g.n_recv, F, geom.n_rbf, _p(res_s),
+                                        _p(res_v), int(v_send is None), _p(out_s), _p(out_v), _p(q), _p(ws), ws_bytes, _stream()),
+               "message_tc_fwd")
     if t0 is not None:
         TIMER.end("message_fwd", t0, dict(n_split=n_split, E=g.n_edges, n_recv=g.n_recv, n_send=g.n_send, F=F,
                                           R=geom.n_rbf, v_zero=v_send is None, tc=True))

@@ -217,10 +217,12 @@ int cgvae_msg_tiles_build(const int32_t* rowptr, const int32_t* col, const int32
 /* cgvae_message_fwd on forward tiles: the filter rbf @ W_filter (modules.py:192-197) is a 3xTF32 tcgen05.mma per batch
  * (accumulators in TMEM, channels on the TMEM lanes), the sender rows are gathered once per (chunk, sender) and re-used
  * from registers for the RC receivers of the chunk.  Same outputs, same arguments as cgvae_message_fwd. */
+size_t cgvae_message_tc_ws_bytes(int n_split, int RC, int64_t n_rows, int F);
 int cgvae_message_tc_fwd(int n_split, const float* phi, const float* v_send, const float* v_recv, const int32_t* bptr,
-                         const int32_t* ngroups, const void* rec, int RC, const float* Wf, const float* bf,
-                         int64_t n_recv, int F, int R, const float* res_s, const float* res_v, int v_is_zero,
-                         float* out_s, float* out_v, float* q, cgvae_stream_t stream);
+                         const int32_t* ngroups, const void* rec, int64_t n_batches_cap, int RC, const float* Wf,
+                         const float* bf, int64_t n_recv, int F, int R, const float* res_s, const float* res_v,
+                         int v_is_zero, float* out_s, float* out_v, float* q, void* ws, size_t ws_bytes,
+                         cgvae_stream_t stream);
 
 /* EquiMessagePsuedo.forward conv.py:180-242 (9 splits) and its backward.  State (s, sbar, v, vbar)
  * on one node set; residual adds fused (cgvae.py:108-111).  The backward also needs the receiver CSR

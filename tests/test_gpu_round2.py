@@ -223,11 +223,14 @@ def test_graphed_step_with_bond_derived_cg_graph_matches_eager():
 
 # ------------------------------------------------------------------------------------------ tensor-core message kernels
 
+NB = 64        # columns per batch record (csrc/message_tc.cu)
+
+
 def _tile_reference(rowptr, col, basis, unit, rc):
     """numpy restatement of the column-tile layout (cgvae_msg_tiles_build): per chunk of rc rows, the sorted union of the
-    partner nodes; column (g, rr) = edge (row chunk*rc+rr <- partner union[g]); 32 columns per batch."""
+    partner nodes; column (g, rr) = edge (row chunk*rc+rr <- partner union[g]); NB columns per batch."""
     n_rows = len(rowptr) - 1
-    gb = 32 // rc
+    gb = NB // rc
     batches = []          # per batch: (gcol list, dense [32, RB] basis, dense [32, 3] unit)
     bptr = [0]
     ngroups = []
@@ -236,7 +239,7 @@ def _tile_reference(rowptr, col, basis, unit, rc):
         union = sorted({int(col[e]) for i in rows for e in range(rowptr[i], rowptr[i + 1])})
         rank = {j: g for g, j in enumerate(union)}
         nb = (len(union) + gb - 1) // gb
-        local = [([0] * gb, np.zeros((32, basis.shape[1]), np.float32), np.zeros((32, 3), np.float32)) for _ in range(nb)]
+        local = [([0] * gb, np.zeros((NB, basis.shape[1]), np.float32), np.zeros((NB, 3), np.float32)) for _ in range(nb)]
         for g, j in enumerate(union):
             local[g // gb][0][g % gb] = j
         for i in rows:
@@ -277,22 +280,24 @@ def test_message_tiles_layout_exact(rc):
             rowptr, col, b_src, u_src = graph.rowptr.cpu().numpy(), graph.col.cpu().numpy(), basis, unit
         bptr, ngroups, batches = _tile_reference(rowptr, col, b_src, u_src, rc)
         assert tiles.bptr.cpu().tolist() == bptr and tiles.ngroups.cpu().tolist() == ngroups
-        rec = tiles.rec.cpu().numpy().reshape(-1, 4608)
-        gb = 32 // rc
+        tile = NB * 16 * 4
+        rec_bytes = (2 * tile + 3 * NB * 4 + (NB // 4) * 4 + 127) // 128 * 128
+        rec = tiles.rec.cpu().numpy().reshape(-1, rec_bytes)
+        gb = NB // rc
         for b, (gcol, bb, uu) in enumerate(batches):
             r = rec[b]
-            hi = r[0:2048].view(np.float32).reshape(4, 4, 8, 4)      # [row group][k chunk][row in group][k in chunk]
-            lo = r[2048:4096].view(np.float32).reshape(4, 4, 8, 4)
-            hi = hi.transpose(0, 2, 1, 3).reshape(32, 16)
-            lo = lo.transpose(0, 2, 1, 3).reshape(32, 16)
-            want = np.zeros((32, 16), np.float32)
+            hi = r[0:tile].view(np.float32).reshape(NB // 8, 4, 8, 4)      # [row group][k chunk][row in group][k in chunk]
+            lo = r[tile:2 * tile].view(np.float32).reshape(NB // 8, 4, 8, 4)
+            hi = hi.transpose(0, 2, 1, 3).reshape(NB, 16)
+            lo = lo.transpose(0, 2, 1, 3).reshape(NB, 16)
+            want = np.zeros((NB, 16), np.float32)
             want[:, :bb.shape[1]] = bb
             assert np.all((hi.view(np.uint32) & 0x1FFF) == 0) and np.all((lo.view(np.uint32) & 0x1FFF) == 0)   # tf32 values
             assert np.abs((hi.astype(np.float64) + lo) - want).max() <= 2.0 ** -21 * max(1e-30, np.abs(want).max())
             assert np.all(hi[np.all(want == 0, axis=1)] == 0)
-            un = r[4096:4096 + 384].view(np.float32).reshape(3, 32).T
+            un = r[2 * tile:2 * tile + 12 * NB].view(np.float32).reshape(3, NB).T
             assert np.array_equal(un, uu)
-            got_gcol = r[4480:4480 + 4 * gb].view(np.int32).tolist()
+            got_gcol = r[2 * tile + 12 * NB:2 * tile + 12 * NB + 4 * gb].view(np.int32).tolist()
             assert got_gcol == gcol, (b, got_gcol, gcol)
 
 

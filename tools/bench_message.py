@@ -63,7 +63,7 @@ def case(tag, xyz_np, cutoff, F, R, n_split, frame_ptr=None):
         if mode != "simt":
             t = ops.message_tiles(geom, False)
             nb = int(t.bptr[-1])
-            row.update(fill=E / (32.0 * nb), build_us=timeit(lambda: (geom.__dict__.pop("_tiles", None), ops.message_tiles(geom, False)), 5)[0])
+            row.update(fill=E / (64.0 * nb), build_us=timeit(lambda: (geom.__dict__.pop("_tiles", None), ops.message_tiles(geom, False)), 5)[0])
         fwd = lambda: ops.message_fwd(n_split, phi, v, v if n_split == 4 else None, geom, Wf, bf, s, v, want_q=n_split == 4)
         med, mn = timeit(fwd)
         row.update(fwd_us=med, fwd_min_us=mn, fwd_Medges_s=E / med, fwd_tflops=flops / med * 1e-6, fwd_frac=flops / med * 1e-6 / PEAK_TF32)
