@@ -32,8 +32,9 @@ if ROOT not in sys.path:
 
 # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) at the chignolin shapes, from the committed
 # ncu --set full capture profiles/r1b_ncu_full_hot_kernels_raw.csv (tools/profile_kernels.py)
-NCU_DRAM_BYTES = {"message_fwd": 12.3e6, "message_bwd": 12.5e6}
-NCU_SOURCE = "profiles/r1b_ncu_full_hot_kernels_raw.csv (tools/profile_kernels.py: same shapes, same build)"
+NCU_DRAM_BYTES = {"message_atom_fwd": 15.0e6, "message_atom_bwd": 12.5e6}
+NCU_SOURCE = ("profiles/r2_ncu_message_tc_fwd_raw.csv (forward, tensor-core kernel) / profiles/r1b_ncu_full_hot_kernels_raw.csv "
+              "(backward): same shapes")
 
 METRIC = "conformations/s (fwd+bwd train step)"
 UNIT = "conformations/s"
@@ -49,6 +50,8 @@ def _args():
     ap.add_argument("--pool", type=int, default=4, help="distinct synthetic batches cycled through")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of one CUDA graph per step")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads (c3 sampling, c4 protein, c5 layer)")
+    ap.add_argument("--fixed-eps", action="store_true", help="pass a fixed noise tensor instead of drawing it inside the step")
     return ap.parse_args()
 
 
@@ -274,6 +277,177 @@ def run_reference(args, cfg):
     print(json.dumps(line))
 
 
+
+# --------------------------------------------------------------------------------------------- kernel families / extras
+
+FAMILY_RULES = (("message_atom_fwd", ("message_tc_fwd", "message_fwd_kernel")), ("message_atom_bwd", ("message_bwd_kernel", "filter_grad_finalize")),
+                ("message9", ("message9_",)), ("gemm_stream", ("gemm_nt_stream", "gemm_nn_stream")),
+                ("gemm_tcgen05", ("gemm_tc_kernel",)), ("gemm_simt", ("gemm_kernel", "gemm_skinny", "gemm_mma", "colsum")),
+                ("wgrad_grouped", ("wgrad_grouped",)), ("adam_clip", ("adam_clip", "sumsq_partial")),
+                ("graph_build", ("csr_", "scan_kernel", "sort_rows", "edge_geometry", "edge_orientation", "segment_", "tile_count", "tile_fill",
+                                 "radius_", "zero_words")),
+                ("nodewise", ("update_", "lift_", "gather_rows", "vec_to_planar", "vec_from_planar", "loss_")))
+
+
+def _family_of(kernel_name):
+    for fam, keys in FAMILY_RULES:
+        if any(k in kernel_name for k in keys):
+            return fam
+    return "torch_aten" if ("at::" in kernel_name or "elementwise" in kernel_name or "reduce" in kernel_name
+                            or "Memcpy" in kernel_name or "Memset" in kernel_name or "cub::" in kernel_name) else "other"
+
+
+def _family_shares(run, n_steps):
+    """CUPTI timeline (torch.profiler) of n_steps steps -> ({family: us per step}, {family: launches per step}, sum us per step).
+    The message family is split by graph size: only the atom-graph launches (the long ones) count as message_atom_*."""
+    import collections
+    import tempfile
+    import torch
+    from torch.profiler import ProfilerActivity, profile
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for i in range(n_steps):
+            run(i)
+        torch.cuda.synchronize()
+    path = os.path.join(tempfile.gettempdir(), "cgvae_bench_trace_%d.json" % os.getpid())
+    prof.export_chrome_trace(path)
+    with open(path) as fh:
+        ev = json.load(fh)["traceEvents"]
+    os.remove(path)
+    dur, cnt = collections.defaultdict(float), collections.defaultdict(int)
+    for e in ev:
+        if e.get("cat") not in ("kernel", "gpu_memset", "gpu_memcpy") or "dur" not in e:
+            continue
+        fam = _family_of(e["name"])
+        if fam in ("message_atom_fwd", "message_atom_bwd") and e["dur"] < 20.0 and "finalize" not in e["name"]:
+            fam = "message_small_graphs"            # prior / contraction / bead-graph launches of the same kernels
+        dur[fam] += e["dur"]
+        cnt[fam] += 1
+    fams = {k: v / n_steps for k, v in dur.items()}
+    return fams, {k: v / n_steps for k, v in cnt.items()}, sum(fams.values())
+
+
+def _timeit(fn, warm, iters):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def _extra_c3(dev, world, rank):
+    """BASELINE config 3: chignolin sampling, n_ensemble 8 -- the prior once + 8 decoder passes per conformation as ONE CUDA
+    graph replay (train.GraphedSampler); under torchrun the 8 members are sharded over the ranks and all-gathered."""
+    import torch
+    import coarsegrainingvae_b200 as cg
+    from coarsegrainingvae_b200 import ops, synthetic
+    from coarsegrainingvae_b200.factory import build_cgvae
+    from coarsegrainingvae_b200.train import GraphedSampler, sample_ensemble_sharded, to_static_batch
+    cfg = dict(synthetic.CONFIGS["c2_chignolin"]); cfg["batch"] = 1
+    rad = lambda xyz, c: ops.radius_graph(torch.as_tensor(xyz, dtype=torch.float32, device=dev), c).cpu().numpy()
+    torch.manual_seed(123)
+    model = build_cgvae(cfg["n_basis"], cfg["n_rbf"], cfg["enc_nconv"], cfg["dec_nconv"], cfg["atom_cutoff"], cfg["cg_cutoff"], cfg["n_cgs"]).to(dev)
+    raw = [synthetic.cgvae_batch(cfg, i, rad, cg.CG_collate) for i in range(4)]
+    n, ncg, n_ens = cfg["n_atoms"], cfg["n_cgs"], 8
+    eps = torch.randn(n_ens, ncg, cfg["n_basis"], device=dev)
+    out = {"what": "1 prior + %d decoder passes per conformation, chignolin model (35 conformations in the config; 4 cycled here)" % n_ens}
+    if world == 1:
+        caps = {"nbr_list": n * (n - 1) // 2, "CG_nbr_list": ncg * (ncg - 1) // 2, "bond_edge_list": max(b["bond_edge_list"].shape[0] for b in raw) + 64}
+        sconfs = [{k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in to_static_batch(b, caps).items()} for b in raw]
+        sampler = GraphedSampler(model, sconfs[0], n_ens)
+        it = [0]
+        def step():
+            sampler.sample(sconfs[it[0] % 4], eps); it[0] += 1
+        ms = _timeit(step, 3, 30)
+        out.update(ms_per_conformation=ms, decoder_passes_per_s=n_ens / ms * 1e3, mode="one CUDA graph per conformation, 1 GPU")
+    else:
+        import torch.distributed as dist
+        confs = [{k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in b.items()} for b in raw]
+        it = [0]
+        def step():
+            sample_ensemble_sharded(model, confs[it[0] % 4], n_ens, eps); it[0] += 1
+        ms = _timeit(step, 2, 10)
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+        out.update(ms_per_conformation=ms, decoder_passes_per_s=n_ens / ms * 1e3,
+                   mode="members sharded m %% world over %d ranks (eager launches) + one all_gather of [n_atoms,3] per member" % world)
+    return out
+
+
+def _extra_c5(dev, world, rank):
+    """BASELINE config 5: one EquiMessageBlock layer on a 20 000-atom graph (message-pass edges/s) + radius-graph build."""
+    import numpy as np
+    import torch
+    from coarsegrainingvae_b200 import ops, synthetic
+    cfg = synthetic.CONFIGS["c5_large"]
+    F, R, cutoff = cfg["n_basis"], cfg["n_rbf"], 8.5
+    xyz = torch.as_tensor(synthetic.lattice_points(cfg["n_atoms"], cfg["spacing"], np.random.default_rng(55), rotate=False), device=dev)
+    n = xyz.shape[0]
+    ms_graph = _timeit(lambda: ops.radius_graph(xyz, 12.0, True), 1, 3)
+    half = ops.radius_graph(xyz, cutoff, True)
+    pairs = torch.cat([half, half.flip(1)], 0)
+    graph = ops.build_graph(pairs, n)
+    geom = ops.edge_geometry(graph, xyz, xyz, R, cutoff)
+    g = torch.Generator().manual_seed(1)
+    phi = torch.randn(n, 3, F, generator=g).to(dev)
+    v = torch.randn(n, 3, F, generator=g).to(dev)
+    s_ = torch.randn(n, F, generator=g).to(dev)
+    Wf = (torch.randn(3 * F, R, generator=g) * 0.3).to(dev)
+    bf = (torch.randn(3 * F, generator=g) * 0.3).to(dev)
+    gs, gv = torch.randn(n, F, generator=g).to(dev), torch.randn(n, 3, F, generator=g).to(dev)
+    E = graph.n_edges
+    ms_f = _timeit(lambda: ops.message_fwd(3, phi, v, None, geom, Wf, bf, s_, v), 2, 5)
+    ms_b = _timeit(lambda: ops.message_bwd(3, phi, v, None, None, geom, Wf, bf, gs, gv, True, sink=False), 2, 5)
+    flops = 2.0 * (R + 1) * 3 * F * E
+    return {"what": "one fused message layer (K=3, F=%d, R=%d) on %d atoms, cutoff %.1f A: %d directed edges; replicas only under "
+                    "torchrun (no graph partitioning)" % (F, R, n, cutoff, E),
+            "fwd_ms": ms_f, "bwd_ms": ms_b, "fwd_edges_per_s": E / ms_f * 1e3, "fwd_bwd_edges_per_s": E / (ms_f + ms_b) * 1e3,
+            "fwd_filter_tflops": flops / ms_f * 1e-9, "bwd_filter_tflops": 2 * flops / ms_b * 1e-9,
+            "radius_graph_12A_ms": ms_graph, "radius_graph_12A_pairs": int(ops.radius_graph(xyz, 12.0, True).shape[0])}
+
+
+def _extra_c4(dev, world, rank):
+    """BASELINE config 4: PCN (run_pdb path), ~2000-atom proteins, alpha-carbon CG; global batch 64 split over the ranks
+    (strong scaling: 64 / world proteins per rank), one NCCL all-reduce of the flat gradient buffer per step."""
+    import torch
+    from coarsegrainingvae_b200 import ops, synthetic
+    from coarsegrainingvae_b200.factory import build_pcn
+    from coarsegrainingvae_b200.train import TrainStep
+    cfg = dict(synthetic.CONFIGS["c4_protein"])
+    per_rank = max(1, cfg["batch"] // world)
+    rad = lambda xyz, c: ops.radius_graph(torch.as_tensor(xyz, dtype=torch.float32, device=dev), c).cpu().numpy()
+    raw = synthetic.pcn_batch(cfg, rank, rad, n_proteins=per_rank)
+    batch = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in raw.items()}
+    torch.manual_seed(123)
+    model = build_pcn(cfg["n_basis"], cfg["n_rbf"], cfg["cg_cutoff"], cfg["dec_nconv"]).to(dev)
+
+    class _PCNStep(TrainStep):
+        def _loss(self, b, eps):
+            out = self.model(b)
+            from coarsegrainingvae_b200.train import training_loss
+            return training_loss(out, out[4], b["bond_edge_list"], 0.0, self.gamma, None, b.get("dp_norms"))[0]
+
+    tr = _PCNStep(model, 0.0, 1.0, lr=1e-4, loss_limit=None)
+    tr.prepare(batch, None)
+    ms = _timeit(lambda: tr.step(batch, None), 2, 4)
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+    out = {"what": "PCN train step (EquivariantDecoder cross_flag=True, F=%d, 9 layers), %d proteins x %d atoms per rank, global batch %d, "
+                   "eager launches" % (cfg["n_basis"], per_rank, cfg["n_res"] * cfg["atoms_per_res"], per_rank * world),
+           "ms_per_step": ms, "conformations_per_s": per_rank * world / ms * 1e3, "scaling": "strong (global batch 64)",
+           "max_memory_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30}
+    tr.flat.release()
+    return out
+
 # --------------------------------------------------------------------------------------------- CUDA arm
 
 def run_cuda(args, cfg):
@@ -316,7 +490,10 @@ def run_cuda(args, cfg):
     torch.manual_seed(123)                                   # identical replicas on every rank
     model = build_cgvae(cfg["n_basis"], cfg["n_rbf"], cfg["enc_nconv"], cfg["dec_nconv"], cfg["atom_cutoff"], cfg["cg_cutoff"],
                         cfg["n_cgs"]).to(dev)
-    eps = torch.randn(cfg["batch"] * cfg["n_cgs"], cfg["n_basis"], generator=torch.Generator().manual_seed(7)).to(dev)
+    # the reparametrisation noise is DRAWN INSIDE the step (torch.randn_like under the graph-safe philox generator: a new
+    # draw every replay, as cgvae.py:445-449 does); --fixed-eps passes one tensor instead (parity runs)
+    eps = torch.randn(cfg["batch"] * cfg["n_cgs"], cfg["n_basis"], generator=torch.Generator().manual_seed(7)).to(dev) \
+        if args.fixed_eps else None
     trainer = TrainStep(model, cfg["beta"], cfg["gamma"], lr=1e-4, max_norm=0.01, capturable=use_graph)
     used = trainer.prepare(dev_batches[0], eps)
     n_used = int(trainer.flat.flat.numel())
@@ -383,123 +560,117 @@ def run_cuda(args, cfg):
     ms_e2e = float(ms_e) / max(args.steps, 1)
     e2e_value = cfg["batch"] * n_gpus / (ms_e2e / 1e3)
 
-    # ---- roofline of the dominant kernel (fused message layer on the ATOM graph): CUDA events around the individual
-    # launches.  Kernel boundaries are not host-visible inside a graph replay, so these launches are timed in eager
-    # steps of the same workload, same process, right after the timed region.
-    ops.TIMER = ops.KernelTimer(["message_fwd", "message_bwd", "adam_clip"])
-    n_prof = min(args.steps, 10)
-    for i in range(n_prof):
-        trainer.step(dev_batches[i % args.pool], eps)
-    sync_all()
-    timer, ops.TIMER = ops.TIMER, None
+    # ---- extra timed regions (same K steps each): run-to-run spread of the headline number
+    reps_ms = [ms]
+    for _ in range(2):
+        sync_all()
+        e0.record()
+        for i in range(args.steps):
+            run_step(i % args.pool)
+        e1.record()
+        sync_all()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        reps_ms.append(float(t) / max(args.steps, 1))
+
     peaks = _peaks()
     tf32_peak = 0.5 * peaks["bf16_sustained"]
-    roof, other = None, {}
-    summ = timer.summary()
-    R, F = cfg["n_rbf"], cfg["n_basis"]
-    for name, factor in (("message_fwd", 1.0), ("message_bwd", 2.0)):
-        recs = [(t, m) for t, m in summ.get(name, []) if m["E"] >= edges // 2 and m["n_recv"] == m["n_send"]]
-        if not recs:
-            continue
-        t_ms = float(np.mean([t for t, _ in recs]))
-        E = float(edges)           # live directed edges (the static-capacity graph holds a few padded slots on top)
-        flops = factor * 2.0 * (R + 1) * 3 * F * E                   # filter contraction incl. the bias column
-        share = (sum(t for t, _ in recs) / n_prof) / ms
-        entry = {"kernel": name + "_kernel<3,%d> (atom graph)" % (ops.rb_for(R) // 4), "bound": "tensor",
-                 "achieved": flops / (t_ms * 1e-3) / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
-                 "frac": flops / (t_ms * 1e-3) / 1e12 / tf32_peak, "traffic": NCU_DRAM_BYTES.get(name),
-                 "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of this launch in " + NCU_SOURCE,
-                 "fp32_simt": {"achieved_tflops": 2.0 * (46.0 if factor == 1.0 else 61.0) * E * F / (t_ms * 1e-3) / 1e12,
-                               "peak_tflops": 2.0 * 148 * 128 * 1.965e-3,
-                               "note": "all fp32 FMAs of the kernel (filter + channel mixing, 46 / 61 per edge and channel "
-                                       "forward / backward) against the SIMT FMA peak: the bound this implementation runs on"},
-                 "peak_source": "derived: 0.5 x bf16_tflops_sustained of %s MEASURED_PEAKS (TF32 is not measured there)" % peaks["source"],
-                 "avg_launch_us": 1e3 * t_ms, "launches_per_step": len(recs) / n_prof, "edges_per_launch": E,
-                 "edges_per_s": E / (t_ms * 1e-3), "share_of_step": share,
-                 "note": "fp32 SIMT implementation this round: the tensor pipe is idle, frac is measured against the "
-                         "tensor roofline the north star names"}
-        other[name] = entry
-    if other:
-        roof = max(other.values(), key=lambda e: e["share_of_step"])
-    # HBM-bound streaming kernels of the step: algorithmic bytes / measured time against the measured copy bandwidth
     hbm_peak = peaks["hbm_gbs"]
+    R, F = cfg["n_rbf"], cfg["n_basis"]
 
-    def hbm_entry(kernel, recs, bytes_of, note):
-        if not recs:
-            return None
-        tot_ms = sum(t for t, _ in recs)
-        tot_b = float(sum(bytes_of(m) for _, m in recs))
-        return {"kernel": kernel, "bound": "hbm", "achieved": tot_b / (tot_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                "frac": tot_b / (tot_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None, "launches_per_step": len(recs) / n_prof,
-                "avg_launch_us": 1e3 * tot_ms / len(recs), "algorithmic_bytes_per_step": tot_b / n_prof,
-                "share_of_step": (tot_ms / n_prof) / ms, "peak_source": "hbm_gbs of %s MEASURED_PEAKS" % peaks["source"], "note": note}
+    # ---- where the step time goes: CUPTI kernel timeline of graph replays (torch.profiler), grouped into kernel families
+    families, fam_launches, timeline_note = {}, {}, None
+    try:
+        families, fam_launches, span_us = _family_shares(lambda i: run_step(i % args.pool), 3)
+        timeline_note = ("torch.profiler (CUPTI) over 3 %s; share = sum of the family's kernel durations / sum of all kernel "
+                         "durations of a step (%.0f us; branches of the captured graph overlap, so the sum exceeds ms_per_step)"
+                         % ("graph replays" if use_graph else "eager steps", span_us))
+    except Exception as exc:                        # the timeline is evidence, not a dependency of the headline number
+        timeline_note = "unavailable: %r" % (exc,)
 
-    # Kernels of a few microseconds cannot be timed launch by launch in eager mode (the host is slower than the GPU, the
-    # event pair would measure the wait for the next launch): the EXACT launches of one step -- same operands, same
-    # weights, 270 MB of them so nothing stays in L2 between replays -- are re-issued back to back inside one CUDA graph
-    # and the graph is timed with CUDA events.
-    ops.TIMER = ops.KernelTimer(["gemm", "wgrad_grouped"], keep_operands=True)
+    # ---- algorithmic work of one step per family: shapes recorded during ONE eager step of the same workload
+    ops.TIMER = ops.KernelTimer(["gemm", "wgrad_grouped", "message_fwd", "message_bwd", "adam_clip"], keep_operands=False)
     trainer.step(dev_batches[0], eps)
     sync_all()
-    keep, ops.TIMER = ops.TIMER, None
-    ksumm = keep.summary()
+    rec, ops.TIMER = ops.TIMER, None
+    rsum = rec.summary()
+    E = float(edges)
 
-    def graph_time_ms(fn, reps=5):
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            fn()
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        g_ = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g_):
-            fn()
-        g_.replay()
-        torch.cuda.synchronize()
-        a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a_.record()
-        for _ in range(reps):
-            g_.replay()
-        b_.record()
-        torch.cuda.synchronize()
-        return a_.elapsed_time(b_) / reps
+    def gemm_family(m):
+        Mr, Nr, Kr, form = m["M"], m["N"], m["K"], m["form"]
+        if (form == ops.GEMM_NT and Mr <= 48) or (form == ops.GEMM_NN and Mr <= 16):
+            return "gemm_stream"
+        if form != ops.GEMM_TN and Mr >= 256 and Nr >= 64 and 64 <= Kr <= 1280:
+            return "gemm_tcgen05"
+        return "gemm_simt"
 
-    calls = [m for _, m in ksumm.get("gemm", []) if m["M"] <= 16 and m["form"] != ops.GEMM_TN and m["N"] * m["K"] >= 4096]
-    tables = [m["table"] for _, m in ksumm.get("wgrad_grouped", []) if m.get("table")]
+    work = {"gemm_stream": 0.0, "gemm_simt": 0.0, "gemm_tcgen05": 0.0}
+    for _, m in rsum.get("gemm", []):
+        fam = gemm_family(m)
+        work[fam] += 4.0 * m["N"] * m["K"] if fam == "gemm_stream" else 2.0 * m["M"] * m["N"] * m["K"]
+    msg_f = [m for _, m in rsum.get("message_fwd", []) if m["E"] >= edges // 2 and m["n_recv"] == m["n_send"]]
+    msg_b = [m for _, m in rsum.get("message_bwd", []) if m["E"] >= edges // 2 and m["n_recv"] == m["n_send"]]
+    filt = 2.0 * (R + 1) * 3 * F * E                 # filter contraction incl. the bias column per launch
+    work["message_atom_fwd"] = filt * len(msg_f)
+    work["message_atom_bwd"] = 2.0 * filt * len(msg_b)
+    work["wgrad_grouped"] = 4.0 * sum(m.get("out_floats", 0) for _, m in rsum.get("wgrad_grouped", []))
+    work["adam_clip"] = 32.0 * n_used
+    tc_fwd = any(m.get("tc") for m in msg_f)
 
-    def replay_gemms():
-        for m in calls:
-            ops.gemm(m["form"], m["A"], m["B"], m["M"], m["N"], m["K"], bias=m["bias"], act=m["act"], z_in=m["z_in"],
-                     dact=m["dact"], add=m["add"])
+    MODELS = {
+        "message_atom_fwd": ("tensor", "message_tc_fwd_kernel (filter on tcgen05, 3xTF32)" if tc_fwd else "message_fwd_kernel<3,%d>" % (ops.rb_for(R) // 4),
+                             "filter flops 2(R+1)*3F per directed edge"),
+        "message_atom_bwd": ("tensor", "message_bwd_kernel<3,%d> (fp32 SIMT)" % (ops.rb_for(R) // 4), "2x the forward filter flops"),
+        "gemm_simt": ("tensor", "gemm_kernel<64,64,16,4,4> family (fp32 SIMT tiles: atom-level Dense layers and their gradients)", "2MNK per call"),
+        "gemm_tcgen05": ("tensor", "tc::gemm_tc_kernel (tcgen05, 3xTF32)", "2MNK per call"),
+        "gemm_stream": ("hbm", "gemm_nt_stream / gemm_nn_stream (12-bead Dense layers, TMA weight streaming)", "the weight matrix once per launch"),
+        "wgrad_grouped": ("hbm", "wgrad_grouped_kernel (small-graph weight / bias gradients)", "gradients written once"),
+        "adam_clip": ("hbm", "sumsq_partial + adam_clip_kernel", "4 (norm pass) + 28 (p, g, m, v read; p, m, v written) bytes per parameter"),
+    }
+    other = {}
+    tot_us = sum(families.values()) or 1.0
+    for fam, (bound, kernel, per_unit) in MODELS.items():
+        t_us = families.get(fam)
+        if not t_us or not work.get(fam):
+            continue
+        if bound == "tensor":
+            ach, peak, unit = work[fam] / (t_us * 1e-6) / 1e12, tf32_peak, "TFLOP/s"
+            src = "derived: 0.5 x bf16_tflops_sustained of %s MEASURED_PEAKS (TF32 is not measured there)" % peaks["source"]
+        else:
+            ach, peak, unit = work[fam] / (t_us * 1e-6) / 1e9, hbm_peak, "GB/s"
+            src = "hbm_gbs of %s MEASURED_PEAKS" % peaks["source"]
+        other[fam] = {"kernel": kernel, "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
+                      "traffic": NCU_DRAM_BYTES.get(fam), "algorithmic_work_per_step": work[fam], "work_model": per_unit,
+                      "time_per_step_us": t_us, "launches_per_step": fam_launches.get(fam), "share_of_step": t_us / tot_us,
+                      "peak_source": src}
+        if fam.startswith("message_atom"):
+            n_l = max(fam_launches.get(fam) or 1, 1)
+            other[fam].update(avg_launch_us=t_us / n_l, edges_per_launch=E, edges_per_s=E / (t_us / n_l * 1e-6),
+                              traffic_source="dram__bytes_read.sum + dram__bytes_write.sum of this launch in " + NCU_SOURCE)
+    # the roofline entry = the modelled family with the largest share of the graph-replay time
+    roof = max(other.values(), key=lambda e: e["share_of_step"]) if other else None
+    family_shares = {k: {"us_per_step": v, "share": v / tot_us, "launches": fam_launches.get(k)} for k, v in
+                     sorted(families.items(), key=lambda kv: -kv[1])}
+    # step-level HBM floor: every used parameter is read in forward and backward, its gradient written, and the optimiser
+    # pass moves 32 bytes per parameter
+    step_bytes = 44.0 * n_used
+    hbm_floor = {"bytes_per_step": step_bytes, "floor_ms": step_bytes / (hbm_peak * 1e9) * 1e3,
+                 "frac_of_floor": (step_bytes / (hbm_peak * 1e9) * 1e3) / ms,
+                 "model": "used parameters x (4 fwd read + 4 bwd read + 4 gradient write + 32 clip/Adam) bytes"}
 
-    def replay_wgrad():
-        for tb in tables:
-            ops.wgrad_grouped(tb)
-
-    iso = []
-    if calls:
-        iso.append(("gemm_stream", "gemm_nt_stream / gemm_nn_stream (12-bead Dense layers, TMA weight streaming)",
-                    graph_time_ms(replay_gemms), len(calls), float(sum(4.0 * m["N"] * m["K"] for m in calls)),
-                    "bytes = the weight matrix once per launch; the %d launches of one step replayed back to back in a CUDA graph" % len(calls)))
-    if tables:
-        n_launch = sum((len(tb) + ops.WGRAD_PROBLEMS_PER_LAUNCH - 1) // ops.WGRAD_PROBLEMS_PER_LAUNCH for tb in tables)
-        iso.append(("wgrad_grouped", "wgrad_grouped_kernel (all small-graph weight / bias gradients of the step)",
-                    graph_time_ms(replay_wgrad), n_launch,
-                    float(sum(4.0 * ((p[2].numel() if p[2] is not None else 0) + (p[3].numel() if p[3] is not None else 0))
-                              for tb in tables for p in tb)),
-                    "bytes = gradients written once; the launches of one step replayed in a CUDA graph"))
-    for key, kernel, t_ms, n_l, tot_b, note in iso:
-        other[key] = {"kernel": kernel, "bound": "hbm", "achieved": tot_b / (t_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                      "frac": tot_b / (t_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None, "launches_per_step": n_l,
-                      "avg_launch_us": 1e3 * t_ms / n_l, "algorithmic_bytes_per_step": tot_b, "share_of_step": t_ms / ms,
-                      "peak_source": "hbm_gbs of %s MEASURED_PEAKS" % peaks["source"], "note": note}
-    del keep, ksumm, calls, tables
-    for key, ent in (
-            ("adam_clip", hbm_entry("sumsq_partial + adam_clip_kernel (clip_grad_norm_ + Adam on flat buffers)",
-                                    summ.get("adam_clip", []), lambda m: 32.0 * m["n"],
-                                    "bytes = 4 (norm pass) + 28 (p, g, m, v read; p, m, v written) per parameter")),):
-        if ent is not None:
-            other[key] = ent
+    # ---- secondary workloads of BASELINE.json (bounded; failures are reported, never fatal)
+    extra = {}
+    if not args.no_extra:
+        graphed = None
+        trainer.flat.release()
+        for name, fn in (("c3_sampling", _extra_c3), ("c5_layer", _extra_c5), ("c4_protein", _extra_c4)):
+            try:
+                torch.cuda.empty_cache()
+                extra[name] = fn(dev, world, rank)
+            except Exception as exc:
+                extra[name] = {"error": repr(exc)[:300]}
+            sync_all()
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -513,8 +684,10 @@ def run_cuda(args, cfg):
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": 4, "last_loss": last},
             "gpu_launches": int(launches),
-            "roofline": roof, "roofline_kernels": other,
-            "message_pass_edges_per_s": (other.get("message_fwd") or {}).get("edges_per_s")}
+            "roofline": roof, "roofline_kernels": other, "kernel_family_shares": family_shares, "timeline": timeline_note,
+            "hbm_floor": hbm_floor, "ms_per_step_repeats": reps_ms, "ms_per_step_median": statistics.median(reps_ms),
+            "message_pass_edges_per_s": (other.get("message_atom_fwd") or {}).get("edges_per_s"),
+            "other_workloads": extra}
 
     if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1

@@ -90,10 +90,10 @@ class EquivariantPsuedoDecoder(nn.Module):
             g.cg = g.directed_graph("cg", CG_nbr_list, S.shape[0])
         geom = g.geometry("cg", cg_xyz, cg_xyz, self.n_rbf, self.cutoff)
         n, f = S.shape
-        V = torch.zeros(n, 3, f, device=S.device, dtype=S.dtype)
-        Sbar = torch.ones(n, f, device=S.device, dtype=S.dtype) if self.breaksym else \
-            torch.zeros(n, f, device=S.device, dtype=S.dtype)
-        Vbar = torch.zeros(n, 3, f, device=S.device, dtype=S.dtype)
+        # initial decoder state (cgvae.py:90-95): V = Vbar = 0, Sbar = 1 (breaksym) or 0 -- two fills of our own
+        zeros = ops.fill((6 * n * f,), 0.0, S)
+        V, Vbar = zeros[:3 * n * f].view(n, 3, f), zeros[3 * n * f:].view(n, 3, f)
+        Sbar = ops.fill((n, f), 1.0 if self.breaksym else 0.0, S)
         for i, message_block in enumerate(self.message_blocks):
             S, Sbar, V, Vbar = message_block.fused(S, Sbar, V, Vbar, geom)
             S, V = self.update_blocks[i].fused(S, V)
@@ -210,7 +210,7 @@ class CGprior(nn.Module):
             h, v = self.message_blocks[i].fused(h, v, geom)
         H_mu = _mlp(self.mu, 3, h)
         H_sigma = _mlp(self.sigma, 3, h)
-        H_std = 1e-9 + torch.exp(H_sigma / 2)
+        H_std = fn.StdLogvar.apply(H_sigma, 1e-9)
         return H_mu, H_std
 
 
@@ -283,8 +283,13 @@ class CGequiVAE(nn.Module):
         z = S_I
         mu = _mlp(self.atom_munet, _act_code_of(self.atom_munet[1]), z)
         logvar = _mlp(self.atom_sigmanet, _act_code_of(self.atom_sigmanet[1]), z)
-        sigma = 1e-12 + torch.exp(logvar / 2)
-        z_sample = self.reparametrize(mu, sigma, eps) if not self.det else z
+        if self.det:
+            sigma, z_sample = fn.StdLogvar.apply(logvar, 1e-12), z
+        else:
+            # sigma = 1e-12 + exp(logvar / 2) and z = eps * sigma + mu in one launch (cgvae.py:445-449,500-507)
+            if eps is None:
+                eps = torch.randn_like(logvar)
+            z_sample, sigma = fn.VAELatent.apply(mu, logvar, eps)
         xyz_recon = self.decoder(cg_xyz, CG_nbr_list, z_sample, s_i, mapping, num_CGs, graphs=g)
         ops.check_device_errors(xyz_recon.device)      # IndexError where the reference raises one (cgvae.py:473)
         return mu, sigma, H_prior_mu, H_prior_sigma, xyz, xyz_recon

@@ -349,14 +349,17 @@ int launch_gemm_tcgen05(int form, const float* A, int64_t lda, const float* B, i
   // K = 1e4..1e5 rows) stay on the SIMT kernel with its two-level fp32 accumulation
   // accuracy: TMEM accumulation is not round-to-nearest, the error grows linearly with the length of the k-loop
   // (3e-6 at K = 512, 1.5e-5 at K = 2048 on B200) -> the 1e-5 gate allows K <= 1280 here
-  if (M < 256 || N < 64 || K < 64 || K > 1280) return 0;
+  static const int min_m = [] { const char* e = getenv("CGVAE_TC_MIN_M"); return e ? atoi(e) : 256; }();
+  static const int min_tiles_nt = [] { const char* e = getenv("CGVAE_TC_MIN_TILES_NT"); return e ? atoi(e) : 64; }();
+  static const int min_tiles_nn = [] { const char* e = getenv("CGVAE_TC_MIN_TILES_NN"); return e ? atoi(e) : 2 * kNumSM; }();
+  if (M < min_m || N < 64 || K < 64 || K > 1280) return 0;
   // measured on B200 against the SIMT tiles (tools/check_tc.py): NT 1.3-1.55x faster once the grid fills the machine;
   // NN (B needs the transposing stage) only pays with >= one full wave of tiles; TN (both operands transposed, and its
   // k-loop runs over node counts) stays on the SIMT kernel
   const int64_t n_tiles = ceil_div(M, tc::BM) * ceil_div(N, tc::BN);
   if (form == CGVAE_GEMM_TN) return 0;
-  if (form == CGVAE_GEMM_NT && n_tiles < 64) return 0;
-  if (form == CGVAE_GEMM_NN && n_tiles < 2 * kNumSM) return 0;
+  if (form == CGVAE_GEMM_NT && n_tiles < min_tiles_nt) return 0;
+  if (form == CGVAE_GEMM_NN && n_tiles < min_tiles_nn) return 0;
   tc::Ep ep{bias, act, z_out, z_in, dact, add};
   const bool a_kc = (form != CGVAE_GEMM_TN), b_kc = (form == CGVAE_GEMM_NT);
   const bool a_vec = aligned16(A) && (lda % 4 == 0), b_vec = aligned16(B) && (ldb % 4 == 0);

@@ -250,3 +250,76 @@ class Lift(Function):
     @once_differentiable
     def backward(ctx, g):
         return None, None, None, ops.lift_bwd(g.contiguous(), ctx.seg, ctx.F, ctx.mode, ctx.pin), None
+
+
+class VAELatent(Function):
+    """(z, sigma) = (eps * sigma + mu, 1e-12 + exp(logvar / 2)): the posterior scale and the reparametrisation of
+    cgvae.py:445-449,500-507 in one launch (three element-wise launches + their backward in the reference)."""
+
+    @staticmethod
+    def forward(ctx, mu, logvar, eps):
+        z, sigma = ops.vae_latent_fwd(mu, logvar, eps)
+        ctx.save_for_backward(eps, sigma)
+        return z, sigma
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_z, g_sigma):
+        eps, sigma = ctx.saved_tensors
+        g_mu, g_logvar = ops.vae_latent_bwd(g_z.contiguous() if g_z is not None else None,
+                                            g_sigma.contiguous() if g_sigma is not None else None, eps, sigma)
+        return g_mu, g_logvar, None
+
+
+class StdLogvar(Function):
+    """y = c + exp(x / 2): the prior std (cgvae.py:401, c = 1e-9) and the posterior std when no sample is drawn."""
+
+    @staticmethod
+    def forward(ctx, x, c):
+        y = ops.std_logvar_fwd(x, c)
+        ctx.c = c
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        (y,) = ctx.saved_tensors
+        return ops.std_logvar_bwd(gy.contiguous(), y, ctx.c), None
+
+
+class TrainingLoss(Function):
+    """scripts/utils.py:117-141 as one node: returns (loss [1], components [4] = loss, recon, kl, graph; not differentiable).
+    Gradients flow to xyz_recon, mu, sigma and the prior mean / std; the bond term uses the CSR of the symmetrised bond list."""
+
+    @staticmethod
+    def forward(ctx, bond_graph, beta, gamma, norms, xyz, xyz_rec, mu, sigma, pmu, pstd):
+        xyz, xyz_rec = xyz.contiguous(), xyz_rec.contiguous()
+        if mu is not None:
+            mu, sigma = mu.contiguous(), sigma.contiguous()
+        if pmu is not None:
+            pmu, pstd = pmu.contiguous(), pstd.contiguous()
+        out4 = ops.loss_fwd(xyz, xyz_rec, bond_graph, mu, sigma, pmu, pstd, norms, beta, gamma)
+        ctx.bond_graph, ctx.beta, ctx.gamma, ctx.norms = bond_graph, beta, gamma, norms
+        ctx.has = (mu is not None, pmu is not None)
+        ctx.save_for_backward(xyz, xyz_rec, *([mu, sigma] if mu is not None else []), *([pmu, pstd] if pmu is not None else []))
+        comps = out4.detach()
+        ctx.mark_non_differentiable(comps)
+        return out4.narrow(0, 0, 1).reshape(()), comps
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_loss, _g_comps):
+        saved = list(ctx.saved_tensors)
+        xyz, xyz_rec = saved[0], saved[1]
+        mu = sigma = pmu = pstd = None
+        k = 2
+        if ctx.has[0]:
+            mu, sigma = saved[k], saved[k + 1]
+            k += 2
+        if ctx.has[1]:
+            pmu, pstd = saved[k], saved[k + 1]
+        g = g_loss.reshape(1).contiguous()
+        g_rec, g_mu, g_sigma, g_pmu, g_pstd = ops.loss_bwd(g, xyz, xyz_rec, ctx.bond_graph, mu, sigma, pmu, pstd, ctx.norms,
+                                                           ctx.beta, ctx.gamma)
+        return None, None, None, None, None, g_rec, g_mu, g_sigma, g_pmu, g_pstd

@@ -614,16 +614,19 @@ class MessageTiles(object):
 
 
 # Tensor-core message path policy.  CGVAE_MSG_TC=0 disables it; =1 forces it wherever it applies (homogeneous graph,
-# R <= 15).  Default "auto": graphs with at least MSG_TC_MIN_EDGES directed edge slots and a mean degree of at least
-# MSG_TC_MIN_DEGREE, and -- measured once per graph SHAPE outside CUDA-graph capture -- a column fill (edges / columns
-# of the tiles) of at least MSG_TC_MIN_FILL: below that the zero columns cost more than the register re-use of the
-# gathered sender rows saves and the SIMT kernel of message.cu (L1 re-use across 4 receivers) is the better path.
+# R <= 15).  Default "auto": 3-split layers on graphs with at least MSG_TC_MIN_EDGES directed edge slots and a mean degree
+# of at least MSG_TC_MIN_DEGREE, and -- measured once per graph SHAPE outside CUDA-graph capture -- a column fill (edges /
+# columns of the tiles) of at least MSG_TC_MIN_FILL.  Measured on B200 (tools/bench_message.py, profiles/r2_bench_message*):
+# at chignolin density (fill 0.89) the tensor-core kernel is 1.7x the SIMT one (85 vs 142 us), at fill 0.5 (20 000 atoms,
+# 12 A) 1.2x, below 0.4 it loses: the zero columns then cost more than the register re-use of the gathered sender rows
+# saves, and the SIMT kernel of message.cu (L1 re-use across 4 receivers) is the better path.  The cross block (4 splits;
+# PCN residue graph, fill 0.45-0.5) measured 0.7x and stays on the SIMT kernel unless forced.
 import os as _os
 MSG_TC = _os.environ.get("CGVAE_MSG_TC", "auto")
 MSG_TC_RC = int(_os.environ.get("CGVAE_MSG_TC_RC", "8"))
 MSG_TC_MIN_EDGES = 4096
 MSG_TC_MIN_DEGREE = 12.0
-MSG_TC_MIN_FILL = float(_os.environ.get("CGVAE_MSG_TC_MIN_FILL", "0.35"))
+MSG_TC_MIN_FILL = float(_os.environ.get("CGVAE_MSG_TC_MIN_FILL", "0.45"))
 _TC_DECISIONS = {}
 
 
@@ -666,6 +669,8 @@ def _tc_applies(geom, n_split):
         return False
     if MSG_TC == "1":
         return True
+    if n_split != 3:
+        return False
     if g.n_edges < MSG_TC_MIN_EDGES or g.n_edges < MSG_TC_MIN_DEGREE * g.n_recv:
         return False
     key = (g.n_recv, (g.n_edges // g.n_recv) // 4, MSG_TC_RC)     # per graph shape: nodes, degree bucket
@@ -938,3 +943,84 @@ def adam_clip_step(p, g, m, v, step, max_norm, lr, betas=(0.9, 0.999), eps=1e-8,
                "adam_clip_step")
     if t0 is not None:
         TIMER.end("adam_clip", t0, dict(n=p.numel()))
+
+
+# --------------------------------------------------------------------------------------------------
+# VAE latent, prior std, fused training loss (csrc/loss.cu)
+# --------------------------------------------------------------------------------------------------
+
+def fill(shape, value, like):
+    """torch.full(shape, value) on ``like``'s device through the library's own fill kernel (initial decoder state, cgvae.py:90-95)."""
+    lib = _lib.load()
+    _f32(like)
+    out = torch.empty(shape, dtype=torch.float32, device=like.device)
+    _need_cuda(out)
+    _lib.check(lib.cgvae_fill(_p(out), out.numel(), float(value), _stream()), "fill")
+    return out
+
+
+def vae_latent_fwd(mu, logvar, eps):
+    """(z, sigma): sigma = 1e-12 + exp(logvar/2), z = eps*sigma + mu (cgvae.py:445-449,500-507); eps None: sigma only."""
+    _need_cuda(logvar)
+    lib = _lib.load()
+    logvar = _f32(logvar)
+    sigma = torch.empty_like(logvar)
+    z = torch.empty_like(logvar) if eps is not None else None
+    _lib.check(lib.cgvae_vae_latent_fwd(_p(_f32(mu)) if eps is not None else None, _p(logvar), _p(_f32(eps)) if eps is not None else None,
+                                        logvar.numel(), _p(sigma), _p(z), _stream()), "vae_latent_fwd")
+    return z, sigma
+
+
+def vae_latent_bwd(g_z, g_sigma, eps, sigma):
+    lib = _lib.load()
+    g_mu = torch.empty_like(sigma) if g_z is not None else None
+    g_logvar = torch.empty_like(sigma)
+    _lib.check(lib.cgvae_vae_latent_bwd(_p(g_z), _p(g_sigma), _p(eps), _p(sigma), sigma.numel(), _p(g_mu), _p(g_logvar), _stream()),
+               "vae_latent_bwd")
+    return g_mu, g_logvar
+
+
+def std_logvar_fwd(x, c):
+    _need_cuda(x)
+    lib = _lib.load()
+    x = _f32(x)
+    y = torch.empty_like(x)
+    _lib.check(lib.cgvae_std_logvar_fwd(_p(x), x.numel(), float(c), _p(y), _stream()), "std_logvar_fwd")
+    return y
+
+
+def std_logvar_bwd(gy, y, c):
+    lib = _lib.load()
+    gx = torch.empty_like(y)
+    _lib.check(lib.cgvae_std_logvar_bwd(_p(_f32(gy)), _p(y), y.numel(), float(c), _p(gx), _stream()), "std_logvar_bwd")
+    return gx
+
+
+def loss_fwd(xyz, xyz_rec, bond_graph, mu, sigma, pmu, pstd, norms, beta, gamma, out=None):
+    """(loss, recon, kl, graph) as one float[4] tensor: scripts/utils.py:117-141 in two launches."""
+    _need_cuda(xyz_rec)
+    lib = _lib.load()
+    dev = xyz_rec.device
+    out4 = out if out is not None else torch.empty(4, dtype=torch.float32, device=dev)
+    ws_bytes = int(lib.cgvae_loss_ws_bytes())
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    n_beads, F = (mu.shape[0], mu.shape[1]) if mu is not None else (0, 0)
+    _lib.check(lib.cgvae_loss_fwd(_p(xyz), _p(xyz_rec), xyz_rec.shape[0], _p(bond_graph.rowptr) if bond_graph is not None else None,
+                                  _p(bond_graph.col) if bond_graph is not None else None, _p(mu), _p(sigma), _p(pmu), _p(pstd),
+                                  n_beads, F, _p(norms), float(beta), float(gamma), _p(out4), _p(ws), ws_bytes, _stream()), "loss_fwd")
+    return out4
+
+
+def loss_bwd(g_loss, xyz, xyz_rec, bond_graph, mu, sigma, pmu, pstd, norms, beta, gamma):
+    lib = _lib.load()
+    g_rec = torch.empty_like(xyz_rec)
+    g_mu = torch.empty_like(mu) if mu is not None else None
+    g_sigma = torch.empty_like(mu) if mu is not None else None
+    g_pmu = torch.empty_like(pmu) if pmu is not None else None
+    g_pstd = torch.empty_like(pmu) if pmu is not None else None
+    n_beads, F = (mu.shape[0], mu.shape[1]) if mu is not None else (0, 0)
+    _lib.check(lib.cgvae_loss_bwd(_p(g_loss), _p(xyz), _p(xyz_rec), xyz_rec.shape[0], _p(bond_graph.rowptr) if bond_graph is not None else None,
+                                  _p(bond_graph.col) if bond_graph is not None else None, _p(mu), _p(sigma), _p(pmu), _p(pstd), n_beads,
+                                  F, _p(norms), float(beta), float(gamma), _p(g_rec), _p(g_mu), _p(g_sigma), _p(g_pmu), _p(g_pstd),
+                                  _stream()), "loss_bwd")
+    return g_rec, g_mu, g_sigma, g_pmu, g_pstd

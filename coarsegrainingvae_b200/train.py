@@ -28,6 +28,8 @@ def training_loss(outputs, xyz, bond_edge_list, beta, gamma, bond_count=None, no
     GLOBAL count / world, so that the mean over ranks of the local losses (and gradients) equals the single-process
     ``mean()`` over the global batch even when the ranks hold different numbers of atoms / bonds."""
     mu, sigma, pmu, pstd, _, xyz_recon = outputs
+    if xyz_recon.is_cuda and FUSED_LOSS:
+        return _training_loss_fused(outputs, xyz, bond_edge_list, beta, gamma, bond_count, norms)
     if norms is None:
         recon = (xyz_recon - xyz).pow(2).mean()
     else:
@@ -51,6 +53,23 @@ def training_loss(outputs, xyz, bond_edge_list, beta, gamma, bond_count=None, no
             graph = (gen - dat).pow(2).sum() / bond_count.to(gen.dtype).reshape(())
         loss = loss + graph * gamma
     return loss, recon, kl, graph
+
+
+FUSED_LOSS = True   # CUDA tensors: csrc/loss.cu (2 launches forward, 2 backward); False keeps the torch expression above
+
+
+def _training_loss_fused(outputs, xyz, bond_edge_list, beta, gamma, bond_count, norms):
+    """The same loss through functions.TrainingLoss: the bond term walks the receiver CSR of the symmetrised bond list
+    (built with the graph kernels, live count taken from ``bond_count`` in static-capacity mode), so neither direction
+    needs an index_put or a host-visible size."""
+    from . import functions, ops
+    mu, sigma, pmu, pstd, _, xyz_recon = outputs
+    n_atoms = xyz_recon.shape[0]
+    bond_graph = None
+    if gamma != 0.0:
+        bond_graph = ops.build_graph(bond_edge_list, n_atoms, symmetrize=True, n_edges_dev=bond_count)
+    loss, comps = functions.TrainingLoss.apply(bond_graph, float(beta), float(gamma), norms, xyz, xyz_recon, mu, sigma, pmu, pstd)
+    return loss, comps[1], (comps[2] if mu is not None else None), (comps[3] if gamma != 0.0 else None)
 
 
 class FlatGrads(object):

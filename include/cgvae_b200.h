@@ -298,6 +298,37 @@ int cgvae_adam_clip_step(float* p, const float* g, float* m, float* v, int64_t n
                          const float* loss, float loss_scale, float loss_limit, float* skipped, void* ws,
                          size_t ws_bytes, cgvae_stream_t stream);
 
+/* ------------------------------------------------------------------ losses and the VAE latent
+
+ * sigma = 1e-12 + exp(logvar / 2), z = eps * sigma + mu (cgvae.py:445-449,500-507; z == NULL: sigma only) and its
+ * backward g_mu = g_z, g_logvar = (g_sigma + g_z * eps) * 0.5 * (sigma - 1e-12) (g_z / g_sigma / eps / g_mu nullable). */
+int cgvae_vae_latent_fwd(const float* mu, const float* logvar, const float* eps, int64_t n, float* sigma, float* z,
+                         cgvae_stream_t stream);
+int cgvae_vae_latent_bwd(const float* g_z, const float* g_sigma, const float* eps, const float* sigma, int64_t n, float* g_mu,
+                         float* g_logvar, cgvae_stream_t stream);
+/* y = c + exp(x / 2) (prior std, cgvae.py:401: c = 1e-9) ; gx = gy * 0.5 * (y - c) */
+int cgvae_std_logvar_fwd(const float* x, int64_t n, float c, float* y, cgvae_stream_t stream);
+int cgvae_std_logvar_bwd(const float* gy, const float* y, int64_t n, float c, float* gx, cgvae_stream_t stream);
+/* Loss of the training loop, scripts/utils.py:81-141: out4 = (loss, recon, kl, graph) with
+ *   loss = mean((xyz_rec - xyz)^2) + beta * KL(mu, sigma || pmu, pstd) + gamma * mean over bonds of (|rec_a - rec_b|_e - |x_a - x_b|_e)^2,
+ * |.|_e = sqrt(sum^2 + 1e-6); KL keeps the reference's division by pstd (not pstd^2, utils.py:85); pmu == NULL: KL against
+ * the standard normal (utils.py:82-83); mu == NULL: no KL term (PCN).  The bonds come as the receiver CSR of the
+ * SYMMETRISED bond list (cgvae_csr_count / cgvae_csr_fill with symmetrize = 1): every list entry is seen from both atoms,
+ * the forward halves the doubled sum and the backward is a per-atom gather (deterministic; no index_put).  norms
+ * (nullable device float[3]): denominators (atoms, beads, bonds) for data-parallel training (global count / world).
+ * Two launches each way; reductions in a fixed order.  ws: cgvae_loss_ws_bytes(). */
+size_t cgvae_loss_ws_bytes(void);
+int cgvae_loss_fwd(const float* xyz, const float* xyz_rec, int64_t n_atoms, const int32_t* bond_rowptr, const int32_t* bond_col,
+                   const float* mu, const float* sigma, const float* pmu, const float* pstd, int64_t n_beads, int F,
+                   const float* norms, float beta, float gamma, float* out4, void* ws, size_t ws_bytes,
+                   cgvae_stream_t stream);
+int cgvae_loss_bwd(const float* g_loss, const float* xyz, const float* xyz_rec, int64_t n_atoms, const int32_t* bond_rowptr,
+                   const int32_t* bond_col, const float* mu, const float* sigma, const float* pmu, const float* pstd,
+                   int64_t n_beads, int F, const float* norms, float beta, float gamma, float* g_xyz_rec, float* g_mu,
+                   float* g_sigma, float* g_pmu, float* g_pstd, cgvae_stream_t stream);
+/* p[0..n) = value (initial decoder state cgvae.py:90-95 without a library fill) */
+int cgvae_fill(float* p, int64_t n, float value, cgvae_stream_t stream);
+
 /* layout conversion at the module boundary: reference v[N][F][3] <-> planar v[N][3][F] */
 int cgvae_vec_to_planar(const float* v_nf3, int64_t N, int F, float* v_n3f, cgvae_stream_t stream);
 int cgvae_vec_from_planar(const float* v_n3f, int64_t N, int F, float* v_nf3, cgvae_stream_t stream);

@@ -370,7 +370,31 @@ def vec_from_planar(v):
     return v.permute(0, 2, 1).contiguous()
 
 
-_NAMES = ["radius_graph", "edge_orientation", "build_graph", "build_segments", "contraction_graph", "edge_geometry",
+def fill(shape, value, like):
+    return torch.full(shape, float(value), dtype=like.dtype, device=like.device)
+
+
+def vae_latent_fwd(mu, logvar, eps):
+    sigma = 1e-12 + torch.exp(logvar / 2)
+    return (eps * sigma + mu if eps is not None else None), sigma
+
+
+def vae_latent_bwd(g_z, g_sigma, eps, sigma):
+    g_s = torch.zeros_like(sigma) if g_sigma is None else g_sigma.clone()
+    if g_z is not None:
+        g_s = g_s + g_z * eps
+    return g_z, g_s * 0.5 * (sigma - 1e-12)
+
+
+def std_logvar_fwd(x, c):
+    return c + torch.exp(x / 2)
+
+
+def std_logvar_bwd(gy, y, c):
+    return gy * 0.5 * (y - c)
+
+
+_NAMES = ["fill", "vae_latent_fwd", "vae_latent_bwd", "std_logvar_fwd", "std_logvar_bwd", "radius_graph", "edge_orientation", "build_graph", "build_segments", "contraction_graph", "edge_geometry",
           "gemm", "colsum", "message_fwd", "message_bwd", "message9_fwd", "message9_bwd", "update_norm_fwd",
           "update_combine_fwd", "update_combine_bwd", "update_norm_bwd", "segment_reduce_fwd", "segment_reduce_bwd",
           "gather_rows", "lift_fwd", "lift_bwd", "vec_to_planar", "vec_from_planar"]

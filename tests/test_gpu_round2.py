@@ -383,3 +383,92 @@ def test_message_block_api_on_tensor_cores(tag, cls):
         pc.message_block_api(DEV, tag, cls, torch.float32, TOL)
     finally:
         ops.MSG_TC = old
+
+
+# ------------------------------------------------------------------------------------------ fused loss / latent kernels
+
+def _loss_inputs(seed, n_atoms, n_beads, F, n_bonds, dtype, dev):
+    g = torch.Generator().manual_seed(seed)
+    xyz = torch.randn(n_atoms, 3, generator=g) * 2
+    rec = xyz + 0.3 * torch.randn(n_atoms, 3, generator=g)
+    a = torch.randint(0, n_atoms, (n_bonds,), generator=g)
+    b = (a + 1 + torch.randint(0, n_atoms - 1, (n_bonds,), generator=g)) % n_atoms
+    bonds = torch.stack([a, b], 1)
+    mu, pmu = torch.randn(n_beads, F, generator=g), torch.randn(n_beads, F, generator=g)
+    sigma = 0.2 + torch.rand(n_beads, F, generator=g)
+    pstd = 0.2 + torch.rand(n_beads, F, generator=g)
+    cast = lambda t: t.to(dtype).to(dev)
+    return cast(xyz), cast(rec), bonds.to(dev), cast(mu), cast(sigma), cast(pmu), cast(pstd)
+
+
+@pytest.mark.parametrize("mode", ["full", "std_normal_prior", "no_kl", "no_bonds", "dp_norms", "static_bonds", "tiny"])
+def test_fused_training_loss_matches_reference_expression(mode):
+    """csrc/loss.cu (two launches each way) == the loop's loss (scripts/utils.py:81-141) evaluated in float64 by the
+    oracle's expression: value, the three components and the gradients of every input, <= 1e-5."""
+    from coarsegrainingvae_b200 import train
+    n_atoms, n_beads, F, n_bonds = (5, 2, 3, 4) if mode == "tiny" else (3001, 411, 96, 2950)
+    beta, gamma = 0.05, (0.0 if mode == "no_bonds" else 25.0)
+    xyz, rec, bonds, mu, sigma, pmu, pstd = _loss_inputs(3, n_atoms, n_beads, F, n_bonds, torch.float32, DEV)
+    if mode == "std_normal_prior":
+        pmu = pstd = None
+    if mode == "no_kl":
+        mu = sigma = pmu = pstd = None
+    norms = torch.tensor([n_atoms * 1.25, n_beads * 0.75, n_bonds * 1.5], device=DEV) if mode == "dp_norms" else None
+    bond_count = None
+    bonds_in = bonds
+    if mode == "static_bonds":
+        bonds_in = torch.cat([bonds, torch.zeros(200, 2, dtype=torch.int64, device=DEV)])
+        bond_count = torch.tensor(n_bonds, dtype=torch.int64, device=DEV)
+
+    def run(fused, dtype):
+        train.FUSED_LOSS = fused
+        try:
+            leaves = [t.detach().to(dtype).requires_grad_(True) if t is not None else None for t in (rec, mu, sigma, pmu, pstd)]
+            out = (leaves[1], leaves[2], leaves[3], leaves[4], None, leaves[0])
+            loss, r, k, gph = train.training_loss(out, xyz.to(dtype), bonds_in, beta, gamma, bond_count=bond_count,
+                                                  norms=norms.to(dtype) if norms is not None else None)
+            (loss * 1.7).backward()
+            return [loss, r, k, gph], [t.grad if t is not None else None for t in leaves]
+        finally:
+            train.FUSED_LOSS = True
+
+    got_v, got_g = run(True, torch.float32)
+    want_v, want_g = run(False, torch.float64)
+    for name, a, b in zip(("loss", "recon", "kl", "graph"), got_v, want_v):
+        assert (a is None) == (b is None), name
+        if a is not None:
+            assert rel_err(a.detach().cpu().numpy(), b.detach().cpu().numpy()) <= TOL, name
+    for name, a, b in zip(("g_rec", "g_mu", "g_sigma", "g_pmu", "g_pstd"), got_g, want_g):
+        assert (a is None) == (b is None), name
+        if a is not None:
+            assert rel_err(a.cpu().numpy(), b.cpu().numpy()) <= TOL, name
+    # deterministic: fixed-order reductions, per-atom gather backward
+    again_v, again_g = run(True, torch.float32)
+    assert torch.equal(again_v[0], got_v[0]) and torch.equal(again_g[0], got_g[0])
+
+
+def test_vae_latent_and_prior_std_kernels():
+    """(z, sigma) of cgvae.py:445-449,500-507 and the prior std of cgvae.py:401: values and gradients vs float64 torch."""
+    from coarsegrainingvae_b200 import functions as fn
+    g = torch.Generator().manual_seed(0)
+    mu, lv, eps = (torch.randn(777, 36, generator=g).to(DEV) for _ in range(3))
+    a, b = mu.clone().requires_grad_(True), lv.clone().requires_grad_(True)
+    z, sigma = fn.VAELatent.apply(a, b, eps)
+    w1, w2 = torch.randn_like(z), torch.randn_like(z)
+    ((z * w1).sum() + (sigma * w2).sum()).backward()
+    a64, b64 = mu.double().requires_grad_(True), lv.double().requires_grad_(True)
+    s64 = 1e-12 + torch.exp(b64 / 2)
+    z64 = eps.double() * s64 + a64
+    ((z64 * w1.double()).sum() + (s64 * w2.double()).sum()).backward()
+    for got, want in ((z, z64), (sigma, s64), (a.grad, a64.grad), (b.grad, b64.grad)):
+        assert rel_err(got.detach().cpu().numpy(), want.detach().cpu().numpy()) <= 1e-6
+    x = lv.clone().requires_grad_(True)
+    y = fn.StdLogvar.apply(x, 1e-9)
+    (y * w1).sum().backward()
+    x64 = lv.double().requires_grad_(True)
+    y64 = 1e-9 + torch.exp(x64 / 2)
+    (y64 * w1.double()).sum().backward()
+    assert rel_err(y.detach().cpu().numpy(), y64.detach().cpu().numpy()) <= 1e-6
+    assert rel_err(x.grad.cpu().numpy(), x64.grad.cpu().numpy()) <= 1e-6
+    f = ops.fill((1000, 7), 1.0, mu)
+    assert f.shape == (1000, 7) and bool((f == 1.0).all())
