@@ -269,7 +269,14 @@ def test_pcn_step_reduced_protein_batch():
     oloss = (oout[5] - oout[4]).pow(2).mean()
     oloss.backward()
     assert rel_err(out[5], oout[5]) < TOL and rel_err(loss, oloss) < TOL
-    pc._check_grads(model, P, TOL)
+    # gradients against the float64 evaluation of the same oracle (ground truth): nine layers deep, the v_mat gradients go
+    # through d sqrt(sum(Vv^2) + 1e-10) / dVv and two fp32 implementations differ from EACH OTHER by up to 1.4e-5 there
+    # while each is within 1e-5 (or 10x the fp32 oracle's own error) of the truth -- see parity_cases._check_grads
+    P64 = {k: v.detach().double().requires_grad_(v.dtype.is_floating_point) for k, v in P.items()}
+    b64 = {k: (v.double() if torch.is_tensor(v) and v.dtype.is_floating_point else v) for k, v in batch.items()}
+    o64 = orc.pcn_forward(P64, spec, b64)
+    (o64[5] - o64[4]).pow(2).mean().backward()
+    pc._check_grads(model, P, TOL, P64=P64)
 
 
 def _layer_inputs(n, cutoff, F, R, seed):
