@@ -451,6 +451,46 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X
   }
 }
 
+// tall matrices (bias gradients over 1e4 .. 1e5 node rows): the rows are split over a cluster (1, S, 1) and 32 row-lanes per
+// CTA with four loads in flight per thread; CTA partials are combined by rank 0 through DSMEM in rank order (deterministic)
+__global__ void __launch_bounds__(1024) colsum_tall_kernel(const float* __restrict__ X, int64_t ldx, int64_t M, int64_t N,
+                                                           float* __restrict__ out) {
+  CGVAE_KERNEL_PROLOGUE();
+  namespace cgx = cooperative_groups;
+  cgx::cluster_group cluster = cgx::this_cluster();
+  __shared__ float red[32][33];
+  __shared__ float part[32];
+  const int S = (int)gridDim.y, z = (int)blockIdx.y;
+  const int64_t rows_per = (M + S - 1) / S, m_lo = z * rows_per, m_hi = min(M, m_lo + rows_per);
+  const int64_t n = (int64_t)blockIdx.x * 32 + threadIdx.x;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (n < N) {
+    int64_t m = m_lo + threadIdx.y;
+    for (; m + 96 < m_hi; m += 128) {
+      s0 += X[m * ldx + n];
+      s1 += X[(m + 32) * ldx + n];
+      s2 += X[(m + 64) * ldx + n];
+      s3 += X[(m + 96) * ldx + n];
+    }
+    for (; m < m_hi; m += 32) s0 += X[m * ldx + n];
+  }
+  red[threadIdx.y][threadIdx.x] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (threadIdx.y == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int r = 0; r < 32; ++r) t += red[r][threadIdx.x];
+    part[threadIdx.x] = t;
+  }
+  cluster.sync();
+  if (z == 0 && threadIdx.y == 0 && n < N) {
+    float t = 0.f;
+    for (int rk = 0; rk < S; ++rk) t += cluster.map_shared_rank(part, rk)[threadIdx.x];
+    out[n] = t;
+  }
+  cluster.sync();
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // 3xTF32 warp-MMA kernel for mid-size problems (64 <= M: the 350-row atom-level layers of chignolin, the weight
 // gradients of the protein configs).  The 64x64 SIMT tile above is bound by shared-memory loads (2 LDS.128 per 16 FMA:
@@ -766,7 +806,7 @@ static int launch_gemm(int form, const float* A, int64_t lda, const float* B, in
 namespace cgvae {
 int launch_gemm_tcgen05(int form, const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t M,
                         int64_t N, int64_t K, const float* bias, int act, float* z_out, const float* z_in, int dact,
-                        const float* add, cudaStream_t st);
+                        const float* add, float* ws, size_t ws_bytes, cudaStream_t st);
 int launch_gemm_stream(int form, const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t M,
                        int64_t N, int64_t K, const float* bias, int act, float* z_out, const float* z_in, int dact,
                        const float* add, cudaStream_t st);
@@ -807,8 +847,16 @@ int cgvae_gemm(int form, const float* A, int64_t lda, const float* B, int64_t ld
   Epilogue ep{bias, act, z_out, z_in, dact, add};
   cudaStream_t st = (cudaStream_t)stream;
   // large node GEMMs: 3xTF32 on the tcgen05 tensor cores (gemm_tc.cu); everything else: fp32 SIMT tiles below
-  if (launch_gemm_tcgen05(form, A, lda, B, ldb, C, ldc, M, N, K, bias, act, z_out, z_in, dact, add, st))
-    return launched("gemm_tcgen05");
+  if (int tc_rc = launch_gemm_tcgen05(form, A, lda, B, ldb, C, ldc, M, N, K, bias, act, z_out, z_in, dact, add,
+                                      reinterpret_cast<float*>(ws), ws_bytes, st)) {
+    if (int rc = launched("gemm_tcgen05")) return rc;
+    if (tc_rc > 1) {     // several cluster groups: add their partial matrices in group order, then the epilogue
+      launch_kernel(splitk_reduce_kernel, dim3((unsigned)ceil_div(M * N, 256)), dim3(256), 0, st, (const float*)ws, tc_rc - 1, M, N, C,
+                    ldc, ep);
+      return launched("gemm_splitk_reduce");
+    }
+    return 0;
+  }
   // M <= 48 rows (decoder graphs): weight-streaming kernels (gemm_stream.cu)
   if (launch_gemm_stream(form, A, lda, B, ldb, C, ldc, M, N, K, bias, act, z_out, z_in, dact, add, st))
     return launched("gemm_stream");
@@ -875,6 +923,26 @@ int cgvae_gemm(int form, const float* A, int64_t lda, const float* B, int64_t ld
 int cgvae_colsum(const float* X, int64_t ldx, int64_t M, int64_t N, float* out, cgvae_stream_t stream) {
   if (N == 0) return 0;
   CGVAE_REQUIRE(X && out, "colsum: null pointer");
+  if (M >= 4096) {
+    const int blocks = (int)ceil_div(N, 32);
+    int S = (int)std::min<int64_t>(8, std::max<int64_t>(1, (2 * kNumSM) / blocks));
+    while (S & (S - 1)) S &= S - 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)blocks, (unsigned)S, 1);
+    cfg.blockDim = dim3(32, 32, 1);
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = (unsigned)S;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    (void)cudaLaunchKernelEx(&cfg, colsum_tall_kernel, X, ldx, M, N, out);
+    return launched("colsum_tall");
+  }
   launch_kernel(colsum_kernel, dim3((unsigned)ceil_div(N, 32)), dim3(dim3(32, 8)), 0, (cudaStream_t)stream, X, ldx, M, N, out);
   return launched("colsum");
 }

@@ -110,6 +110,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 
 // 32 columns of the result for this thread's row: small accumulator + the big accumulators that were written, in order
 __device__ __forceinline__ void load_acc(uint32_t taddr, int nbig, float (&out)[32]) {
+  if (nbig == 0) {                       // empty K-slice
+#pragma unroll
+    for (int j = 0; j < 32; ++j) out[j] = 0.f;
+    return;
+  }
   uint32_t r[32], t[32];
   tmem_ld32(taddr, r);
   tmem_ld32(taddr + BN, t);
@@ -129,7 +134,7 @@ template <bool A_KC, bool B_KC>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                  const __grid_constant__ CUtensorMap map_b, float* __restrict__ C,
                                                                  int64_t ldc, int64_t M, int64_t N, int64_t K, int kt_per_split, Ep ep,
-                                                                 int split_mode) {
+                                                                 int split_mode, int cluster_size, float* __restrict__ partial) {
   CGVAE_KERNEL_PROLOGUE();
   extern __shared__ __align__(1024) char smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte aligned bases: add the (runtime) pad to the extern array, not to an integer
@@ -143,9 +148,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t m0 = (int64_t)blockIdx.y * BM, n0 = (int64_t)blockIdx.x * BN;
   const int num_kt = (int)((K + BK - 1) / BK);
-  const int S = (int)gridDim.z, z = (int)blockIdx.z;
-  const int kt0 = z * kt_per_split, kt1 = min(num_kt, kt0 + kt_per_split);   // non-empty by construction of the grid
-  const int nkt = kt1 - kt0;
+  // gridDim.z = groups x cluster_size K-slices: a cluster reduces its slices through DSMEM; with more than one group
+  // (reductions over > 8 x MAX_KT_PER_CTA k-steps) every group writes a raw partial matrix and splitk_reduce_kernel
+  // (gemm.cu) adds the groups in order and applies the epilogue
+  const int S = cluster_size, z = (int)blockIdx.z % cluster_size, group = (int)blockIdx.z / cluster_size;
+  const int kt0 = (int)blockIdx.z * kt_per_split, kt1 = min(num_kt, kt0 + kt_per_split);
+  const int nkt = max(0, kt1 - kt0);        // trailing slices of the last group may be empty: they park zeros
+  if (partial != nullptr) {
+    C = partial + (int64_t)group * M * N;
+    ldc = N;
+  }
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -255,7 +267,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
 
   // ---------------- epilogue ----------------
   // warp w < 8 reads TMEM lanes 32*(w%4)..+31 (= output rows) and the column half (w/4)
-  if (warp < NUM_SPLIT_WARPS) {
+  if (warp < NUM_SPLIT_WARPS && nkt > 0) {
     mbar_wait(acc_bar, 0);
     tc_fence_after();
   }
@@ -373,7 +385,7 @@ bool tcgen05_enabled() {
 // returns 1 when the problem was launched on the tensor-core path, 0 when the caller should use the SIMT kernel
 int launch_gemm_tcgen05(int form, const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t M,
                         int64_t N, int64_t K, const float* bias, int act, float* z_out, const float* z_in, int dact,
-                        const float* add, cudaStream_t st) {
+                        const float* add, float* ws, size_t ws_bytes, cudaStream_t st) {
   if (!tcgen05_enabled()) return 0;
   static const int min_m = [] { const char* e = getenv("CGVAE_TC_MIN_M"); return e ? atoi(e) : 64; }();
   static const int split_mode = [] { const char* e = getenv("CGVAE_TC_SPLIT"); return e ? atoi(e) : 0; }();
@@ -388,16 +400,24 @@ int launch_gemm_tcgen05(int form, const float* A, int64_t lda, const float* B, i
   int S = (int)std::min<int64_t>(8, std::max<int64_t>(1, kNumSM / tiles));
   S = std::min(S, std::max(1, num_kt / 2));
   S = std::max(S, (int)ceil_div(num_kt, tc::MAX_KT_PER_CTA));
-  if (S > 8) return 0;                       // reductions over > 24 576 rows stay on the SIMT kernel (two-level fp32 sums)
-  const int kps = (int)ceil_div(num_kt, S);
-  S = (int)ceil_div(num_kt, kps);
+  int groups = 1;
+  if (S > 8) {
+    // longer reductions (weight gradients over 1e4 .. 1e5 node rows): several clusters, one raw partial matrix each
+    groups = (int)ceil_div(S, 8);
+    if (ws == nullptr || (size_t)groups * (size_t)(M * N) * sizeof(float) > ws_bytes) return 0;
+    S = 8;
+  }
+  const int kps = (int)ceil_div(num_kt, S * groups);
+  if (groups == 1) S = (int)ceil_div(num_kt, kps);
   CUtensorMap map_a, map_b;
   // K-contiguous operand: inner = K, outer = rows, box [128 rows][32 k]; MN-contiguous: inner = rows, outer = K, box [32 k][32 mn]
   if (!(a_kc ? tc::encode_map(&map_a, A, K, M, lda, tc::BM, true) : tc::encode_map(&map_a, A, M, K, lda, tc::BK, false))) return 0;
   if (!(b_kc ? tc::encode_map(&map_b, B, K, N, ldb, tc::BN, true) : tc::encode_map(&map_b, B, N, K, ldb, tc::BK, false))) return 0;
   tc::Ep ep{bias, act, z_out, z_in, dact, add};
+  if (groups > 1) ep = tc::Ep{nullptr, 0, nullptr, nullptr, 0, nullptr};
+  float* partial = groups > 1 ? ws : nullptr;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)ceil_div(N, tc::BN), (unsigned)ceil_div(M, tc::BM), (unsigned)S);
+  cfg.gridDim = dim3((unsigned)ceil_div(N, tc::BN), (unsigned)ceil_div(M, tc::BM), (unsigned)(S * groups));
   cfg.blockDim = dim3(tc::NUM_THREADS);
   cfg.dynamicSmemBytes = tc::SMEM_BYTES;
   cfg.stream = st;
@@ -416,12 +436,12 @@ int launch_gemm_tcgen05(int form, const float* A, int64_t lda, const float* B, i
       cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
       attr_done[idx] = true;
     }
-    (void)cudaLaunchKernelEx(&cfg, kernel, map_a, map_b, C, ldc, M, N, K, kps, ep, split_mode);
+    (void)cudaLaunchKernelEx(&cfg, kernel, map_a, map_b, C, ldc, M, N, K, kps, ep, split_mode, S, partial);
   };
   if (a_kc && b_kc) go(tc::gemm_tc_kernel<true, true>, 0);
   else if (a_kc) go(tc::gemm_tc_kernel<true, false>, 1);
   else go(tc::gemm_tc_kernel<false, false>, 2);
-  return 1;
+  return groups > 1 ? 1 + groups : 1;          // > 1: the caller reduces `groups` partial matrices in ws
 }
 
 }  // namespace cgvae

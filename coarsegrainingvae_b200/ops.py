@@ -409,7 +409,7 @@ def gemm(form, A, B, M, N, K, bias=None, act=0, z_out=False, z_in=None, dact=0, 
     tiles = ((M + 63) // 64) * ((N + 63) // 64) if M > 32 else ((N + 31) // 32)
     st = _stream()
     ws = tk = None
-    if tiles < 148 and K >= 512:
+    if (tiles < 148 and K >= 512) or (K > 24576 and M >= 64):      # split-K workspace (SIMT tiles; tcgen05 group partials)
         ws = torch.empty(_SPLITK_WS_BYTES, dtype=torch.uint8, device=dev)
         tk = _tickets(dev, st)
     t0 = TIMER.begin("gemm") if TIMER is not None else None
@@ -417,7 +417,7 @@ def gemm(form, A, B, M, N, K, bias=None, act=0, z_out=False, z_in=None, dact=0, 
                               _p(z_in), dact, _p(add), _p(ws), _SPLITK_WS_BYTES if ws is not None else 0, _p(tk),
                               _N_TICKETS if tk is not None else 0, st), "gemm")
     if t0 is not None:
-        meta = dict(form=form, M=M, N=N, K=K)
+        meta = dict(form=form, M=M, N=N, K=K, lda=A.stride(0), ldb=B.stride(0))
         if TIMER.keep_operands:
             meta.update(A=A, B=B, bias=bias, act=act, z_in=z_in, dact=dact, add=add)
         TIMER.end("gemm", t0, meta)

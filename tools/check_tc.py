@@ -49,3 +49,12 @@ for (M, N, K) in shapes:
     fl = 2.0 * M * N * K / 1e6
     print("M%6d N%5d K%5d  err NT %.2e NN %.2e TN %.2e | NT %8.1f us %6.1f TF  NN %8.1f us %6.1f TF  TN %8.1f us %6.1f TF" %
           (M, N, K, e_nt, e_nn, e_tn, us_nt, fl / us_nt, us_nn, fl / us_nn, us_tn, fl / us_tn), flush=True)
+if "--long" in sys.argv:
+    for (M, N, K) in [(512, 512, 48000), (1536, 512, 16000), (600, 1800, 128000)]:
+        g = torch.Generator().manual_seed(1)
+        X = torch.randn(K, M, generator=g).to(dev); Y = torch.randn(K, N, generator=g).to(dev)
+        ref = X.double().cpu().t() @ Y.double().cpu()
+        got = ops.gemm(ops.GEMM_TN, X, Y, M, N, K)
+        o = torch.empty(M, N, device=dev)
+        us = graph_time(lambda i: ops.gemm(ops.GEMM_TN, X, Y, M, N, K, out=o), reps=5)
+        print("TN M%5d N%5d K%7d err %.2e  %8.1f us %6.1f TF" % (M, N, K, rel(got, ref), us, 2.0 * M * N * K / us / 1e6), flush=True)
