@@ -418,33 +418,31 @@ def _extra_c4(dev, world, rank):
     import torch
     from coarsegrainingvae_b200 import ops, synthetic
     from coarsegrainingvae_b200.factory import build_pcn
-    from coarsegrainingvae_b200.train import TrainStep
     cfg = dict(synthetic.CONFIGS["c4_protein"])
     per_rank = max(1, cfg["batch"] // world)
     rad = lambda xyz, c: ops.radius_graph(torch.as_tensor(xyz, dtype=torch.float32, device=dev), c).cpu().numpy()
     raw = synthetic.pcn_batch(cfg, rank, rad, n_proteins=per_rank)
-    batch = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in raw.items()}
     torch.manual_seed(123)
     model = build_pcn(cfg["n_basis"], cfg["n_rbf"], cfg["cg_cutoff"], cfg["dec_nconv"]).to(dev)
 
-    class _PCNStep(TrainStep):
-        def _loss(self, b, eps):
-            out = self.model(b)
-            from coarsegrainingvae_b200.train import training_loss
-            return training_loss(out, out[4], b["bond_edge_list"], 0.0, self.gamma, None, b.get("dp_norms"))[0]
-
-    tr = _PCNStep(model, 0.0, 1.0, lr=1e-4, loss_limit=None)
+    from coarsegrainingvae_b200.train import GraphedTrainStep, PCNTrainStep, to_static_pcn_batch
+    caps = {k: int(raw[k].shape[0]) + 64 for k in ("CG_nbr_list", "bond_edge_list", "dihe_idxs", "ca_idx")}
+    batch = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in to_static_pcn_batch(raw, caps).items()}
+    # loss = MSE + gamma * bond-graph term + kappa * dihedral term (scripts/pcn_utils.py:160-183), skip guard on the device
+    tr = PCNTrainStep(model, 1.0, 0.1, lr=1e-4, capturable=True)
     tr.prepare(batch, None)
-    ms = _timeit(lambda: tr.step(batch, None), 2, 4)
+    graphed = GraphedTrainStep(tr, batch, None)
+    ms = _timeit(lambda: graphed.step(batch), 2, 4)
     if world > 1:
         import torch.distributed as dist
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t)
     out = {"what": "PCN train step (EquivariantDecoder cross_flag=True, F=%d, 9 layers), %d proteins x %d atoms per rank, global batch %d, "
-                   "eager launches" % (cfg["n_basis"], per_rank, cfg["n_res"] * cfg["atoms_per_res"], per_rank * world),
+                   "one CUDA graph per step (PCNTrainStep, static-capacity batch; loss = MSE + bond + 0.1 x dihedral)" % (cfg["n_basis"], per_rank, cfg["n_res"] * cfg["atoms_per_res"], per_rank * world),
            "ms_per_step": ms, "conformations_per_s": per_rank * world / ms * 1e3, "scaling": "strong (global batch 64)",
            "max_memory_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30}
+    graphed = None
     tr.flat.release()
     return out
 

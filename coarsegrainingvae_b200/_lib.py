@@ -67,6 +67,9 @@ SIGNATURES = {
     "cgvae_adam_ws_bytes": (_SZ, []),
     "cgvae_adam_clip_step": (_INT, [_P, _P, _P, _P, _I64, _F32, _F32, _F32, _F32, _F32, _F32, _P, _P, _P, _F32, _F32, _P,
                                     _P, _SZ, _P]),
+    "cgvae_dihedral_loss_fwd": (_INT, [_P, _P, _P, _I64, _P, _P, _P, _P, _P, _SZ, _P]),
+    "cgvae_dihedral_loss_bwd": (_INT, [_P, _P, _P, _P, _I64, _I64, _P, _P, _P, _P]),
+    "cgvae_pin_mask": (_INT, [_P, _I64, _P, _I64, _P, _SZ, _P]),
     "cgvae_vae_latent_fwd": (_INT, [_P, _P, _P, _I64, _P, _P, _P]),
     "cgvae_vae_latent_bwd": (_INT, [_P, _P, _P, _P, _I64, _P, _P, _P]),
     "cgvae_std_logvar_fwd": (_INT, [_P, _I64, _F32, _P, _P]),

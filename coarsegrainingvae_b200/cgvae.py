@@ -311,24 +311,25 @@ class PCN(nn.Module):
         mapping = batch['cg_map']
         nbr_list = batch['bond_edge_list']
         CG_nbr_list = batch['CG_nbr_list']
-        num_CGs = [len(seq) for seq in batch['seq']]
+        num_CGs = [len(seq) for seq in batch['seq']] if 'seq' in batch else None     # unused by the decoder
         return cg_z, xyz, cg_xyz, nbr_list, CG_nbr_list, mapping, num_CGs
 
     def CG2ChannelIdx(self, CG_mapping):
         n_beads = int(CG_mapping.max().item()) + 1 if CG_mapping.numel() else 0
         return ops.build_segments(CG_mapping, n_beads).rank
 
-    def decoder(self, cg_xyz, CG_nbr_list, S_I, ca_idx, mapping, num_CGs, graphs=None):
+    def decoder(self, cg_xyz, CG_nbr_list, S_I, ca_idx, mapping, num_CGs, graphs=None, ca_count=None):
         g = graphs if graphs is not None else BatchGraphs()
         if g.seg is None:
             g.seg = ops.build_segments(mapping, cg_xyz.shape[0])
         cg_s, cg_v = self.equivaraintconv(cg_xyz, CG_nbr_list, mapping, S_I, graphs=g, planar=True)
         n_atoms = mapping.shape[0]
         pin = None
-        # cgvae.py:569-571: C-alpha atoms are pinned to their bead unless the index list overruns the atoms
-        if ca_idx.numel() and int(ca_idx[-1].item()) < n_atoms:
-            pin = torch.zeros(n_atoms, dtype=torch.uint8, device=mapping.device)
-            pin[ca_idx] = 1
+        # cgvae.py:569-571: C-alpha atoms are pinned to their bead unless the index list overruns the atoms.  The
+        # predicate (ca_idx[-1] < n_atoms) is evaluated on the device: an all-zero mask == no re-anchoring, and no host
+        # read stands between the step and a CUDA-graph capture.  ca_count: live entries of a zero-padded static list.
+        if ca_idx.numel():
+            pin = ops.pin_mask(ca_idx, n_atoms, ca_count)
         return fn.Lift.apply(g.seg, 2 if pin is not None else 0, pin, cg_v, cg_xyz.contiguous())
 
     def forward(self, batch):
@@ -336,6 +337,7 @@ class PCN(nn.Module):
         S_I = _embed(self.embedding, cg_z)
         xyz_recon = self.decoder(cg_xyz.contiguous(), CG_nbr_list, S_I, batch['ca_idx'], mapping, num_CGs,
                                  graphs=batch.get('_graphs') or BatchGraphs(None, batch.get('CG_nbr_count'), True,
-                                                                            batch.get('CG_nbr_symmetrize', True)))
+                                                                            batch.get('CG_nbr_symmetrize', True)),
+                                 ca_count=batch.get('ca_count'))
         ops.check_device_errors(xyz_recon.device)
         return None, None, None, None, xyz, xyz_recon

@@ -215,6 +215,108 @@ __global__ void __launch_bounds__(256) fill_kernel(float* __restrict__ p, int64_
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = value;
 }
 
+// ---- dihedral loss of the PCN loop (scripts/pcn_utils.py:114-132,178-180) ------------------------------------------------------
+// theta(x; i0..i3) = atan(p1 / (p2 + EPS)),  b1 = x1 - x0, b2 = x2 - x1, b3 = x3 - x2, c1 = b2 x b3, c2 = b1 x b2,
+// p1 = (b1 . c1) * sqrt(b2 . b2 + EPS),  p2 = c1 . c2  -- the reference's formula, EPS quirks included (arctan, not atan2).
+struct Vec3 {
+  float x, y, z;
+};
+__device__ __forceinline__ Vec3 v3(const float* p) { return Vec3{p[0], p[1], p[2]}; }
+__device__ __forceinline__ Vec3 operator-(Vec3 a, Vec3 b) { return Vec3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ Vec3 operator+(Vec3 a, Vec3 b) { return Vec3{a.x + b.x, a.y + b.y, a.z + b.z}; }
+__device__ __forceinline__ Vec3 operator*(float s, Vec3 a) { return Vec3{s * a.x, s * a.y, s * a.z}; }
+__device__ __forceinline__ float dot3(Vec3 a, Vec3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ Vec3 cross3(Vec3 a, Vec3 b) { return Vec3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+
+// angle and (optionally) its gradient with respect to the four positions
+__device__ __forceinline__ float dihedral(const float* __restrict__ xyz, const int64_t* __restrict__ q, Vec3* g) {
+  constexpr float EPS = 1e-6f;
+  const Vec3 x0 = v3(xyz + 3 * q[0]), x1 = v3(xyz + 3 * q[1]), x2 = v3(xyz + 3 * q[2]), x3 = v3(xyz + 3 * q[3]);
+  const Vec3 b1 = x1 - x0, b2 = x2 - x1, b3 = x3 - x2;
+  const Vec3 c1 = cross3(b2, b3), c2 = cross3(b1, b2);
+  const float u = dot3(b1, c1), nrm = sqrtf(dot3(b2, b2) + EPS);
+  const float p1 = u * nrm, p2 = dot3(c1, c2), den = p2 + EPS, t = p1 / den;
+  if (g != nullptr) {
+    const float dt = 1.0f / (1.0f + t * t);
+    const float g_p1 = dt / den, g_p2 = -dt * p1 / (den * den);
+    // p1 = u * nrm ; u = b1 . c1 ; nrm = sqrt(b2 . b2 + EPS) ; p2 = c1 . c2
+    const float g_u = g_p1 * nrm, g_n = g_p1 * u;
+    Vec3 g_b1 = g_u * c1, g_c1 = g_u * b1 + g_p2 * c2, g_c2 = g_p2 * c1;
+    Vec3 g_b2 = (g_n / nrm) * b2;
+    // c1 = b2 x b3 : g_b2 += b3 x g_c1, g_b3 = g_c1 x b2 ;  c2 = b1 x b2 : g_b1 += b2 x g_c2, g_b2 += g_c2 x b1
+    g_b2 = g_b2 + cross3(b3, g_c1) + cross3(g_c2, b1);
+    const Vec3 g_b3 = cross3(g_c1, b2);
+    g_b1 = g_b1 + cross3(b2, g_c2);
+    g[0] = -1.0f * g_b1;
+    g[1] = g_b1 - g_b2;
+    g[2] = g_b2 - g_b3;
+    g[3] = g_b3;
+  }
+  return atanf(t);
+}
+
+// per dihedral: diff = theta(rec) - theta(xyz); contrib[d][slot] = 2 diff dtheta/dx_slot (unscaled); block partial of diff^2
+__global__ void __launch_bounds__(256) dihedral_fwd_kernel(const float* __restrict__ xyz, const float* __restrict__ rec,
+                                                           const int64_t* __restrict__ idx, int64_t n_dihe, const int64_t* __restrict__ n_live,
+                                                           float* __restrict__ contrib, float* __restrict__ partial) {
+  CGVAE_KERNEL_PROLOGUE();
+  __shared__ float red[8];
+  const int64_t n = n_live ? min(*n_live, n_dihe) : n_dihe;
+  float acc = 0.f;
+  for (int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; d < n_dihe; d += (int64_t)gridDim.x * blockDim.x) {
+    Vec3 g[4] = {Vec3{0.f, 0.f, 0.f}, Vec3{0.f, 0.f, 0.f}, Vec3{0.f, 0.f, 0.f}, Vec3{0.f, 0.f, 0.f}};
+    if (d < n) {
+      const float diff = dihedral(rec, idx + 4 * d, g) - dihedral(xyz, idx + 4 * d, nullptr);
+      acc += diff * diff;
+#pragma unroll
+      for (int s = 0; s < 4; ++s) g[s] = (2.0f * diff) * g[s];
+    }
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      contrib[(d * 4 + s) * 3 + 0] = g[s].x;
+      contrib[(d * 4 + s) * 3 + 1] = g[s].y;
+      contrib[(d * 4 + s) * 3 + 2] = g[s].z;
+    }
+  }
+  acc = block_sum_256(acc, red);
+  if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+// out[0] = mean over the live dihedrals (fixed-order sum of the block partials)
+__global__ void __launch_bounds__(256) dihedral_final_kernel(const float* __restrict__ partial, int nb, int64_t n_dihe,
+                                                             const int64_t* __restrict__ n_live, const float* __restrict__ norm,
+                                                             float* __restrict__ out) {
+  CGVAE_KERNEL_PROLOGUE();
+  __shared__ float red[8];
+  float v = 0.f;
+  for (int i = threadIdx.x; i < nb; i += 256) v += partial[i];
+  v = block_sum_256(v, red);
+  if (threadIdx.x == 0) {
+    const float n = norm ? *norm : (float)(n_live ? min(*n_live, n_dihe) : n_dihe);
+    out[0] = v / fmaxf(n, 1.0f);
+  }
+}
+// per atom: g_rec[a] = g_loss / n * sum over the (dihedral, slot) entries that name atom a (CSR of the flattened index list)
+__global__ void __launch_bounds__(256) dihedral_bwd_kernel(const float* __restrict__ g_loss, const float* __restrict__ contrib,
+                                                           const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                                           int64_t n_atoms, int64_t n_dihe, const int64_t* __restrict__ n_live,
+                                                           const float* __restrict__ norm, float* __restrict__ g_rec) {
+  CGVAE_KERNEL_PROLOGUE();
+  const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n_atoms) return;
+  const float n = norm ? *norm : (float)(n_live ? min(*n_live, n_dihe) : n_dihe);
+  const float scale = g_loss[0] / fmaxf(n, 1.0f);
+  float gx = 0.f, gy = 0.f, gz = 0.f;
+  for (int j = rowptr[a]; j < rowptr[a + 1]; ++j) {
+    const int64_t e = col[j];
+    gx += contrib[e * 3 + 0];
+    gy += contrib[e * 3 + 1];
+    gz += contrib[e * 3 + 2];
+  }
+  g_rec[a * 3 + 0] = scale * gx;
+  g_rec[a * 3 + 1] = scale * gy;
+  g_rec[a * 3 + 2] = scale * gz;
+}
+
 }  // namespace cgvae
 
 using namespace cgvae;
@@ -293,6 +395,29 @@ int cgvae_loss_bwd(const float* g_loss, const float* xyz, const float* xyz_rec, 
     return launched("loss_bwd_kl");
   }
   return 0;
+}
+
+
+/* Dihedral loss (scripts/pcn_utils.py:114-132,178-180): out[0] = mean_d (theta(rec; idx[d]) - theta(xyz; idx[d]))^2.
+ * contrib [n_dihe][4][3]: unscaled per-(dihedral, slot) gradients kept for the backward; ws: 256 floats. */
+int cgvae_dihedral_loss_fwd(const float* xyz, const float* xyz_rec, const int64_t* idx, int64_t n_dihe, const int64_t* n_live,
+                            const float* norm, float* contrib, float* out, void* ws, size_t ws_bytes, cgvae_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  CGVAE_REQUIRE(out && ws && ws_bytes >= sizeof(float) * kLossBlocks, "dihedral_loss_fwd: workspace too small");
+  CGVAE_REQUIRE(n_dihe == 0 || (xyz && xyz_rec && idx && contrib), "dihedral_loss_fwd: null pointer");
+  const int nb = (int)std::max<int64_t>(1, std::min<int64_t>(kLossBlocks, ceil_div(n_dihe, 256)));
+  float* partial = reinterpret_cast<float*>(ws);
+  launch_kernel(dihedral_fwd_kernel, dim3(nb), dim3(256), 0, st, xyz, xyz_rec, idx, n_dihe, n_live, contrib, partial);
+  launch_kernel(dihedral_final_kernel, dim3(1), dim3(256), 0, st, (const float*)partial, nb, n_dihe, n_live, norm, out);
+  return launched("dihedral_loss_fwd");
+}
+int cgvae_dihedral_loss_bwd(const float* g_loss, const float* contrib, const int32_t* rowptr, const int32_t* col, int64_t n_atoms,
+                            int64_t n_dihe, const int64_t* n_live, const float* norm, float* g_xyz_rec, cgvae_stream_t stream) {
+  if (n_atoms == 0) return 0;
+  CGVAE_REQUIRE(g_loss && rowptr && g_xyz_rec && (n_dihe == 0 || (contrib && col)), "dihedral_loss_bwd: null pointer");
+  launch_kernel(dihedral_bwd_kernel, dim3((unsigned)ceil_div(n_atoms, 256)), dim3(256), 0, (cudaStream_t)stream, g_loss, contrib, rowptr,
+                col, n_atoms, n_dihe, n_live, norm, g_xyz_rec);
+  return launched("dihedral_loss_bwd");
 }
 
 }  // extern "C"

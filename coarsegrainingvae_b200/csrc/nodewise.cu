@@ -201,11 +201,40 @@ __global__ void __launch_bounds__(128) lift_bwd_kernel(const float* __restrict__
   }
 }
 
+// PCN C-alpha pin mask (cgvae.py:569-571: `if ca_idx[-1] < n_atoms: xyz_rel[ca_idx] = 0`) with the predicate evaluated on
+// the device: no host read of ca_idx[-1], so the PCN step can be captured in a CUDA graph
+__global__ void __launch_bounds__(256) pin_mask_kernel(const int64_t* __restrict__ idx, int64_t n_idx, const int64_t* __restrict__ n_live,
+                                                       int64_t n_atoms, uint8_t* __restrict__ pin, int32_t* __restrict__ err) {
+  CGVAE_KERNEL_PROLOGUE();
+  const int64_t n = n_live ? min(*n_live, n_idx) : n_idx;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || n <= 0) return;
+  if (idx[n - 1] >= n_atoms) return;                 // the reference skips the re-anchoring altogether
+  const int64_t a = idx[i];
+  if (a < 0 || a >= n_atoms) {
+    raise_flag(err, CGVAE_ERR_NODE_INDEX);
+    return;
+  }
+  pin[a] = 1;
+}
+
 }  // namespace cgvae
 
 using namespace cgvae;
 
 extern "C" {
+
+int cgvae_pin_mask(const int64_t* idx, int64_t n_idx, const int64_t* n_live, int64_t n_atoms, uint8_t* pin, size_t pin_bytes,
+                   cgvae_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_atoms == 0) return 0;
+  CGVAE_REQUIRE(pin && pin_bytes >= (size_t)n_atoms && pin_bytes % 4 == 0, "pin_mask: pin buffer must hold n_atoms bytes, padded to 4");
+  CGVAE_ZERO(pin, pin_bytes, st);
+  if (n_idx == 0) return 0;
+  CGVAE_REQUIRE(idx, "pin_mask: null index list");
+  launch_kernel(pin_mask_kernel, dim3((unsigned)ceil_div(n_idx, 256)), dim3(256), 0, st, idx, n_idx, n_live, n_atoms, pin, err_flags());
+  return launched("pin_mask");
+}
 
 int cgvae_update_norm_fwd(const float* s, const float* Vv, int64_t N, int F, float* x, cgvae_stream_t stream) {
   if (N == 0) return 0;

@@ -323,3 +323,28 @@ class TrainingLoss(Function):
         g_rec, g_mu, g_sigma, g_pmu, g_pstd = ops.loss_bwd(g, xyz, xyz_rec, ctx.bond_graph, mu, sigma, pmu, pstd, ctx.norms,
                                                            ctx.beta, ctx.gamma)
         return None, None, None, None, None, g_rec, g_mu, g_sigma, g_pmu, g_pstd
+
+
+class DihedralLoss(Function):
+    """mean_d (theta(xyz_rec; idx_d) - theta(xyz; idx_d))^2, the dihedral term of the PCN loop (scripts/pcn_utils.py:114-132,
+    178-180).  Gradient to xyz_rec only (the reference moves the target to the CPU, detached); backward = per-atom gather
+    over the CSR of the flattened index list: no atomics."""
+
+    @staticmethod
+    def forward(ctx, xyz, xyz_rec, idx, count, norm):
+        n_atoms = xyz_rec.shape[0]
+        idx = idx.to(torch.int64).contiguous()
+        out, contrib = ops.dihedral_loss_fwd(xyz.contiguous(), xyz_rec.contiguous(), idx, count, norm)
+        D = idx.shape[0]
+        pairs = torch.stack([idx.reshape(-1), torch.arange(4 * D, dtype=torch.int64, device=idx.device)], 1)
+        ctx.graph = ops.build_graph(pairs, n_atoms, n_send=max(4 * D, 1))
+        ctx.n_atoms, ctx.count, ctx.norm = n_atoms, count, norm
+        ctx.save_for_backward(contrib)
+        return out.reshape(())
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        (contrib,) = ctx.saved_tensors
+        g_rec = ops.dihedral_loss_bwd(g.reshape(1).contiguous(), contrib, ctx.graph, ctx.n_atoms, ctx.count, ctx.norm)
+        return None, g_rec, None, None, None

@@ -1024,3 +1024,38 @@ def loss_bwd(g_loss, xyz, xyz_rec, bond_graph, mu, sigma, pmu, pstd, norms, beta
                                   F, _p(norms), float(beta), float(gamma), _p(g_rec), _p(g_mu), _p(g_sigma), _p(g_pmu), _p(g_pstd),
                                   _stream()), "loss_bwd")
     return g_rec, g_mu, g_sigma, g_pmu, g_pstd
+
+
+def pin_mask(idx, n_atoms, count=None):
+    """uint8 [n_atoms] mask of the PCN C-alpha re-anchoring (cgvae.py:569-571), predicate evaluated on the device."""
+    _need_cuda(idx)
+    lib = _lib.load()
+    idx = idx.to(torch.int64).contiguous()
+    nbytes = (n_atoms + 3) // 4 * 4
+    buf = torch.empty(max(nbytes, 4), dtype=torch.uint8, device=idx.device)
+    error_flags(idx.device)
+    _lib.check(lib.cgvae_pin_mask(_p(idx), idx.numel(), _p(count), n_atoms, _p(buf), buf.numel(), _stream()), "pin_mask")
+    return buf[:n_atoms]
+
+
+def dihedral_loss_fwd(xyz, xyz_rec, idx, count=None, norm=None):
+    """(loss [1], contrib [D,4,3]): scripts/pcn_utils.py:114-132,178-180."""
+    _need_cuda(xyz_rec)
+    lib = _lib.load()
+    idx = idx.to(torch.int64).contiguous()
+    D = idx.shape[0]
+    dev = xyz_rec.device
+    contrib = torch.empty((D, 4, 3), dtype=torch.float32, device=dev)
+    out = torch.empty(1, dtype=torch.float32, device=dev)
+    ws = torch.empty(256, dtype=torch.float32, device=dev)
+    _lib.check(lib.cgvae_dihedral_loss_fwd(_p(_f32(xyz)), _p(_f32(xyz_rec)), _p(idx), D, _p(count), _p(norm), _p(contrib), _p(out),
+                                           _p(ws), 1024, _stream()), "dihedral_loss_fwd")
+    return out, contrib
+
+
+def dihedral_loss_bwd(g_loss, contrib, graph, n_atoms, count=None, norm=None):
+    lib = _lib.load()
+    g = torch.empty((n_atoms, 3), dtype=torch.float32, device=contrib.device)
+    _lib.check(lib.cgvae_dihedral_loss_bwd(_p(g_loss), _p(contrib), _p(graph.rowptr), _p(graph.col), n_atoms, contrib.shape[0],
+                                           _p(count), _p(norm), _p(g), _stream()), "dihedral_loss_bwd")
+    return g

@@ -90,10 +90,11 @@ def cgvae_batch(cfg, step, radius_fn, collate_fn, config_id=1):
 
 
 def pcn_batch(cfg, step, radius_fn, n_proteins=None, config_id=4):
-    """SCNCG_collate-shaped batch (data.py:368-398): keys xyz, ca_xyz, res, cg_map, bond_edge_list, CG_nbr_list, seq, ca_idx."""
+    """SCNCG_collate-shaped batch (data.py:368-398): keys xyz, ca_xyz, res, cg_map, bond_edge_list, CG_nbr_list, seq, ca_idx,
+    dihe_idxs."""
     n_prot = cfg["batch"] if n_proteins is None else n_proteins
     n_res, per = cfg["n_res"], cfg["atoms_per_res"]
-    xyz_l, ca_l, res_l, map_l, bond_l, nbr_l, ca_idx_l, seqs = [], [], [], [], [], [], [], []
+    xyz_l, ca_l, res_l, map_l, bond_l, nbr_l, ca_idx_l, seqs, dihe_l = [], [], [], [], [], [], [], [], []
     a_off = r_off = 0
     for p in range(n_prot):
         rng = _rng(1234 + 100 * config_id + step * n_prot + p)
@@ -108,9 +109,12 @@ def pcn_batch(cfg, step, radius_fn, n_proteins=None, config_id=4):
         map_l.append(mapping + r_off); bond_l.append(bonds + a_off)
         nbr_l.append(np.asarray(radius_fn(ca, cfg["cg_cutoff"]), dtype=np.int64) + r_off)
         ca_idx_l.append(ca_idx + a_off); seqs.append("A" * n_res)
+        # backbone-like dihedrals: (N, CA, C) of a residue and the N of the next one, and the shifted quadruple
+        r = np.arange(n_res - 1) * per
+        dihe_l.append(np.concatenate([np.stack([r, r + 1, r + 2, r + per], 1), np.stack([r + 1, r + 2, r + per, r + per + 1], 1)], 0) + a_off)
         a_off += n_res * per
         r_off += n_res
     cat = lambda xs, dt: torch.from_numpy(np.concatenate(xs, 0).astype(dt))
     return {"xyz": cat(xyz_l, np.float32), "ca_xyz": cat(ca_l, np.float32), "res": cat(res_l, np.int64),
             "cg_map": cat(map_l, np.int64), "bond_edge_list": cat(bond_l, np.int64), "CG_nbr_list": cat(nbr_l, np.int64),
-            "seq": seqs, "ca_idx": cat(ca_idx_l, np.int64)}
+            "seq": seqs, "ca_idx": cat(ca_idx_l, np.int64), "dihe_idxs": cat(dihe_l, np.int64)}

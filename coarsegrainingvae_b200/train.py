@@ -402,6 +402,75 @@ class TrainStep(object):
 STATIC_LISTS = (("nbr_list", "nbr_count"), ("CG_nbr_list", "CG_nbr_count"), ("bond_edge_list", "bond_count"))
 
 
+def compute_dihe(xyz, indices):
+    """scripts/pcn_utils.py:114-132 (torch expression; CPU tensors and the float64 checks)."""
+    b1 = xyz[indices[:, 1]] - xyz[indices[:, 0]]
+    b2 = xyz[indices[:, 2]] - xyz[indices[:, 1]]
+    b3 = xyz[indices[:, 3]] - xyz[indices[:, 2]]
+    c1 = torch.linalg.cross(b2, b3)
+    c2 = torch.linalg.cross(b1, b2)
+    p1 = (b1 * c1).sum(-1) * ((b2 * b2).sum(-1) + EPS) ** 0.5
+    p2 = (c1 * c2).sum(-1)
+    return torch.arctan(p1 / (p2 + EPS))
+
+
+def dihedral_loss(xyz_recon, xyz, dihe_idxs, count=None, norm=None):
+    """loss_dihe of the PCN loop (scripts/pcn_utils.py:178-180): mean squared difference of the generated and the data
+    dihedrals.  CUDA tensors: two launches forward, one backward (csrc/loss.cu)."""
+    if xyz_recon.is_cuda and FUSED_LOSS:
+        from . import functions
+        return functions.DihedralLoss.apply(xyz, xyz_recon, dihe_idxs, count, norm)
+    n = dihe_idxs.shape[0] if count is None else int(count)
+    idx = dihe_idxs[:n]
+    sq = (compute_dihe(xyz_recon, idx) - compute_dihe(xyz.detach(), idx)).pow(2)
+    return sq.sum() / norm if norm is not None else sq.mean()
+
+
+def to_static_pcn_batch(batch, capacities):
+    """``to_static_batch`` for the PCN (run_pdb) batches: ``CG_nbr_list`` / ``bond_edge_list`` / ``dihe_idxs`` / ``ca_idx``
+    zero-padded to fixed capacities with their live counts (``CG_nbr_count``, ``bond_count``, ``dihe_count``, ``ca_count``);
+    python lists (``seq``) are dropped -- the decoder does not read them."""
+    out = {k: v for k, v in batch.items() if torch.is_tensor(v)}
+    for key, count_key, width in (("CG_nbr_list", "CG_nbr_count", 2), ("bond_edge_list", "bond_count", 2),
+                                  ("dihe_idxs", "dihe_count", 4), ("ca_idx", "ca_count", 0)):
+        if key not in batch:
+            continue
+        t = batch[key]
+        cap, n = int(capacities[key]), int(t.shape[0])
+        if n > cap:
+            raise ValueError("%s has %d rows, capacity %d" % (key, n, cap))
+        padded = torch.zeros((cap, width) if width else (cap,), dtype=torch.int64)
+        padded[:n] = t
+        out[key] = padded
+        out[count_key] = torch.tensor([n], dtype=torch.int64)
+        if key == "CG_nbr_list":
+            up = bool((t[:, 0] > t[:, 1]).any()) if n else False
+            down = bool((t[:, 1] > t[:, 0]).any()) if n else False
+            out["CG_nbr_symmetrize"] = not (up and down)
+    return out
+
+
+class PCNTrainStep(TrainStep):
+    """one optimisation step of the PCN loop (scripts/pcn_utils.py::loop): MSE + gamma * bond-graph loss + kappa *
+    dihedral loss (the KL term is absent: PCN returns no latent), skip guard at gamma * 300 (pcn_utils.py:191), then
+    clip_grad_norm_(0.01) + Adam as in the CGVAE loop.  Batches from ``to_static_pcn_batch`` make the step
+    CUDA-graph-capturable (``GraphedTrainStep(PCNTrainStep(..., capturable=True), batch, None)``)."""
+
+    def __init__(self, model, gamma, kappa=0.0, loss_limit="reference", **kw):
+        TrainStep.__init__(self, model, 0.0, gamma, loss_limit=None, **kw)
+        self.kappa = kappa
+        self.loss_limit = (gamma * 300.0) if loss_limit == "reference" else loss_limit
+
+    def _loss(self, batch, eps):
+        out = self.model(batch)
+        norms = batch.get("dp_norms")
+        loss = training_loss(out, out[4], batch["bond_edge_list"], 0.0, self.gamma, batch.get("bond_count"), norms)[0]
+        if self.kappa != 0.0 and "dihe_idxs" in batch:
+            loss = loss + self.kappa * dihedral_loss(out[5], out[4], batch["dihe_idxs"], batch.get("dihe_count"),
+                                                     batch.get("dihe_norm"))
+        return loss
+
+
 def to_static_batch(batch, capacities):
     """Pad the variable-length index lists of a collated batch to fixed capacities and add their live row counts
     (``nbr_count``, ``CG_nbr_count``, ``bond_count``: int64 [1]).  Host-side, once per batch at dataset-preparation time

@@ -326,6 +326,21 @@ int cgvae_loss_bwd(const float* g_loss, const float* xyz, const float* xyz_rec, 
                    const int32_t* bond_col, const float* mu, const float* sigma, const float* pmu, const float* pstd,
                    int64_t n_beads, int F, const float* norms, float beta, float gamma, float* g_xyz_rec, float* g_mu,
                    float* g_sigma, float* g_pmu, float* g_pstd, cgvae_stream_t stream);
+/* Dihedral loss of the PCN loop (scripts/pcn_utils.py:114-132 compute_dihe, :178-180):
+ *   out[0] = mean_d (theta(xyz_rec; idx[d]) - theta(xyz; idx[d]))^2,  theta = atan(p1 / (p2 + 1e-6)) exactly as the reference
+ * forms it (b1..b3, c1 = b2 x b3, c2 = b1 x b2, p1 = (b1.c1) sqrt(b2.b2 + 1e-6), p2 = c1.c2).  idx int64 [n_dihe][4];
+ * n_live (nullable device int64): live rows of a zero-padded static list; norm (nullable device float): denominator for
+ * data-parallel training.  contrib float [n_dihe][4][3]: per-(dihedral, slot) gradients kept for the backward, which is a
+ * per-atom gather over the receiver CSR of the flattened list (cgvae_csr_* on pairs (idx[d][s], 4 d + s)): deterministic.
+ * ws: 256 floats. */
+int cgvae_dihedral_loss_fwd(const float* xyz, const float* xyz_rec, const int64_t* idx, int64_t n_dihe, const int64_t* n_live,
+                            const float* norm, float* contrib, float* out, void* ws, size_t ws_bytes, cgvae_stream_t stream);
+int cgvae_dihedral_loss_bwd(const float* g_loss, const float* contrib, const int32_t* rowptr, const int32_t* col, int64_t n_atoms,
+                            int64_t n_dihe, const int64_t* n_live, const float* norm, float* g_xyz_rec, cgvae_stream_t stream);
+/* PCN C-alpha pin mask with the predicate of cgvae.py:569-571 evaluated on the device: pin[0..n_atoms) = 0, then
+ * pin[idx[i]] = 1 for the live entries iff idx[last] < n_atoms.  pin_bytes >= n_atoms, a multiple of 4. */
+int cgvae_pin_mask(const int64_t* idx, int64_t n_idx, const int64_t* n_live, int64_t n_atoms, uint8_t* pin, size_t pin_bytes,
+                   cgvae_stream_t stream);
 /* p[0..n) = value (initial decoder state cgvae.py:90-95 without a library fill) */
 int cgvae_fill(float* p, int64_t n, float value, cgvae_stream_t stream);
 

@@ -389,3 +389,39 @@ def training_loss(outputs, batch, beta, gamma):
     kl = kl_divergence(mu, sigma, pmu, pstd) if mu is not None else torch.zeros(())
     g = graph_loss(xyz_recon, xyz, batch["bond_edge_list"]) if gamma != 0.0 else torch.zeros(())
     return recon + kl * beta + g * gamma, recon, kl, g
+
+
+EPS = 1e-6      # scripts/pcn_utils.py:21, scripts/utils.py:27
+
+
+def compute_dihe(xyz, indices):
+    """scripts/pcn_utils.py:114-132: theta = arctan(p1 / (p2 + EPS)) with b1..b3 the three bond vectors of the quadruple,
+    c1 = b2 x b3, c2 = b1 x b2, p1 = (b1 . c1) * sqrt(b2 . b2 + EPS), p2 = c1 . c2 (EPS = 1e-6, pcn_utils.py:21)."""
+    b1 = xyz[indices[:, 1]] - xyz[indices[:, 0]]
+    b2 = xyz[indices[:, 2]] - xyz[indices[:, 1]]
+    b3 = xyz[indices[:, 3]] - xyz[indices[:, 2]]
+    c1 = torch.linalg.cross(b2, b3)
+    c2 = torch.linalg.cross(b1, b2)
+    p1 = (b1 * c1).sum(-1) * ((b2 * b2).sum(-1) + EPS) ** 0.5
+    p2 = (c1 * c2).sum(-1)
+    return torch.arctan(p1 / (p2 + EPS))
+
+
+def pcn_loss(xyz_recon, xyz, bond_edge_list, dihe_idxs, gamma, kappa):
+    """the loss of the PCN loop, scripts/pcn_utils.py:160-183 (no KL: PCN.forward returns S_mu = None):
+    mean((rec - xyz)^2) + gamma * mean over bonds (|d_rec|_e - |d_xyz|_e)^2 + kappa * mean over dihedrals (theta_rec - theta_xyz)^2."""
+    recon = (xyz_recon - xyz).pow(2).mean()
+    a, b = bond_edge_list[:, 0], bond_edge_list[:, 1]
+    gen = ((xyz_recon[a] - xyz_recon[b]).pow(2).sum(-1) + EPS).sqrt()
+    dat = ((xyz[a] - xyz[b]).pow(2).sum(-1) + EPS).sqrt()
+    graph = (gen - dat).pow(2).mean() if gamma != 0.0 else torch.zeros((), dtype=xyz.dtype)
+    dihe = (compute_dihe(xyz_recon, dihe_idxs) - compute_dihe(xyz, dihe_idxs)).pow(2).mean()
+    return recon + graph * gamma + dihe * kappa, recon, graph, dihe
+
+
+def pcn_loop_step(loss, gamma, train=True):
+    """scripts/pcn_utils.py:191-206: ``loss >= gamma * 300`` or NaN -> ``continue``; validation still runs ``loss.backward()``."""
+    l = float(loss)
+    if l >= gamma * 300.0 or l != l:
+        return False, False
+    return True, bool(train)

@@ -386,6 +386,14 @@ def vae_latent_bwd(g_z, g_sigma, eps, sigma):
     return g_z, g_s * 0.5 * (sigma - 1e-12)
 
 
+def pin_mask(idx, n_atoms, count=None):
+    pin = torch.zeros(n_atoms, dtype=torch.uint8, device=idx.device)
+    n = int(count) if count is not None else idx.numel()
+    if n and int(idx[n - 1]) < n_atoms:
+        pin[idx[:n]] = 1
+    return pin
+
+
 def std_logvar_fwd(x, c):
     return c + torch.exp(x / 2)
 
@@ -394,7 +402,7 @@ def std_logvar_bwd(gy, y, c):
     return gy * 0.5 * (y - c)
 
 
-_NAMES = ["fill", "vae_latent_fwd", "vae_latent_bwd", "std_logvar_fwd", "std_logvar_bwd", "radius_graph", "edge_orientation", "build_graph", "build_segments", "contraction_graph", "edge_geometry",
+_NAMES = ["fill", "pin_mask", "vae_latent_fwd", "vae_latent_bwd", "std_logvar_fwd", "std_logvar_bwd", "radius_graph", "edge_orientation", "build_graph", "build_segments", "contraction_graph", "edge_geometry",
           "gemm", "colsum", "message_fwd", "message_bwd", "message9_fwd", "message9_bwd", "update_norm_fwd",
           "update_combine_fwd", "update_combine_bwd", "update_norm_bwd", "segment_reduce_fwd", "segment_reduce_bwd",
           "gather_rows", "lift_fwd", "lift_bwd", "vec_to_planar", "vec_from_planar"]

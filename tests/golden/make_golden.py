@@ -407,6 +407,30 @@ def dataset_lists(ref_data):
     _save("dataset_lists.npz", store)
 
 
+def pcn_dihedral():
+    """compute_dihe of the PCN loop (scripts/pcn_utils.py:114-132) and its dihedral loss term (:178-180), value and gradient.
+    pcn_utils.py imports ase / networkx / sklearn at module level, so the function is lifted out of the UNMODIFIED source
+    with ast and executed as it stands (its only globals: torch, EPS)."""
+    import ast
+    src_path = os.path.join(ref_shim.REFERENCE_ROOT, "scripts", "pcn_utils.py")
+    tree = ast.parse(open(src_path).read())
+    fn = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "compute_dihe"][0]
+    eps = [n for n in tree.body if isinstance(n, ast.Assign) and getattr(n.targets[0], "id", None) == "EPS"][0]
+    ns = {"torch": torch}
+    exec(compile(ast.Module(body=[eps, fn], type_ignores=[]), src_path, "exec"), ns)
+    compute_dihe = ns["compute_dihe"]
+    gen = torch.Generator().manual_seed(31)
+    n_atoms, n_dihe = 64, 90
+    xyz = torch.randn(n_atoms, 3, generator=gen) * 2.0
+    rec = (xyz + 0.4 * torch.randn(n_atoms, 3, generator=gen)).requires_grad_(True)
+    idx = torch.stack([torch.randperm(n_atoms, generator=gen)[:4] for _ in range(n_dihe)])
+    gen_d, dat_d = compute_dihe(rec, idx), compute_dihe(xyz, idx)
+    loss = (gen_d - dat_d).pow(2).mean()
+    loss.backward()
+    _save("pcn_dihedral.npz", {"xyz": _np(xyz), "xyz_rec": _np(rec), "idx": _np(idx), "gen_dihe": _np(gen_d), "data_dihe": _np(dat_d),
+                               "loss": _np(loss), "g_xyz_rec": _np(rec.grad)})
+
+
 def main():
     torch.set_num_threads(1)
     ref_modules, ref_conv, ref_cgvae, ref_data = ref_shim.import_reference()
@@ -418,6 +442,7 @@ def main():
     graphs(ref_data, ref_cgvae)
     sampling(ref_cgvae, ref_data)
     dataset_lists(ref_data)
+    pcn_dihedral()
 
 
 if __name__ == "__main__":

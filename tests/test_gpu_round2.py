@@ -472,3 +472,95 @@ def test_vae_latent_and_prior_std_kernels():
     assert rel_err(x.grad.cpu().numpy(), x64.grad.cpu().numpy()) <= 1e-6
     f = ops.fill((1000, 7), 1.0, mu)
     assert f.shape == (1000, 7) and bool((f == 1.0).all())
+
+
+# ------------------------------------------------------------------------------------------ PCN: dihedral loss, device predicate, graph
+
+def test_dihedral_loss_kernel_matches_reference_golden():
+    """csrc/loss.cu dihedral kernels (analytic backward, per-atom CSR gather) == the reference's compute_dihe + autograd
+    (tests/golden/pcn_dihedral.npz, generated by executing scripts/pcn_utils.py:114-132 from the reference source)."""
+    from coarsegrainingvae_b200 import train
+    z = load("pcn_dihedral.npz")
+    xyz = torch.from_numpy(np.asarray(z["xyz"])).to(DEV)
+    idx = torch.from_numpy(np.asarray(z["idx"])).to(DEV)
+    rec = torch.from_numpy(np.asarray(z["xyz_rec"])).to(DEV).requires_grad_(True)
+    loss = train.dihedral_loss(rec, xyz, idx)
+    (loss * 1.0).backward()
+    assert rel_err(loss, z["loss"]) <= TOL and rel_err(rec.grad, z["g_xyz_rec"]) <= TOL
+    # float64 torch expression on a larger random case + static-capacity (padded) list + a data-parallel denominator
+    g = torch.Generator().manual_seed(5)
+    n, D = 4000, 7001
+    x = (torch.randn(n, 3, generator=g) * 3).to(DEV)
+    r0 = (x.cpu() + 0.3 * torch.randn(n, 3, generator=g)).to(DEV)
+    q = torch.stack([torch.randperm(n, generator=g)[:4] for _ in range(D)]).to(DEV)
+    r = r0.clone().requires_grad_(True)
+    pad = torch.cat([q, torch.zeros(99, 4, dtype=torch.int64, device=DEV)])
+    cnt = torch.tensor([D], dtype=torch.int64, device=DEV)
+    norm = torch.tensor([D * 1.5], device=DEV)
+    l1 = train.dihedral_loss(r, x, pad, count=cnt, norm=norm)
+    l1.backward()
+    r64 = r0.double().requires_grad_(True)
+    l64 = (train.compute_dihe(r64, q) - train.compute_dihe(x.double(), q)).pow(2).sum() / (D * 1.5)
+    l64.backward()
+    assert rel_err(l1, l64) <= TOL and rel_err(r.grad, r64.grad) <= TOL
+    r2 = r0.clone().requires_grad_(True)
+    train.dihedral_loss(r2, x, pad, count=cnt, norm=norm).backward()
+    assert torch.equal(r2.grad, r.grad)                      # deterministic
+
+
+def test_pcn_pin_mask_device_predicate():
+    """cgvae.py:569-571 without the host read: mask set iff ca_idx[-1] < n_atoms; live count honoured; bad index flagged."""
+    idx = torch.tensor([1, 9, 17, 25], device=DEV)
+    m = ops.pin_mask(idx, 30).cpu().numpy()
+    assert m.sum() == 4 and m[[1, 9, 17, 25]].all()
+    assert int(ops.pin_mask(idx, 25).sum()) == 0               # last index overruns the atoms: the reference skips the re-anchoring
+    padded = torch.tensor([1, 9, 17, 25, 0, 0], device=DEV)
+    m = ops.pin_mask(padded, 30, torch.tensor([4], device=DEV)).cpu().numpy()
+    assert m.sum() == 4 and m[0] == 0
+
+
+def test_pcn_step_graphed_matches_eager_and_reference_loss():
+    """PCNTrainStep (gamma * bond loss + kappa * dihedral loss, skip guard at gamma * 300) on a reduced c4 batch: the loss equals
+    the oracle's restatement of scripts/pcn_utils.py:160-183, and the CUDA-graph replay over static-capacity buffers
+    reproduces the eager steps bit for bit (losses and parameters after 3 steps)."""
+    from coarsegrainingvae_b200 import train
+    from coarsegrainingvae_b200.factory import build_pcn
+    cfg = dict(synthetic.CONFIGS["c4_protein"])
+    cfg["n_res"], cfg["n_basis"] = 40, 128
+    raws = [synthetic.pcn_batch(cfg, i, _gpu_radius, n_proteins=2) for i in range(3)]
+    caps = {"CG_nbr_list": max(b["CG_nbr_list"].shape[0] for b in raws) + 16, "bond_edge_list": raws[0]["bond_edge_list"].shape[0] + 8,
+            "dihe_idxs": raws[0]["dihe_idxs"].shape[0] + 5, "ca_idx": raws[0]["ca_idx"].shape[0] + 3}
+    statics = [_to(train.to_static_pcn_batch(b, caps), DEV) for b in raws]
+    gamma, kappa = 2.0, 0.5
+
+    def make():
+        torch.manual_seed(3)
+        return build_pcn(cfg["n_basis"], cfg["n_rbf"], cfg["cg_cutoff"], 3).to(DEV)
+
+    # loss of the step == oracle (float64) on the unpadded batch
+    m0 = make()
+    tr0 = train.PCNTrainStep(m0, gamma, kappa)
+    out = m0(_to(raws[0], DEV))
+    want = orc.pcn_loss(out[5].detach().double().cpu(), raws[0]["xyz"].double(), raws[0]["bond_edge_list"], raws[0]["dihe_idxs"],
+                        gamma, kappa)[0]
+    got = tr0._loss(statics[0], None)
+    assert rel_err(got, want) <= TOL
+    assert tr0.loss_limit == gamma * 300.0
+    # eager vs graph
+    ma, mb = make(), make()
+    ta = train.PCNTrainStep(ma, gamma, kappa, capturable=True)
+    ta.prepare(statics[0], None)
+    tb = train.PCNTrainStep(mb, gamma, kappa, capturable=True)
+    tb.prepare(statics[0], None)
+    graphed = train.GraphedTrainStep(tb, statics[0], None)
+    mb.load_state_dict(ma.state_dict())
+    for name in ("exp_avg", "exp_avg_sq", "step_count"):
+        getattr(tb, name).zero_()
+    # the warm-up steps of the capture advanced tb; reset it to ta's state (parameters are views of the flat buffers)
+    tb.flat_p.copy_(ta.flat_p)
+    la, lb = [], []
+    for b in statics:
+        la.append(float(ta.step(b, None)))
+        lb.append(float(graphed.step(b)))
+    assert la == lb, (la, lb)
+    assert torch.equal(ta.flat_p, tb.flat_p)

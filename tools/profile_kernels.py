@@ -1,4 +1,5 @@
-"""Small-footprint driver for `ncu --set full` captures of the hot kernels at the chignolin shapes (350 atoms, F = 600,
+"""(round 2: + the tensor-core message forward, the tcgen05 GEMM at the three atom-level shapes)
+Small-footprint driver for `ncu --set full` captures of the hot kernels at the chignolin shapes (350 atoms, F = 600,
 12 beads).  ncu saves / restores device memory around every replay pass, so profiling inside the full training step
 (2 GB resident) costs seconds per launch; this script keeps < 200 MB resident.  Launches, in order:
 message_fwd, message_bwd (atom graph, 3 splits), gemm NT / NN stream (W2 5400x600, 12 rows), wgrad_grouped (one decoder
@@ -26,7 +27,16 @@ for rep in range(2):                      # rep 0 warms up (attribute calls, cac
     phi, v = rn(N, 3, F), rn(N, 3, F)
     Wf, bf = rn(3 * F, R) * 0.1, rn(3 * F) * 0.1
     s_res, v_res = rn(N, F), rn(N, 3, F)
-    out_s, out_v, _ = ops.message_fwd(3, phi, v, None, geom, Wf, bf, s_res, v_res)
+    out_s, out_v, _ = ops.message_fwd(3, phi, v, None, geom, Wf, bf, s_res, v_res)     # tensor-core path (policy: auto)
+    ops.MSG_TC = "0"
+    ops.message_fwd(3, phi, v, None, geom, Wf, bf, s_res, v_res)                        # fp32 SIMT path for comparison
+    ops.MSG_TC = "auto"
+    # atom-level Dense layers on tcgen05 (csrc/gemm_tc.cu): phi-MLP forward (NT), input gradient (NN), weight gradient (TN)
+    xa, W1, b1 = rn(N, F), rn(3 * F, F) * 0.05, rn(3 * F)
+    ya = ops.gemm(ops.GEMM_NT, xa, W1, N, 3 * F, F, bias=b1, act=1)
+    ga = rn(N, 3 * F)
+    ops.gemm(ops.GEMM_NN, ga, W1, N, F, 3 * F)
+    ops.gemm(ops.GEMM_TN, ga, xa, 3 * F, F, N)
     ops.message_bwd(3, phi, v, None, None, geom, Wf, bf, rn(N, F), rn(N, 3, F), True, sink=False)
     x12, W2, b2 = rn(12, F), rn(9 * F, F) * 0.05, rn(9 * F)
     y = ops.gemm(ops.GEMM_NT, x12, W2, 12, 9 * F, F, bias=b2, act=1)
