@@ -290,6 +290,10 @@ class CGequiVAE(nn.Module):
             if eps is None:
                 eps = torch.randn_like(logvar)
             z_sample, sigma = fn.VAELatent.apply(mu, logvar, eps)
+        hook = getattr(self, "_latent_grad_hook", None)
+        if hook is not None and z_sample.requires_grad:
+            # fires when the backward pass has left the decoder (train.TrainStep: data-parallel overlap)
+            z_sample.register_hook(hook)
         xyz_recon = self.decoder(cg_xyz, CG_nbr_list, z_sample, s_i, mapping, num_CGs, graphs=g)
         ops.check_device_errors(xyz_recon.device)      # IndexError where the reference raises one (cgvae.py:473)
         return mu, sigma, H_prior_mu, H_prior_sigma, xyz, xyz_recon

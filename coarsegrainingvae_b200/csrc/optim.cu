@@ -133,12 +133,41 @@ int cgvae_adam_clip_step(float* p, const float* g, float* m, float* v, int64_t n
   CGVAE_REQUIRE(aligned16(p) && aligned16(g) && aligned16(m) && aligned16(v), "adam_clip_step: buffers must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   float* partial = reinterpret_cast<float*>(ws);
-  unsigned int* ticket = reinterpret_cast<unsigned int*>(partial + kNormBlocks);
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(partial + kNormBlocks + 1);      // [1024] = loss slot of the sharded form
   launch_kernel(sumsq_partial_kernel, dim3(kNormBlocks), dim3(256), 0, st, g, n, partial, ticket);
   if (int rc = launched("sumsq_partial")) return rc;
   const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(n, 256 * 4), 148 * 8);
   launch_kernel(adam_clip_kernel, dim3(blocks), dim3(256), 0, st, p, g, m, v, n, (const float*)partial, max_norm, grad_scale, lr, beta1, beta2, eps,
                 step, norm_out, loss, loss_scale, loss_limit, skipped, ticket);
+  return launched("adam_clip");
+}
+
+// Sharded form (data parallel, reduce-scatter -> Adam on 1/world of the flat buffers -> all-gather of the parameters):
+// phase 1 leaves the 1024 partial sums of squares of THIS rank's gradient shard in ws[0..1024) and a copy of the local loss
+// in ws[1024]; the caller all-reduces ws[0..1025) (SUM) so that every rank holds the partials of the whole gradient and the
+// summed loss; phase 2 re-reduces them in every block exactly like the unsharded kernel and updates the shard.
+int cgvae_grad_sumsq(const float* g, int64_t n, const float* loss, void* ws, size_t ws_bytes, cgvae_stream_t stream) {
+  CGVAE_REQUIRE(ws && ws_bytes >= cgvae_adam_ws_bytes() && (n == 0 || g), "grad_sumsq: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* partial = reinterpret_cast<float*>(ws);
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(partial + kNormBlocks + 1);
+  launch_kernel(sumsq_partial_kernel, dim3(kNormBlocks), dim3(256), 0, st, g, n, partial, ticket);
+  if (int rc = launched("sumsq_partial")) return rc;
+  if (loss != nullptr) CGVAE_CUDA(cudaMemcpyAsync(partial + kNormBlocks, loss, sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+int cgvae_adam_apply(float* p, const float* g, float* m, float* v, int64_t n, float max_norm, float grad_scale, float lr, float beta1,
+                     float beta2, float eps, float* step, float* norm_out, int use_ws_loss, float loss_scale, float loss_limit,
+                     float* skipped, void* ws, size_t ws_bytes, cgvae_stream_t stream) {
+  if (n == 0) return 0;
+  CGVAE_REQUIRE(p && g && m && v && step && ws && ws_bytes >= cgvae_adam_ws_bytes(), "adam_apply: bad arguments");
+  CGVAE_REQUIRE(aligned16(p) && aligned16(g) && aligned16(m) && aligned16(v), "adam_apply: buffers must be 16-byte aligned");
+  float* partial = reinterpret_cast<float*>(ws);
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(partial + kNormBlocks + 1);
+  const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(n, 256 * 4), 148 * 8);
+  launch_kernel(adam_clip_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, n, (const float*)partial, max_norm, grad_scale, lr,
+                beta1, beta2, eps, step, norm_out, use_ws_loss ? (const float*)(partial + kNormBlocks) : (const float*)nullptr, loss_scale,
+                loss_limit, skipped, ticket);
   return launched("adam_clip");
 }
 

@@ -488,6 +488,14 @@ class DeferredGrads(object):
         _DEFERRED = []
         return self
 
+    def flush_now(self):
+        """launch what has been recorded so far (data-parallel overlap: the decoder's gradients must be final before their
+        all-reduce starts, while the encoder's backward is still to come)."""
+        global _DEFERRED
+        pending, _DEFERRED = _DEFERRED, []
+        if pending:
+            wgrad_grouped(merge_deferred(pending))
+
     def __exit__(self, exc_type, exc, tb):
         global _DEFERRED
         pending, _DEFERRED = _DEFERRED, None
@@ -943,6 +951,28 @@ def adam_clip_step(p, g, m, v, step, max_norm, lr, betas=(0.9, 0.999), eps=1e-8,
                "adam_clip_step")
     if t0 is not None:
         TIMER.end("adam_clip", t0, dict(n=p.numel()))
+
+
+def adam_ws(device):
+    """workspace of the two-phase (sharded) optimiser: float [1028] = 1024 norm partials | loss | ticket | pad."""
+    lib = _lib.load()
+    return torch.zeros(int(lib.cgvae_adam_ws_bytes()) // 4, dtype=torch.float32, device=device)
+
+
+def grad_sumsq(g, loss, ws):
+    _need_cuda(g, ws)
+    lib = _lib.load()
+    _lib.check(lib.cgvae_grad_sumsq(_p(g), g.numel(), _p(loss), _p(ws), ws.numel() * 4, _stream()), "grad_sumsq")
+
+
+def adam_apply(p, g, m, v, step, max_norm, lr, ws, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0, use_ws_loss=False, loss_scale=1.0,
+               loss_limit=float("inf"), skipped=None):
+    """phase 2 of the sharded optimiser: ws holds the all-reduced norm partials (and loss); p / g / m / v are this rank's slices."""
+    _need_cuda(p, g, m, v, step, ws)
+    lib = _lib.load()
+    _lib.check(lib.cgvae_adam_apply(_p(p), _p(g), _p(m), _p(v), p.numel(), float(max_norm), float(grad_scale), float(lr), float(betas[0]),
+                                    float(betas[1]), float(eps), _p(step), None, int(bool(use_ws_loss)), float(loss_scale),
+                                    float(min(loss_limit, 3.0e38)), _p(skipped), _p(ws), ws.numel() * 4, _stream()), "adam_apply")
 
 
 # --------------------------------------------------------------------------------------------------

@@ -235,5 +235,190 @@ def _segment_bwd(ctx, g):
 
 register_autograd(NS + "::segment_reduce", _segment_bwd, setup_context=_segment_setup)
 
+
+# ------------------------------------------------------------------------------------------------ 9-split (pseudo-scalar) layer
+
+@custom_op(NS + "::message9_layer", mutates_args=(), device_types="cuda")
+def message9_layer(phi: torch.Tensor, s: torch.Tensor, sbar: torch.Tensor, v: torch.Tensor, vbar: torch.Tensor, rowptr: torch.Tensor,
+                   col: torch.Tensor, rowptr_t: torch.Tensor, col_t: torch.Tensor, perm_t: torch.Tensor, basis: torch.Tensor,
+                   unit: torch.Tensor, Wf: torch.Tensor, bf: torch.Tensor, residual: bool, n_rbf: int
+                   ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """EquiMessagePsuedo (conv.py:180-242) on one homogeneous graph: phi [n, 9, F] (phi-MLP output), scalar / pseudo-scalar
+    states s, sbar [n, F], planar vector / pseudo-vector states v, vbar [n, 3, F]; residual: the adds of cgvae.py:108-111."""
+    g = _graph(rowptr, col, rowptr_t, col_t, perm_t, phi.shape[0])
+    outs = ops.message9_fwd(phi.contiguous(), s.contiguous(), sbar.contiguous(), v.contiguous(), vbar.contiguous(),
+                            _geom(g, basis, unit, n_rbf), Wf, bf, residual)
+    return outs[0], outs[1], outs[2], outs[3]
+
+
+@message9_layer.register_fake
+def _(phi, s, sbar, v, vbar, rowptr, col, rowptr_t, col_t, perm_t, basis, unit, Wf, bf, residual, n_rbf):
+    return torch.empty_like(s), torch.empty_like(sbar), torch.empty_like(v), torch.empty_like(vbar)
+
+
+@custom_op(NS + "::message9_layer_backward", mutates_args=(), device_types="cuda")
+def message9_layer_backward(phi: torch.Tensor, s: torch.Tensor, sbar: torch.Tensor, v: torch.Tensor, vbar: torch.Tensor,
+                            rowptr: torch.Tensor, col: torch.Tensor, rowptr_t: torch.Tensor, col_t: torch.Tensor, perm_t: torch.Tensor,
+                            basis: torch.Tensor, unit: torch.Tensor, Wf: torch.Tensor, bf: torch.Tensor, residual: bool, n_rbf: int,
+                            g_s: torch.Tensor, g_sbar: torch.Tensor, g_v: torch.Tensor, g_vbar: torch.Tensor
+                            ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    g = _graph(rowptr, col, rowptr_t, col_t, perm_t, phi.shape[0])
+    geom = _geom(g, basis, unit, n_rbf)
+    fork, ops.FORK_ENABLED = ops.FORK_ENABLED, False          # a dispatcher op returns finished tensors: no forked branch
+    try:
+        outs = ops.message9_bwd(phi.contiguous(), s.contiguous(), sbar.contiguous(), v.contiguous(), vbar.contiguous(), geom, Wf, bf,
+                                residual, g_s.contiguous(), g_sbar.contiguous(), g_v.contiguous(), g_vbar.contiguous())
+    finally:
+        ops.FORK_ENABLED = fork
+    return tuple(outs)
+
+
+@message9_layer_backward.register_fake
+def _(phi, s, sbar, v, vbar, rowptr, col, rowptr_t, col_t, perm_t, basis, unit, Wf, bf, residual, n_rbf, g_s, g_sbar, g_v, g_vbar):
+    return (torch.empty_like(s), torch.empty_like(sbar), torch.empty_like(v), torch.empty_like(vbar), torch.empty_like(phi),
+            torch.empty_like(Wf), torch.empty_like(bf))
+
+
+def _message9_setup(ctx, inputs, output):
+    phi, s, sbar, v, vbar, rowptr, col, rowptr_t, col_t, perm_t, basis, unit, Wf, bf, residual, n_rbf = inputs
+    ctx.save_for_backward(phi, s, sbar, v, vbar, rowptr, col, rowptr_t, col_t, perm_t, basis, unit, Wf, bf)
+    ctx.residual, ctx.n_rbf = residual, n_rbf
+
+
+def _message9_bwd(ctx, g_s, g_sbar, g_v, g_vbar):
+    phi, s, sbar, v, vbar, rowptr, col, rowptr_t, col_t, perm_t, basis, unit, Wf, bf = ctx.saved_tensors
+    gi_s, gi_sbar, gi_v, gi_vbar, g_phi, dWf, dbf = torch.ops.cgvae_b200.message9_layer_backward(
+        phi, s, sbar, v, vbar, rowptr, col, rowptr_t, col_t, perm_t, basis, unit, Wf, bf, ctx.residual, ctx.n_rbf, g_s, g_sbar, g_v,
+        g_vbar)
+    return g_phi, gi_s, gi_sbar, gi_v, gi_vbar, None, None, None, None, None, None, None, dWf, dbf, None, None
+
+
+register_autograd(NS + "::message9_layer", _message9_bwd, setup_context=_message9_setup)
+
+
+# ------------------------------------------------------------------------------------------------ update block
+
+@custom_op(NS + "::update_block", mutates_args=(), device_types="cuda")
+def update_block(s: torch.Tensor, v: torch.Tensor, U: torch.Tensor, V: torch.Tensor, A0: torch.Tensor, c0: torch.Tensor,
+                 A1: torch.Tensor, c1: torch.Tensor, act: int, residual: bool
+                 ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """UpdateBlock.forward (conv.py:588-616) on planar vectors: s [N, F], v [N, 3, F]; U, V the bias-free u_mat / v_mat
+    weights, (A0, c0), (A1, c1) the two Dense layers of s_dense; residual: s + ds, v + dv (cgvae.py:122-123).
+    Returns (s_out, v_out, Uv, Vv, x, h, z, q) -- the last six are the tensors the backward needs."""
+    s, v = s.contiguous(), v.contiguous()
+    N, F = s.shape
+    Uv, Vv = ops.linear_pair_fwd(v.view(3 * N, F), U, V)
+    Uv, Vv = Uv.view(N, 3, F), Vv.view(N, 3, F)
+    x = ops.update_norm_fwd(s, Vv)
+    h, z = ops.linear_fwd(x, A0, c0, act, save_pre=True)
+    q = ops.linear_fwd(h, A1, c1, 0).view(N, 3, F)
+    s_out, v_out = ops.update_combine_fwd(s, v, Uv, Vv, q, residual)
+    return s_out, v_out, Uv, Vv, x, h, z, q
+
+
+@update_block.register_fake
+def _(s, v, U, V, A0, c0, A1, c1, act, residual):
+    N, F = s.shape
+    h = s.new_empty((N, A0.shape[0]))
+    return (torch.empty_like(s), torch.empty_like(v), torch.empty_like(v), torch.empty_like(v), s.new_empty((N, A0.shape[1])), h,
+            torch.empty_like(h), torch.empty_like(v))
+
+
+@custom_op(NS + "::update_block_backward", mutates_args=(), device_types="cuda")
+def update_block_backward(g_s: torch.Tensor, g_v: torch.Tensor, v: torch.Tensor, Uv: torch.Tensor, Vv: torch.Tensor, x: torch.Tensor,
+                          h: torch.Tensor, z: torch.Tensor, q: torch.Tensor, U: torch.Tensor, V: torch.Tensor, A0: torch.Tensor,
+                          A1: torch.Tensor, act: int, residual: bool
+                          ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    g_s, g_v = g_s.contiguous(), g_v.contiguous()
+    N, _, F = v.shape
+    gq, gUv, gVv = ops.update_combine_bwd(Uv, Vv, q, g_s, g_v)
+    gq2, v2 = gq.view(N, 3 * F), v.view(3 * N, F)
+    gUv2, gVv2 = gUv.view(3 * N, F), gVv.view(3 * N, F)
+    gz = ops.linear_bwd_input(gq2, A1, z_in=z, dact=act)
+    gA1, gc1 = ops.linear_bwd_weight(gq2, h), ops.colsum(gq2)
+    gU = ops.linear_bwd_weight(gUv2, v2)
+    gx = ops.linear_bwd_input(gz, A0)
+    gA0, gc0 = ops.linear_bwd_weight(gz, x), ops.colsum(gz)
+    gs_in = ops.update_norm_bwd(x, Vv, gx, g_s, gVv, residual)               # adds the norm path into gVv in place
+    gv_in = ops.linear_bwd_input(gUv2, U, add=g_v.view(3 * N, F) if residual else None)
+    gv_in = ops.linear_bwd_input(gVv2, V, add=gv_in).view(N, 3, F)
+    gV = ops.linear_bwd_weight(gVv2, v2)
+    return gs_in, gv_in, gU, gV, gA0, gc0, gA1, gc1
+
+
+@update_block_backward.register_fake
+def _(g_s, g_v, v, Uv, Vv, x, h, z, q, U, V, A0, A1, act, residual):
+    return (torch.empty_like(g_s), torch.empty_like(v), torch.empty_like(U), torch.empty_like(V), torch.empty_like(A0),
+            A0.new_empty((A0.shape[0],)), torch.empty_like(A1), A1.new_empty((A1.shape[0],)))
+
+
+def _update_setup(ctx, inputs, output):
+    s, v, U, V, A0, c0, A1, c1, act, residual = inputs
+    ctx.save_for_backward(v, output[2], output[3], output[4], output[5], output[6], output[7], U, V, A0, A1)
+    ctx.act, ctx.residual = act, residual
+
+
+def _update_bwd(ctx, g_s, g_v, *unused):
+    v, Uv, Vv, x, h, z, q, U, V, A0, A1 = ctx.saved_tensors
+    gs_in, gv_in, gU, gV, gA0, gc0, gA1, gc1 = torch.ops.cgvae_b200.update_block_backward(g_s, g_v, v, Uv, Vv, x, h, z, q, U, V, A0, A1,
+                                                                                          ctx.act, ctx.residual)
+    return gs_in, gv_in, gU, gV, gA0, gc0, gA1, gc1, None, None
+
+
+register_autograd(NS + "::update_block", _update_bwd, setup_context=_update_setup)
+
+
+# ------------------------------------------------------------------------------------------------ bead -> atom lifting
+
+@custom_op(NS + "::lift", mutates_args=(), device_types="cuda")
+def lift(V: torch.Tensor, cg_xyz: torch.Tensor, mapping: torch.Tensor, rank: torch.Tensor, rowptr: torch.Tensor, atoms: torch.Tensor,
+         pin: Optional[torch.Tensor], mode: int) -> torch.Tensor:
+    """xyz [N, 3] = cg_xyz[mapping] + V[mapping, :, rank] (cgvae.py:466-482); mode 1 subtracts the bead mean (offset=True), mode 2
+    zeroes the displacement of pinned atoms (PCN C-alpha re-anchoring, cgvae.py:569-571); bead CSR / ranks from build_segments."""
+    seg = ops.Segments(rowptr.shape[0] - 1, mapping, rowptr, atoms, None, rank)
+    return ops.lift_fwd(V.contiguous(), cg_xyz.contiguous(), seg, mode, pin)
+
+
+@lift.register_fake
+def _(V, cg_xyz, mapping, rank, rowptr, atoms, pin, mode):
+    return cg_xyz.new_empty((mapping.shape[0], 3))
+
+
+@custom_op(NS + "::lift_backward", mutates_args=(), device_types="cuda")
+def lift_backward(g: torch.Tensor, mapping: torch.Tensor, rank: torch.Tensor, rowptr: torch.Tensor, atoms: torch.Tensor,
+                  pin: Optional[torch.Tensor], mode: int, F: int) -> torch.Tensor:
+    seg = ops.Segments(rowptr.shape[0] - 1, mapping, rowptr, atoms, None, rank)
+    return ops.lift_bwd(g.contiguous(), seg, F, mode, pin)
+
+
+@lift_backward.register_fake
+def _(g, mapping, rank, rowptr, atoms, pin, mode, F):
+    return g.new_empty((rowptr.shape[0] - 1, 3, F))
+
+
+def _lift_setup(ctx, inputs, output):
+    V, cg_xyz, mapping, rank, rowptr, atoms, pin, mode = inputs
+    ctx.save_for_backward(mapping, rank, rowptr, atoms, pin)
+    ctx.mode, ctx.F = mode, V.shape[-1]
+
+
+def _lift_bwd(ctx, g):
+    mapping, rank, rowptr, atoms, pin = ctx.saved_tensors
+    return torch.ops.cgvae_b200.lift_backward(g, mapping, rank, rowptr, atoms, pin, ctx.mode, ctx.F), None, None, None, None, None, None, None
+
+
+register_autograd(NS + "::lift", _lift_bwd, setup_context=_lift_setup)
+
+
+# ------------------------------------------------------------------------------------------------ clip + Adam
+
+@custom_op(NS + "::adam_clip_step", mutates_args=("p", "m", "v", "step"), device_types="cuda")
+def adam_clip_step(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor, step: torch.Tensor, max_norm: float, lr: float,
+                   beta1: float, beta2: float, eps: float, grad_scale: float) -> None:
+    """clip_grad_norm_(max_norm) + Adam.step() (scripts/utils.py:151-157) on flat fp32 buffers, in place; step: float [1]."""
+    ops.adam_clip_step(p, g, m, v, step, max_norm, lr, betas=(beta1, beta2), eps=eps, grad_scale=grad_scale)
+
+
 OPS = ("radius_graph", "dense", "dense_backward", "mlp2", "mlp2_backward", "message_layer", "message_layer_backward", "segment_reduce",
-       "segment_reduce_backward")
+       "segment_reduce_backward", "message9_layer", "message9_layer_backward", "update_block", "update_block_backward", "lift",
+       "lift_backward", "adam_clip_step")

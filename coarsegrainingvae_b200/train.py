@@ -80,7 +80,7 @@ class FlatGrads(object):
     no flatten copy; the data-parallel all-reduce is ONE collective on ONE tensor and clipping is two passes over it.
     On CPU (tests) ``p.grad`` is pre-set to views and autograd accumulates in place."""
 
-    def __init__(self, params):
+    def __init__(self, params, align=4):
         self.params = [p for p in params]
         n = sum(p.numel() for p in self.params)
         dev = self.params[0].device if self.params else "cpu"
@@ -88,7 +88,9 @@ class FlatGrads(object):
         # storage = [ gradients (n) | pad to 16 bytes | loss slot ]: the loss of the step rides at the tail so that the
         # data-parallel all-reduce of ``buffer`` also sums the per-rank losses -- the skip guard of the reference loop
         # (scripts/utils.py:145-148) is then decided on the SAME all-reduced value on every rank
-        pad = (-n) % 4
+        # align: 4 floats (16 bytes), or 4 * world for the sharded optimiser (equal 16-byte aligned slices per rank)
+        pad = (-n) % align
+        self.n_padded = n + pad
         self.buffer = torch.zeros(n + pad + 4, dtype=dtype, device=dev)
         self.flat = self.buffer[:n]
         self.loss_slot = self.buffer[n + pad:n + pad + 1]
@@ -187,6 +189,23 @@ class TrainStep(object):
         # 8x the rows in the grouped kernel) while a ring all-reduce does not, so "auto" enables it for 2 ranks only;
         # CGVAE_GATHER_FACTORS=1 / 0 forces / disables it.
         self.gather_factors = os.environ.get("CGVAE_GATHER_FACTORS", "auto")
+        # data parallel, overlap: the decoder's parameters (83 % of the gradient bytes at chignolin) are laid out FIRST in the
+        # flat buffers; a hook on the latent's gradient fires when the backward pass leaves the decoder, and their
+        # all-reduce runs on a side stream while the encoder's backward (message + atom-level GEMM kernels) proceeds.
+        # Measured on 2 x B200 (chignolin, graph replay): plain all-reduce 3.30 ms per step, overlapped 3.64 ms (the NCCL
+        # kernel holds its SMs for the whole transfer and the encoder's backward slows down by more than the transfer
+        # takes: 270 MB move in 0.37 ms at 730 GB/s), factor exchange 3.46 ms -> overlap is opt-in (CGVAE_DP_OVERLAP=1).
+        self.dp_overlap = os.environ.get("CGVAE_DP_OVERLAP", "0") == "1"
+        # sharded optimiser (opt-in, CGVAE_SHARD_OPT=1): reduce-scatter of the flat gradient buffer, clip + Adam on this
+        # rank's 1/world slice (global norm and loss from a 1025-float all-reduce), all-gather of the parameters: the 0.35 ms
+        # HBM-bound optimiser pass (28 B per parameter) shrinks world-fold.  Measured on 2 x B200 (tools/nccl_micro.py, 270
+        # MB): all-reduce 543 us, reduce-scatter 347 + all-gather 321 us -- NCCL's all-reduce beats the pair by more than
+        # the optimiser saves (3.58 vs 3.30 ms per step), so the plain all-reduce stays the default.
+        self.shard_opt = os.environ.get("CGVAE_SHARD_OPT", "0") == "1"
+        self._adam_ws = None
+        self.n_overlap = 0
+        self._comm_stream = None
+        self._scope = None
         self.n_reduce = None            # floats at the head of the flat gradient buffer that still need the all-reduce
         self._arena = self._gathered = self._factor_table = None
         self._factor_layout = None
@@ -224,26 +243,38 @@ class TrainStep(object):
         params = [p for _, p in used]
         on_cuda = bool(params) and params[0].is_cuda
         want = self.gather_factors
-        want = (self._world() == 2) if want == "auto" else (want not in ("0", False, None))
+        overlap_ok = (self.dp_overlap and on_cuda and self.optimizer == "fused" and self._world() > 1
+                      and any(k.startswith("equivaraintconv.") for k, _ in used)
+                      and any(not k.startswith("equivaraintconv.") for k, _ in used))
+        want = False if want == "auto" else (want not in ("0", False, None))
         self.gather_factors = bool(want and on_cuda and self.optimizer == "fused" and self.defer_grads and self._world() > 1)
         if self.gather_factors:
             params = self._deferred_last(params, batch, eps)
+        elif overlap_ok:
+            dec = [p for k, p in used if k.startswith("equivaraintconv.")]
+            params = dec + [p for k, p in used if not k.startswith("equivaraintconv.")]
+            self.n_overlap = sum(p.numel() for p in dec)
+        world = self._world()
+        self.shard_opt = bool(self.shard_opt and on_cuda and self.optimizer == "fused" and world > 1
+                              and not self.gather_factors and not self.n_overlap)
+        align = 4 * world if self.shard_opt else 4
         if on_cuda and self.optimizer == "fused":
             # parameters of the used set become views of ONE buffer (same order as the gradient buffer): the optimiser
             # is then a single streaming pass.  Must happen before FlatGrads registers the sinks (keyed by data_ptr).
             n = sum(p.numel() for p in params)
-            self.flat_p = torch.empty(n, dtype=torch.float32, device=params[0].device)
+            self.flat_p = torch.zeros(n + ((-n) % align if self.shard_opt else 0), dtype=torch.float32, device=params[0].device)
             off = 0
             for p in params:
                 view = self.flat_p[off:off + p.numel()].view_as(p)
                 view.copy_(p.data)
                 p.data = view
                 off += p.numel()
-            self.exp_avg = torch.zeros_like(self.flat_p)
-            self.exp_avg_sq = torch.zeros_like(self.flat_p)
+            n_moment = self.flat_p.numel() // world if self.shard_opt else self.flat_p.numel()    # sharded: this rank's slice
+            self.exp_avg = torch.zeros(n_moment, dtype=torch.float32, device=params[0].device)
+            self.exp_avg_sq = torch.zeros(n_moment, dtype=torch.float32, device=params[0].device)
             self.step_count = torch.zeros(1, dtype=torch.float32, device=params[0].device)
             self.skipped = torch.zeros(1, dtype=torch.float32, device=params[0].device)
-        self.flat = FlatGrads(params)
+        self.flat = FlatGrads(params, align=align)
         fused = self.flat.flat.is_cuda
         if self.flat_p is None:
             self.opt = torch.optim.Adam(self.flat.params, lr=self.lr, fused=fused, capturable=bool(self.capturable and fused))
@@ -288,13 +319,41 @@ class TrainStep(object):
                     loss.backward()
                 self._pack_factors(scope.pending)
             else:
-                with ops.DeferredGrads():  # small-graph weight / bias gradients: recorded, then ONE grouped launch
-                    loss.backward()
+                with ops.DeferredGrads() as scope:  # small-graph weight / bias gradients: recorded, then ONE grouped launch
+                    self._scope = scope
+                    self._arm_overlap()
+                    try:
+                        loss.backward()
+                    finally:
+                        self._scope = None
+                        self.model._latent_grad_hook = None
         else:
             loss.backward()
         with torch.no_grad():
             self.flat.loss_slot.copy_(loss.detach().reshape(1))     # read by the skip guard (after the all-reduce)
         return loss
+
+    def _arm_overlap(self):
+        self._overlapped = False
+        if self.n_overlap and self._world() > 1 and getattr(self, "_exchange_follows", False):
+            self.model._latent_grad_hook = self._on_decoder_done
+
+    def _on_decoder_done(self, grad):
+        """autograd hook on the latent's gradient: every decoder node has run (they were created after the latent, so the
+        engine schedules them first).  Flush the deferred decoder weight gradients, then all-reduce the decoder block of
+        the flat buffer on the communication stream; the encoder's backward continues on the compute stream."""
+        import torch.distributed as dist
+        if self._overlapped or self._scope is None:
+            return None
+        self._overlapped = True
+        self._scope.flush_now()
+        cur = torch.cuda.current_stream()
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream()
+        self._comm_stream.wait_stream(cur)
+        with torch.cuda.stream(self._comm_stream):
+            dist.all_reduce(self.flat.buffer[:self.n_overlap], op=dist.ReduceOp.SUM, group=self.group)
+        return None
 
     def _pack_factors(self, pending):
         """copy gy / x of every deferred problem into one contiguous arena (one torch.cat) in a fixed layout; on the first
@@ -357,6 +416,20 @@ class TrainStep(object):
             dist.all_reduce(self.flat.loss_slot, op=dist.ReduceOp.SUM, group=self.group)
             dist.all_gather_into_tensor(self._gathered, self._arena, group=self.group)
             return
+        if self.shard_opt:
+            import torch.distributed as dist
+            cnt = self.flat.n_padded // self._world()
+            r = dist.get_rank(self.group)
+            dist.reduce_scatter_tensor(self.flat.buffer[r * cnt:(r + 1) * cnt], self.flat.buffer[:self.flat.n_padded],
+                                       op=dist.ReduceOp.SUM, group=self.group)
+            return
+        if getattr(self, "_overlapped", False):
+            # the decoder block is already in flight on the communication stream: reduce the rest (+ the loss slot), join
+            import torch.distributed as dist
+            self._overlapped = False
+            dist.all_reduce(self.flat.buffer[self.n_overlap:], op=dist.ReduceOp.SUM, group=self.group)
+            torch.cuda.current_stream().wait_stream(self._comm_stream)
+            return
         self.flat.allreduce_mean_(self.group, scale_in_optimizer=self.flat_p is not None)
 
     def apply_gradients(self):
@@ -365,6 +438,20 @@ class TrainStep(object):
             if self.gather_factors:        # every rank forms the SUM over ranks of the deferred gradients itself
                 ops.wgrad_grouped_table(self._factor_table, self._factor_out_floats)
             guard = self.loss_limit is not None
+            if self.shard_opt:
+                import torch.distributed as dist
+                world, r = self._world(), dist.get_rank(self.group)
+                cnt = self.flat.n_padded // world
+                g_sl, p_sl = self.flat.buffer[r * cnt:(r + 1) * cnt], self.flat_p[r * cnt:(r + 1) * cnt]
+                if self._adam_ws is None:
+                    self._adam_ws = ops.adam_ws(self.flat_p.device)
+                ops.grad_sumsq(g_sl, self.flat.loss_slot if guard else None, self._adam_ws)
+                dist.all_reduce(self._adam_ws[:1025], op=dist.ReduceOp.SUM, group=self.group)     # global norm^2 partials + loss
+                ops.adam_apply(p_sl, g_sl, self.exp_avg, self.exp_avg_sq, self.step_count, self.max_norm, self.lr, self._adam_ws,
+                               grad_scale=1.0 / world, use_ws_loss=guard, loss_scale=1.0 / world,
+                               loss_limit=self.loss_limit if guard else float("inf"), skipped=self.skipped)
+                dist.all_gather_into_tensor(self.flat_p, p_sl, group=self.group)
+                return
             ops.adam_clip_step(self.flat_p, self.flat.flat, self.exp_avg, self.exp_avg_sq, self.step_count, self.max_norm, self.lr,
                                grad_scale=1.0 / self._world(), loss=self.flat.loss_slot if guard else None,
                                loss_scale=1.0 / self._world(), loss_limit=self.loss_limit if guard else float("inf"),
@@ -392,7 +479,11 @@ class TrainStep(object):
         backward (the reference calls loss.backward() there too), no gradient exchange and no optimiser step."""
         if self._world() > 1 and "dp_norms" not in batch and not torch.cuda.is_current_stream_capturing():
             batch = self.update_dp_norms(dict(batch))
-        loss = self.forward_backward(batch, eps)
+        self._exchange_follows = bool(train)      # arms the overlapped all-reduce of the decoder block (data parallel)
+        try:
+            loss = self.forward_backward(batch, eps)
+        finally:
+            self._exchange_follows = False
         if train:
             self.exchange_gradients()
             self.apply_gradients()
@@ -565,7 +656,10 @@ class GraphedTrainStep(object):
         before = ops.launch_count()
         self.graph = torch.cuda.CUDAGraph()
         self.opt_graph = None
-        if not self.distributed:
+        if not self.distributed or trainer.n_overlap:
+            # one graph for the whole step.  Data parallel with overlap: the NCCL all-reduces are captured too -- the
+            # decoder block on the communication stream (forked and joined inside the capture), the rest on the compute
+            # stream (CGVAE_DP_OVERLAP=0: the two-graph form below with an eager all-reduce in between)
             with torch.cuda.graph(self.graph, stream=side):   # same stream as the warm-up: autograd's accumulate nodes match
                 self.loss = trainer.step(self.static, self.eps)
         else:
@@ -573,9 +667,12 @@ class GraphedTrainStep(object):
             # (forward+backward | clip+Adam); collectives inside a capture depend on process-group internals
             with torch.cuda.graph(self.graph, stream=side):
                 self.loss = trainer.forward_backward(self.static, self.eps)
-            self.opt_graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.opt_graph, stream=side, pool=self.graph.pool()):
-                trainer.apply_gradients()
+            if not trainer.shard_opt:
+                self.opt_graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.opt_graph, stream=side, pool=self.graph.pool()):
+                    trainer.apply_gradients()
+            # sharded optimiser: its three launches (norm partials, loss copy, update) sit between three collectives and
+            # stay ordinary stream work; the host enqueues them while the forward/backward graph is still running
         cur.wait_stream(side)
         self.launches_per_step = ops.launch_count() - before
 
@@ -606,12 +703,15 @@ class GraphedTrainStep(object):
     def step(self, batch):
         """batch: a dict from ``to_static_batch`` (one copy per key) or its ``pack``ed form (one copy)."""
         self.load(batch)
-        if self.opt_graph is not None:
+        if self.distributed:
             self.trainer.update_dp_norms(self.static)          # tiny all-reduce of the (atoms, beads, bonds) counts
         self.graph.replay()
         if self.opt_graph is not None:
             self.trainer.exchange_gradients()
             self.opt_graph.replay()
+        elif self.distributed and not self.trainer.n_overlap:
+            self.trainer.exchange_gradients()
+            self.trainer.apply_gradients()
         return self.loss
 
 

@@ -297,6 +297,14 @@ int cgvae_adam_clip_step(float* p, const float* g, float* m, float* v, int64_t n
                          float lr, float beta1, float beta2, float eps, float* step, float* norm_out,
                          const float* loss, float loss_scale, float loss_limit, float* skipped, void* ws,
                          size_t ws_bytes, cgvae_stream_t stream);
+/* The same update for a data-parallel run that shards the optimiser (reduce-scatter of the gradients, Adam on this rank's
+ * 1/world slice, all-gather of the parameters): cgvae_grad_sumsq leaves the 1024 partial sums of squares of the local slice
+ * in ws[0..1024) and a copy of loss[0] in ws[1024]; the caller all-reduces (SUM) the 1025 floats; cgvae_adam_apply then clips
+ * with the GLOBAL norm, applies the skip guard on ws[1024] * loss_scale (use_ws_loss != 0) and updates the slice. */
+int cgvae_grad_sumsq(const float* g, int64_t n, const float* loss, void* ws, size_t ws_bytes, cgvae_stream_t stream);
+int cgvae_adam_apply(float* p, const float* g, float* m, float* v, int64_t n, float max_norm, float grad_scale, float lr, float beta1,
+                     float beta2, float eps, float* step, float* norm_out, int use_ws_loss, float loss_scale, float loss_limit,
+                     float* skipped, void* ws, size_t ws_bytes, cgvae_stream_t stream);
 
 /* ------------------------------------------------------------------ losses and the VAE latent
 

@@ -48,6 +48,7 @@ ref = {k: p.grad.detach().clone() for k, p in ref_model.named_parameters() if p.
 
 worst_all = 0.0
 modes = ["0", "1"] if world == 2 else ["0"]
+os.environ["CGVAE_SHARD_OPT"] = "0"          # this section reads the fully reduced gradient buffer on every rank
 for mode in modes:
     os.environ["CGVAE_GATHER_FACTORS"] = mode
     model = make()
@@ -83,11 +84,66 @@ for mode in modes:
             solo.forward_backward(global_batch, eps_global)
             solo.apply_gradients()
         named_solo = dict(ref_model.named_parameters())
-        rel = max(float((p - named_solo[k]).abs().max() / named_solo[k].abs().max().clamp_min(1e-30))
-                  for k, p in model.named_parameters() if k in ref)
-        assert rel < 1e-4, rel
+        # Adam divides by sqrt(v): an entry whose gradient sits at rounding-noise level moves by up to lr per step in EITHER
+        # run, so the gate is the relative L2 distance of the whole parameter vector plus a bound on the largest single
+        # deviation as a fraction of the largest possible movement (3 steps x lr); the 1e-5 gradient gate above is the
+        # parity statement proper
+        num = sum(float((p.detach() - named_solo[k].detach()).double().pow(2).sum()) for k, p in model.named_parameters() if k in ref)
+        den = sum(float(named_solo[k].detach().double().pow(2).sum()) for k in ref)
+        dmax = max(float((p.detach() - named_solo[k].detach()).abs().max()) for k, p in model.named_parameters() if k in ref)
+        assert (num / den) ** 0.5 < 1e-4, (num / den) ** 0.5
+        assert dmax < 0.1 * 3 * 1e-3, dmax
         solo.flat.release()
     tr.flat.release()
+
+# the whole step as CUDA graph replays: overlapped exchange (decoder block all-reduced on the communication stream while the
+# encoder's backward runs, NCCL captured inside the graph) == the two-graph form with one eager all-reduce in between
+from coarsegrainingvae_b200.train import GraphedTrainStep, to_static_batch
+cpu_local = cg.CG_collate(samples[rank::world])
+caps = {"nbr_list": cpu_local["nbr_list"].shape[0] + 64, "CG_nbr_list": cpu_local["CG_nbr_list"].shape[0] + 8,
+        "bond_edge_list": cpu_local["bond_edge_list"].shape[0] + 16}
+cap_t = torch.tensor([caps["nbr_list"], caps["CG_nbr_list"], caps["bond_edge_list"]], device=dev)
+dist.all_reduce(cap_t, op=dist.ReduceOp.MAX)
+caps = dict(zip(("nbr_list", "CG_nbr_list", "bond_edge_list"), [int(x) for x in cap_t.tolist()]))
+static_local = to_dev(to_static_batch(cpu_local, caps))
+finals = {}
+for overlap in ("0", "1", "shard"):
+    # "0": one all-reduce between two graphs; "1": overlapped decoder block, NCCL captured; "shard": reduce-scatter ->
+    # Adam on 1/world of the buffers -> all-gather of the parameters (the default)
+    os.environ["CGVAE_DP_OVERLAP"] = "1" if overlap == "1" else "0"
+    os.environ["CGVAE_SHARD_OPT"] = "1" if overlap == "shard" else "0"
+    os.environ["CGVAE_GATHER_FACTORS"] = "0"
+    model = make()
+    init = {k: p.detach().clone() for k, p in model.named_parameters()}
+    tr = TrainStep(model, cfg["beta"], cfg["gamma"], lr=1e-3, capturable=True)
+    sb = tr.update_dp_norms(dict(static_local))
+    tr.prepare(sb, eps_local)
+    assert (tr.n_overlap > 0) == (overlap == "1") and tr.shard_opt == (overlap == "shard")
+    graphed = GraphedTrainStep(tr, sb, eps_local)
+    with torch.no_grad():                                   # undo the warm-up steps of the capture
+        for k, p in model.named_parameters():
+            p.copy_(init[k])
+        tr.exp_avg.zero_(); tr.exp_avg_sq.zero_(); tr.step_count.zero_()
+        if tr.flat_p.numel() > tr.flat.flat.numel():
+            tr.flat_p[tr.flat.flat.numel():].zero_()
+    losses = [float(graphed.step(static_local)) for _ in range(3)]
+    torch.cuda.synchronize()
+    finals[overlap] = ({k: p.detach().clone() for k, p in model.named_parameters()}, losses)
+    graphed = None
+    tr.flat.release()
+pa, la = finals["0"]
+for other in ("1", "shard"):
+    pb, lb_ = finals[other]
+    num = sum(float((pa[k] - pb[k]).double().pow(2).sum()) for k in pa)
+    den = sum(float(pa[k].double().pow(2).sum()) for k in pa)
+    assert (num / den) ** 0.5 < 1e-5, (other, "vs plain exchange", (num / den) ** 0.5)
+    assert max(abs(x - y) for x, y in zip(la, lb_)) <= 1e-5 * max(abs(x) for x in la), (other, la, lb_)
+    # every rank holds the same parameters
+    chk = torch.stack([sum(p.double().sum() for p in pb.values()), sum(p.double().abs().sum() for p in pb.values())])
+    allc = [torch.zeros_like(chk) for _ in range(world)]
+    dist.all_gather(allc, chk)
+    assert all(torch.equal(allc[0], c) for c in allc), (other, "parameters diverged across ranks")
+os.environ.pop("CGVAE_DP_OVERLAP"); os.environ.pop("CGVAE_SHARD_OPT")
 
 # ensemble members sharded over the ranks + all_gather == the single-device loop, member by member
 model = make()

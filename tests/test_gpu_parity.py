@@ -550,6 +550,97 @@ def test_torch_library_ops_match_autograd_nodes():
     torch.library.opcheck(T.mlp2.default, tuple(t.detach().requires_grad_() for t in ps) + (1,), test_utils=checks)
 
 
+def test_torch_library_ops_round2():
+    """the remaining entry points behind the dispatcher: contraction (message_layer on the atoms -> beads graph), 9-split
+    layer, update block, lifting, clip + Adam -- each equal to the autograd node / raw kernels the models use (bitwise:
+    same kernels in the same order) and passing opcheck."""
+    from coarsegrainingvae_b200 import functions, torch_ops  # noqa: F401
+    T = torch.ops.cgvae_b200
+    g = torch.Generator().manual_seed(33)
+    rn = lambda *sh: torch.randn(*sh, generator=g).to(DEV)
+    checks = ("test_schema", "test_faketensor", "test_autograd_registration")
+    n, nb, F, R = 120, 12, 64, 8
+    xyz, cg_xyz = rn(n, 3) * 3.0, rn(nb, 3) * 3.0
+    mapping = torch.sort(torch.randint(0, nb, (n,), generator=g))[0].to(DEV)
+    seg = ops.build_segments(mapping, nb)
+    # contraction: receivers = beads, senders = atoms, residual state on the receiver set (conv.py:703-733)
+    cgraph = ops.contraction_graph(seg)
+    cgeom = ops.edge_geometry(cgraph, xyz, cg_xyz, R, 6.0)
+    phi, v = rn(n, 3, F).requires_grad_(), rn(n, 3, F).requires_grad_()
+    Wf, bf = (rn(3 * F, R) * 0.1).requires_grad_(), (rn(3 * F) * 0.1).requires_grad_()
+    H, V = rn(nb, F).requires_grad_(), rn(nb, 3, F).requires_grad_()
+    o_s, o_v, _ = T.message_layer(3, phi, v, cgraph.rowptr, cgraph.col, cgraph.rowptr_t, cgraph.col_t, cgraph.perm_t, cgeom.basis,
+                                  cgeom.unit, Wf, bf, H, V, R)
+    w_s, w_v, _ = ops.message_fwd(3, phi.detach(), v.detach(), None, cgeom, Wf.detach(), bf.detach(), H.detach(), V.detach())
+    assert o_s.shape == (nb, F) and torch.equal(o_s, w_s) and torch.equal(o_v, w_v)
+    gs, gv = rn(nb, F), rn(nb, 3, F)
+    torch.autograd.backward([o_s, o_v], [gs, gv])
+    g_phi, g_vs, dWf, dbf = ops.message_bwd(3, phi.detach(), v.detach(), None, None, cgeom, Wf.detach(), bf.detach(), gs, gv, False,
+                                            sink=False)
+    assert torch.equal(phi.grad, g_phi) and torch.equal(v.grad, g_vs) and torch.equal(Wf.grad, dWf) and torch.equal(H.grad, gs)
+    # 9-split layer on the bead graph == functions.Message9Block minus its phi-MLP
+    pairs = ops.radius_graph(cg_xyz, 50.0)
+    gr = ops.build_graph(pairs, nb, symmetrize=True)
+    geom = ops.edge_geometry(gr, cg_xyz, cg_xyz, R, 50.0)
+    ins = [rn(nb, 9, F), rn(nb, F), rn(nb, F), rn(nb, 3, F), rn(nb, 3, F), rn(9 * F, R) * 0.1, rn(9 * F) * 0.1]
+    a = [t.clone().requires_grad_() for t in ins]
+    outs = T.message9_layer(a[0], a[1], a[2], a[3], a[4], gr.rowptr, gr.col, gr.rowptr_t, gr.col_t, gr.perm_t, geom.basis, geom.unit,
+                            a[5], a[6], True, R)
+    want = ops.message9_fwd(*ins[:5], geom, ins[5], ins[6], True)
+    gouts = [rn(nb, F), rn(nb, F), rn(nb, 3, F), rn(nb, 3, F)]
+    torch.autograd.backward(list(outs), gouts)
+    wb = ops.message9_bwd(*ins[:5], geom, ins[5], ins[6], True, *gouts)
+    torch.cuda.synchronize()
+    assert all(torch.equal(x, y) for x, y in zip(outs, want))
+    for got, ref in zip((a[1].grad, a[2].grad, a[3].grad, a[4].grad, a[0].grad, a[5].grad, a[6].grad), wb):
+        assert rel_err(got, ref) <= 1e-6
+    # update block == functions.UpdateBlockFn
+    ps = [rn(n, F), rn(n, 3, F), rn(F, F) * 0.1, rn(F, F) * 0.1, rn(F, 2 * F) * 0.1, rn(F), rn(3 * F, F) * 0.1, rn(3 * F)]
+    a = [t.clone().requires_grad_() for t in ps]
+    c = [t.clone().requires_grad_() for t in ps]
+    gs, gv = rn(n, F), rn(n, 3, F)
+    o = T.update_block(*a, 1, True)
+    torch.autograd.backward([o[0], o[1]], [gs, gv])
+    w = functions.UpdateBlockFn.apply(True, 1, *c)
+    torch.autograd.backward(list(w), [gs, gv])
+    torch.cuda.synchronize()
+    assert torch.equal(o[0], w[0]) and torch.equal(o[1], w[1])
+    for u, x in zip(a, c):
+        assert rel_err(u.grad, x.grad) <= 1e-6
+    # lifting == functions.Lift (all three modes)
+    pin = torch.zeros(n, dtype=torch.uint8, device=DEV)
+    pin[::7] = 1
+    for mode in (0, 1, 2):
+        Vb = rn(nb, 3, F).requires_grad_()
+        Vc = Vb.detach().clone().requires_grad_()
+        got = T.lift(Vb, cg_xyz, seg.mapping, seg.rank, seg.rowptr, seg.atoms, pin if mode == 2 else None, mode)
+        ref = functions.Lift.apply(seg, mode, pin if mode == 2 else None, Vc, cg_xyz)
+        gx = rn(n, 3)
+        got.backward(gx)
+        ref.backward(gx)
+        assert torch.equal(got, ref) and torch.equal(Vb.grad, Vc.grad)
+    # clip + Adam (mutating op) == ops.adam_clip_step
+    m = 10007
+    p0, g0 = rn(m), rn(m) * 1e-2
+    bufs_a = [p0.clone(), torch.zeros(m, device=DEV), torch.zeros(m, device=DEV), torch.zeros(1, device=DEV)]
+    bufs_b = [t.clone() for t in bufs_a]
+    for _ in range(3):
+        T.adam_clip_step(bufs_a[0], g0, bufs_a[1], bufs_a[2], bufs_a[3], 0.01, 1e-3, 0.9, 0.999, 1e-8, 1.0)
+        ops.adam_clip_step(bufs_b[0], g0, bufs_b[1], bufs_b[2], bufs_b[3], 0.01, 1e-3)
+    assert all(torch.equal(x, y) for x, y in zip(bufs_a, bufs_b)) and float(bufs_a[3]) == 3.0
+    # dispatcher-level checks
+    torch.library.opcheck(T.update_block.default, tuple(t.detach().requires_grad_() for t in ps) + (1, True), test_utils=checks)
+    torch.library.opcheck(T.lift.default, (rn(nb, 3, F).requires_grad_(), cg_xyz, seg.mapping, seg.rank, seg.rowptr, seg.atoms, None, 1),
+                          test_utils=checks)
+    torch.library.opcheck(T.message9_layer.default,
+                          tuple(t.detach().requires_grad_() for t in ins[:5]) + (gr.rowptr, gr.col, gr.rowptr_t, gr.col_t, gr.perm_t,
+                                                                                 geom.basis, geom.unit, ins[5].requires_grad_(),
+                                                                                 ins[6].requires_grad_(), True, R), test_utils=checks)
+    torch.library.opcheck(T.adam_clip_step.default, (p0.clone(), g0, torch.zeros(m, device=DEV), torch.zeros(m, device=DEV),
+                                                     torch.zeros(1, device=DEV), 0.01, 1e-3, 0.9, 0.999, 1e-8, 1.0),
+                          test_utils=("test_schema", "test_faketensor"))
+
+
 def test_graphed_sampler_matches_eager_members():
     """train.GraphedSampler (prior + n_ensemble decoder passes of scripts/sampling.py:265-284 as one CUDA graph over
     static-capacity inputs) reproduces the eager member-by-member geometries for the same noise, for conformations
