@@ -579,13 +579,35 @@ def run_cuda(args, cfg):
 
     # ---- where the step time goes: CUPTI kernel timeline of graph replays (torch.profiler), grouped into kernel families
     families, fam_launches, timeline_note = {}, {}, None
+    ms_no_pdl = None
+    pdl_was_on = ops.set_pdl(False)
     try:
-        families, fam_launches, span_us = _family_shares(lambda i: run_step(i % args.pool), 3)
-        timeline_note = ("torch.profiler (CUPTI) over 3 %s; share = sum of the family's kernel durations / sum of all kernel "
+        # Programmatic dependent launch (on in the timed runs above) makes a dependent grid resident while it still waits for
+        # its predecessor, so a profiler's per-kernel durations overlap and overstate every family.  The timeline is
+        # therefore taken from a SECOND capture of the same step with PDL off (its step time is reported next to it).
+        timeline_step = run_step
+        if use_graph and pdl_was_on and world == 1:
+            graphed_tl = GraphedTrainStep(trainer, dev_batches[0], eps)
+            timeline_step = lambda i: graphed_tl.step(packed_dev[i])
+            for i in range(3):
+                timeline_step(i % args.pool)
+            sync_all()
+            e0.record()
+            for i in range(args.steps):
+                timeline_step(i % args.pool)
+            e1.record()
+            sync_all()
+            ms_no_pdl = e0.elapsed_time(e1) / max(args.steps, 1)
+        families, fam_launches, span_us = _family_shares(lambda i: timeline_step(i % args.pool), 3)
+        timeline_note = ("torch.profiler (CUPTI) over 3 %s%s; share = sum of the family's kernel durations / sum of all kernel "
                          "durations of a step (%.0f us; branches of the captured graph overlap, so the sum exceeds ms_per_step)"
-                         % ("graph replays" if use_graph else "eager steps", span_us))
+                         % ("graph replays" if use_graph else "eager steps",
+                            (" of a second capture WITHOUT programmatic dependent launch (%.3f ms per step; the timed runs use PDL: "
+                             "weight copies of the streaming GEMMs start before the dependency wait)" % ms_no_pdl) if ms_no_pdl else "",
+                            span_us))
     except Exception as exc:                        # the timeline is evidence, not a dependency of the headline number
         timeline_note = "unavailable: %r" % (exc,)
+    ops.set_pdl(pdl_was_on)
 
     # ---- algorithmic work of one step per family: shapes recorded during ONE eager step of the same workload
     ops.TIMER = ops.KernelTimer(["gemm", "wgrad_grouped", "message_fwd", "message_bwd", "adam_clip"], keep_operands=False)

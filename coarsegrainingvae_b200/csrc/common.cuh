@@ -76,6 +76,8 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
   } while (0)
 
 bool pdl_enabled();
+// inside a parameter range registered with cgvae_register_const_range, and PDL on (gemm_stream.cu)
+bool weights_are_constant(const void* p, size_t bytes);
 
 template <typename... KArgs, typename... Args>
 inline void launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {

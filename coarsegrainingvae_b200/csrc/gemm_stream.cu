@@ -20,6 +20,8 @@
 #include "common.cuh"
 #include <cooperative_groups.h>
 #include <cuda.h>
+#include <algorithm>
+#include <vector>
 
 namespace cgvae {
 
@@ -137,8 +139,10 @@ constexpr uint32_t kBulkPiece = 32768;   // bytes per bulk copy of a contiguous 
 template <int MR, int RW>
 __global__ void __launch_bounds__(MR > 16 ? 256 : 512) gemm_nt_stream_kernel(
     const float* __restrict__ X, int64_t ldx, const float* __restrict__ W, int64_t ldw, float* __restrict__ C, int64_t ldc,
-    int M, int N, int K, int rows_per_cta, StreamEpilogue ep) {
-  CGVAE_KERNEL_PROLOGUE();
+    int M, int N, int K, int rows_per_cta, StreamEpilogue ep, int w_const) {
+  // w_const: the weight matrix is not written by any kernel still in flight (a registered parameter range): its bulk copies
+  // are issued BEFORE griddepcontrol.wait, i.e. while the preceding kernel is still running (programmatic dependent launch)
+  if (!w_const) CGVAE_KERNEL_PROLOGUE();
   extern __shared__ __align__(128) float smem[];
   constexpr int NV = RW * MR;
   float* Xs = smem;                                   // [MR][K]
@@ -167,6 +171,7 @@ __global__ void __launch_bounds__(MR > 16 ? 256 : 512) gemm_nt_stream_kernel(
     } else {
       for (int r = 0; r < rows; ++r) bulk_g2s(Ws + (size_t)r * K, W + (int64_t)(row0 + r) * ldw, row_bytes, bar);
     }
+    if (w_const) pdl_wait();              // the activations ARE produced by the preceding kernel
     if (ldx == K) {
       const char* src = reinterpret_cast<const char*>(X);
       char* dst = reinterpret_cast<char*>(Xs);
@@ -176,6 +181,7 @@ __global__ void __launch_bounds__(MR > 16 ? 256 : 512) gemm_nt_stream_kernel(
       for (int m = 0; m < M; ++m) bulk_g2s(Xs + (size_t)m * K, X + (int64_t)m * ldx, row_bytes, bar);
     }
   }
+  if (w_const) CGVAE_KERNEL_PROLOGUE();     // every thread: the epilogue operands / the output belong to the dependency chain
   bar_wait(bar, 0);
 
   const int nchunks = (K + 127) / 128;
@@ -236,8 +242,8 @@ template <> struct VecT<4> { using type = float4; };
 template <int MR, int VEC, int NW>
 __global__ void __launch_bounds__(NW * 32) gemm_nn_stream_kernel(
     const __grid_constant__ CUtensorMap wmap, const float* __restrict__ G, int64_t ldg, float* __restrict__ C, int64_t ldc,
-    int M, int N, int K, int k_per_cta, int box_rows, StreamEpilogue ep) {
-  CGVAE_KERNEL_PROLOGUE();
+    int M, int N, int K, int k_per_cta, int box_rows, StreamEpilogue ep, int w_const) {
+  if (!w_const) CGVAE_KERNEL_PROLOGUE();     // w_const: see gemm_nt_stream_kernel
   namespace cg = cooperative_groups;
   using vec_t = typename VecT<VEC>::type;
   constexpr int COLS = 32 * VEC;         // output columns per CTA = inner box extent
@@ -268,6 +274,7 @@ __global__ void __launch_bounds__(NW * 32) gemm_nn_stream_kernel(
       }
     }
   }
+  if (w_const) CGVAE_KERNEL_PROLOGUE();
   // G^T for this CTA's slice of the contraction (plain loads; overlaps with the weight panel in flight)
   for (int idx = tid; idx < MR * cnt; idx += NW * 32) {
     const int m = idx / cnt, j = idx - m * cnt;
@@ -352,9 +359,31 @@ static EncodeTiledFn encode_tiled_fn() {
 
 constexpr size_t kMaxStreamSmem = 220 * 1024;
 
+// Parameter ranges registered by the host (cgvae_register_const_range: the flat parameter buffer of a training step): memory
+// that no kernel writes between two optimiser steps.  A weight matrix inside such a range may be fetched before the
+// dependency wait of a programmatic dependent launch -- its bulk copies then overlap with the tail of the preceding kernel
+// instead of starting after it.  The optimiser is the only writer; every kernel between it and the first weight-streaming
+// launch of the next step runs its own griddepcontrol.wait before triggering its dependents, so the chain of completed
+// grids always includes the optimiser.
+struct ConstRange {
+  uintptr_t begin, end;
+};
+static std::vector<ConstRange> g_const_ranges;     // sorted by begin, disjoint (host-side, launch thread only)
+
+bool weights_are_constant(const void* p, size_t bytes) {
+  if (!pdl_enabled() || g_const_ranges.empty()) return false;
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  auto it = std::upper_bound(g_const_ranges.begin(), g_const_ranges.end(), a,
+                             [](uintptr_t v, const ConstRange& r) { return v < r.begin; });
+  if (it == g_const_ranges.begin()) return false;
+  --it;
+  return a >= it->begin && a + bytes <= it->end;
+}
+
 template <int MR, int RW>
 static bool launch_nt(const float* X, int64_t ldx, const float* W, int64_t ldw, float* C, int64_t ldc, int M, int N, int K,
                       const StreamEpilogue& ep, cudaStream_t st) {
+  const int w_const = weights_are_constant(W, sizeof(float) * ((size_t)(N - 1) * (size_t)ldw + (size_t)K)) ? 1 : 0;
   int rpc = (int)ceil_div(ceil_div(N, kNumSM), RW) * RW;       // one CTA per SM, whole tasks
   const size_t smem = sizeof(float) * ((size_t)MR * K + (size_t)rpc * K) + 16;
   if (smem > kMaxStreamSmem) return false;
@@ -369,13 +398,14 @@ static bool launch_nt(const float* X, int64_t ldx, const float* W, int64_t ldw, 
   const int tasks = rpc / RW;
   const int nwarps = tasks <= 2 ? 2 : (tasks <= 4 ? 4 : ((tasks <= 8 || MR > 16) ? 8 : 16));
   launch_kernel(gemm_nt_stream_kernel<MR, RW>, dim3((unsigned)ceil_div(N, rpc)), dim3(nwarps * 32), smem, st, X, ldx, W, ldw, C, ldc, M,
-                N, K, rpc, ep);
+                N, K, rpc, ep, w_const);
   return true;
 }
 
 template <int MR, int VEC, int NW>
 static bool launch_nn(const float* G, int64_t ldg, const float* W, int64_t ldw, float* C, int64_t ldc, int M, int N, int K,
                       const StreamEpilogue& ep, cudaStream_t st) {
+  const int w_const = weights_are_constant(W, sizeof(float) * ((size_t)(K - 1) * (size_t)ldw + (size_t)N)) ? 1 : 0;
   constexpr int COLS = 32 * VEC;
   EncodeTiledFn encode = encode_tiled_fn();
   if (encode == nullptr) return false;
@@ -421,7 +451,7 @@ static bool launch_nn(const float* G, int64_t ldg, const float* W, int64_t ldw, 
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  (void)cudaLaunchKernelEx(&cfg, gemm_nn_stream_kernel<MR, VEC, NW>, map, G, ldg, C, ldc, M, N, K, k_per_cta, box_rows, ep);
+  (void)cudaLaunchKernelEx(&cfg, gemm_nn_stream_kernel<MR, VEC, NW>, map, G, ldg, C, ldc, M, N, K, k_per_cta, box_rows, ep, w_const);
   return true;
 }
 
@@ -470,3 +500,30 @@ int launch_dense_pair_stream(const float* X, int64_t ldx, const float* W, int64_
 }
 
 }  // namespace cgvae
+
+extern "C" {
+
+int cgvae_register_const_range(const void* p, size_t bytes) {
+  using namespace cgvae;
+  if (p == nullptr || bytes == 0) {        // clear
+    g_const_ranges.clear();
+    return 0;
+  }
+  ConstRange r{reinterpret_cast<uintptr_t>(p), reinterpret_cast<uintptr_t>(p) + bytes};
+  // insert, merging every range that overlaps or touches the new one
+  std::vector<ConstRange> out;
+  out.reserve(g_const_ranges.size() + 1);
+  for (const ConstRange& q : g_const_ranges) {
+    if (q.end < r.begin || q.begin > r.end) out.push_back(q);
+    else {
+      r.begin = std::min(r.begin, q.begin);
+      r.end = std::max(r.end, q.end);
+    }
+  }
+  out.push_back(r);
+  std::sort(out.begin(), out.end(), [](const ConstRange& x, const ConstRange& y) { return x.begin < y.begin; });
+  g_const_ranges.swap(out);
+  return 0;
+}
+
+}  // extern "C"

@@ -134,8 +134,10 @@ template <bool A_KC, bool B_KC>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                  const __grid_constant__ CUtensorMap map_b, float* __restrict__ C,
                                                                  int64_t ldc, int64_t M, int64_t N, int64_t K, int kt_per_split, Ep ep,
-                                                                 int split_mode, int cluster_size, float* __restrict__ partial) {
-  CGVAE_KERNEL_PROLOGUE();
+                                                                 int split_mode, int cluster_size, float* __restrict__ partial, int b_const) {
+  // b_const: B is a weight matrix inside a registered parameter range -- the producer issues its first tiles BEFORE the
+  // dependency wait of the programmatic dependent launch (they overlap with the preceding kernel), A follows the wait
+  if (!b_const) CGVAE_KERNEL_PROLOGUE();
   extern __shared__ __align__(1024) char smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte aligned bases: add the (runtime) pad to the extern array, not to an integer
   char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -174,6 +176,26 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_sh;
   const uint32_t smem_base = smem_u32(smem);
+  const int npre = b_const ? min(nkt, STAGES) : 0;
+  if (b_const) {
+    if (warp == NUM_SPLIT_WARPS) {
+      if (elect_one()) {
+        for (int i = 0; i < npre; ++i) {
+          const int k0 = (kt0 + i) * BK;
+          const uint32_t b_dst = smem_base + (uint32_t)i * STAGE_BYTES + A_BYTES;
+          mbar_expect_tx(&raw_full[i], RAW_BYTES);
+          if (B_KC) {
+            tma_2d(b_dst, &map_b, k0, (int)n0, &raw_full[i]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 32; ++j) tma_2d(b_dst + (uint32_t)j * 4096u, &map_b, (int)n0 + 32 * j, k0, &raw_full[i]);
+          }
+        }
+      }
+      __syncwarp();
+    }
+    CGVAE_KERNEL_PROLOGUE();
+  }
 
   if (warp < NUM_SPLIT_WARPS) {
     // ---------------- lo pass: raw tile -> lo tile, same physical offset (the swizzle is irrelevant element-wise) ----------
@@ -222,18 +244,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
       if (elect_one()) {
         const int k0 = (kt0 + i) * BK;
         const uint32_t a_dst = smem_base + (uint32_t)s * STAGE_BYTES, b_dst = a_dst + A_BYTES;
-        mbar_expect_tx(&raw_full[s], RAW_BYTES);
+        if (i >= npre) mbar_expect_tx(&raw_full[s], RAW_BYTES);
         if (A_KC) {
           tma_2d(a_dst, &map_a, k0, (int)m0, &raw_full[s]);
         } else {
 #pragma unroll
           for (int j = 0; j < BM / 32; ++j) tma_2d(a_dst + (uint32_t)j * 4096u, &map_a, (int)m0 + 32 * j, k0, &raw_full[s]);
         }
-        if (B_KC) {
-          tma_2d(b_dst, &map_b, k0, (int)n0, &raw_full[s]);
-        } else {
+        if (i >= npre) {
+          if (B_KC) {
+            tma_2d(b_dst, &map_b, k0, (int)n0, &raw_full[s]);
+          } else {
 #pragma unroll
-          for (int j = 0; j < BN / 32; ++j) tma_2d(b_dst + (uint32_t)j * 4096u, &map_b, (int)n0 + 32 * j, k0, &raw_full[s]);
+            for (int j = 0; j < BN / 32; ++j) tma_2d(b_dst + (uint32_t)j * 4096u, &map_b, (int)n0 + 32 * j, k0, &raw_full[s]);
+          }
         }
       }
       __syncwarp();
@@ -413,6 +437,8 @@ int launch_gemm_tcgen05(int form, const float* A, int64_t lda, const float* B, i
   // K-contiguous operand: inner = K, outer = rows, box [128 rows][32 k]; MN-contiguous: inner = rows, outer = K, box [32 k][32 mn]
   if (!(a_kc ? tc::encode_map(&map_a, A, K, M, lda, tc::BM, true) : tc::encode_map(&map_a, A, M, K, lda, tc::BK, false))) return 0;
   if (!(b_kc ? tc::encode_map(&map_b, B, K, N, ldb, tc::BN, true) : tc::encode_map(&map_b, B, N, K, ldb, tc::BK, false))) return 0;
+  const int b_const = (form != CGVAE_GEMM_TN &&
+                       weights_are_constant(B, sizeof(float) * (size_t)(((b_kc ? N : K) - 1) * ldb + (b_kc ? K : N)))) ? 1 : 0;
   tc::Ep ep{bias, act, z_out, z_in, dact, add};
   if (groups > 1) ep = tc::Ep{nullptr, 0, nullptr, nullptr, 0, nullptr};
   float* partial = groups > 1 ? ws : nullptr;
@@ -436,7 +462,7 @@ int launch_gemm_tcgen05(int form, const float* A, int64_t lda, const float* B, i
       cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
       attr_done[idx] = true;
     }
-    (void)cudaLaunchKernelEx(&cfg, kernel, map_a, map_b, C, ldc, M, N, K, kps, ep, split_mode, S, partial);
+    (void)cudaLaunchKernelEx(&cfg, kernel, map_a, map_b, C, ldc, M, N, K, kps, ep, split_mode, S, partial, b_const);
   };
   if (a_kc && b_kc) go(tc::gemm_tc_kernel<true, true>, 0);
   else if (a_kc) go(tc::gemm_tc_kernel<true, false>, 1);

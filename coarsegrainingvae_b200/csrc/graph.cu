@@ -9,14 +9,20 @@ thread_local char g_err[512] = {0};
 std::atomic<unsigned long long> g_launches{0};
 std::atomic<int32_t*> g_err_flags[kMaxDevices];
 
+// Programmatic dependent launch: on by default since round 2.  On its own it changed the captured step by < 1 % (dependent-node
+// gaps are ~0.35 us already); what pays is what it enables: the weight-streaming GEMMs issue the bulk copies of a registered
+// parameter matrix BEFORE their dependency wait (gemm_stream.cu), 2.93 -> 2.81 ms per chignolin step.  It inflates the
+// per-kernel durations a profiler reports (a dependent grid is resident while it waits), so bench.py takes its kernel timeline
+// from a second capture with cgvae_set_pdl(0).  CGVAE_PDL=0 disables it.
+static std::atomic<int> g_pdl{-1};
 bool pdl_enabled() {
-  static const bool on = [] {
-    // opt-in: measured on B200 inside the captured step, dependent-node gaps are already ~0.35 us (median) and PDL
-    // changed the step time by < 1 %, while it inflates per-kernel durations in profiles
+  int v = g_pdl.load(std::memory_order_relaxed);
+  if (v < 0) {
     const char* e = getenv("CGVAE_PDL");
-    return e && e[0] == '1';
-  }();
-  return on;
+    v = (e && e[0] == '0') ? 0 : 1;
+    g_pdl.store(v, std::memory_order_relaxed);
+  }
+  return v != 0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -489,6 +495,12 @@ extern "C" {
 int cgvae_abi_version(void) { return CGVAE_ABI_VERSION; }
 const char* cgvae_last_error(void) { return g_err; }
 unsigned long long cgvae_launch_count(void) { return g_launches.load(); }
+int cgvae_set_pdl(int on) {
+  const int prev = cgvae::pdl_enabled() ? 1 : 0;
+  cgvae::g_pdl.store(on ? 1 : 0, std::memory_order_relaxed);
+  return prev;
+}
+
 int cgvae_set_error_flags(int device, int32_t* flags) {
   CGVAE_REQUIRE(device >= 0 && device < kMaxDevices, "set_error_flags: bad device %d", device);
   g_err_flags[device].store(flags);

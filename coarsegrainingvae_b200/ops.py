@@ -953,6 +953,28 @@ def adam_clip_step(p, g, m, v, step, max_norm, lr, betas=(0.9, 0.999), eps=1e-8,
         TIMER.end("adam_clip", t0, dict(n=p.numel()))
 
 
+def set_pdl(on):
+    """programmatic dependent launch on / off for subsequent launches; returns the previous setting."""
+    return bool(_lib.load().cgvae_set_pdl(int(bool(on))))
+
+
+def register_const_range(t):
+    """declare a parameter buffer constant between optimiser steps (weight prefetch before the PDL dependency wait);
+    None clears the table."""
+    lib = _lib.load()
+    if t is None:
+        _lib.check(lib.cgvae_register_const_range(None, 0), "register_const_range")
+    else:
+        _lib.check(lib.cgvae_register_const_range(_p(t), t.numel() * t.element_size()), "register_const_range")
+
+
+def register_const_params(module):
+    """every CUDA parameter of a module whose weights are frozen (sampling)."""
+    for p in module.parameters():
+        if p.is_cuda:
+            register_const_range(p.data)
+
+
 def adam_ws(device):
     """workspace of the two-phase (sharded) optimiser: float [1028] = 1024 norm partials | loss | ticket | pad."""
     lib = _lib.load()

@@ -125,6 +125,9 @@ class FlatGrads(object):
     def release(self):
         if self.sink:
             from . import ops
+            # the flat parameter buffer of this step may be freed next: forget every "constant weights" range (conservative:
+            # a stale range would let a streaming GEMM prefetch an operand that IS written by the preceding kernel)
+            ops.register_const_range(None)
             for p in self.params:
                 ops.GRAD_SINK.pop(p.data_ptr(), None)
 
@@ -272,6 +275,8 @@ class TrainStep(object):
             n_moment = self.flat_p.numel() // world if self.shard_opt else self.flat_p.numel()    # sharded: this rank's slice
             self.exp_avg = torch.zeros(n_moment, dtype=torch.float32, device=params[0].device)
             self.exp_avg_sq = torch.zeros(n_moment, dtype=torch.float32, device=params[0].device)
+            from . import ops
+            ops.register_const_range(self.flat_p)      # weights are only written by the optimiser kernel (see gemm_stream.cu)
             self.step_count = torch.zeros(1, dtype=torch.float32, device=params[0].device)
             self.skipped = torch.zeros(1, dtype=torch.float32, device=params[0].device)
         self.flat = FlatGrads(params, align=align)
@@ -780,6 +785,13 @@ class GraphedSampler(object):
     Ensemble members of different conformations are independent: under torchrun each rank samples its own conformations
     (or members) with no exchange step."""
 
+    def __del__(self):
+        try:                                   # the model may be freed next: forget the "constant weights" ranges
+            from . import ops
+            ops.register_const_range(None)
+        except Exception:
+            pass
+
     def __init__(self, model, example_batch, n_ensemble):
         self.model, self.n_ensemble = model, int(n_ensemble)
         self.static = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in example_batch.items()}
@@ -787,6 +799,10 @@ class GraphedSampler(object):
         F = model.atom_munet[0].weight.shape[1]
         dev = self.static["CG_nxyz"].device
         self.eps = torch.zeros((self.n_ensemble, n_beads, F), dtype=torch.float32, device=dev)
+        # sampling never writes the weights: the streaming GEMMs may fetch them before their dependency wait (gemm_stream.cu).
+        # A caller that updates the parameters afterwards (fine-tuning) clears the table with ops.register_const_range(None).
+        from . import ops
+        ops.register_const_params(model)
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
         side.wait_stream(cur)

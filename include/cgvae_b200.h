@@ -349,6 +349,14 @@ int cgvae_dihedral_loss_bwd(const float* g_loss, const float* contrib, const int
  * pin[idx[i]] = 1 for the live entries iff idx[last] < n_atoms.  pin_bytes >= n_atoms, a multiple of 4. */
 int cgvae_pin_mask(const int64_t* idx, int64_t n_idx, const int64_t* n_live, int64_t n_atoms, uint8_t* pin, size_t pin_bytes,
                    cgvae_stream_t stream);
+/* Programmatic dependent launch for every launch of the library from now on (default on; CGVAE_PDL=0); returns the previous
+ * setting.  Launches already captured in a CUDA graph keep the edges they were captured with. */
+int cgvae_set_pdl(int on);
+/* Declare [p, p + bytes) a parameter range: memory no kernel writes between two optimiser steps (the flat parameter buffer of
+ * a training step).  With programmatic dependent launch enabled (CGVAE_PDL, default on) the weight-streaming GEMMs fetch a
+ * weight matrix inside such a range BEFORE their dependency wait, overlapping the copy with the preceding kernel.  Ranges that
+ * touch are merged; p == NULL clears the table. */
+int cgvae_register_const_range(const void* p, size_t bytes);
 /* p[0..n) = value (initial decoder state cgvae.py:90-95 without a library fill) */
 int cgvae_fill(float* p, int64_t n, float value, cgvae_stream_t stream);
 
