@@ -67,6 +67,8 @@ SIGNATURES = {
     "cgvae_adam_ws_bytes": (_SZ, []),
     "cgvae_adam_clip_step": (_INT, [_P, _P, _P, _P, _I64, _F32, _F32, _F32, _F32, _F32, _F32, _P, _P, _P, _F32, _F32, _P,
                                     _P, _SZ, _P]),
+    "cgvae_bond_graph": (_INT, [_P, _P, _I64, _F32, _P, _P]),
+    "cgvae_sample_quality": (_INT, [_P, _P, _P, _P, _I64, _I64, _F32, _P, _P, _P]),
     "cgvae_set_pdl": (_INT, [_INT]),
     "cgvae_register_const_range": (_INT, [_P, _SZ]),
     "cgvae_grad_sumsq": (_INT, [_P, _I64, _P, _P, _SZ, _P]),

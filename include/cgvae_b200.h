@@ -349,6 +349,16 @@ int cgvae_dihedral_loss_bwd(const float* g_loss, const float* contrib, const int
  * pin[idx[i]] = 1 for the live entries iff idx[last] < n_atoms.  pin_bytes >= n_atoms, a multiple of 4. */
 int cgvae_pin_mask(const int64_t* idx, int64_t n_idx, const int64_t* n_live, int64_t n_atoms, uint8_t* pin, size_t pin_bytes,
                    cgvae_stream_t stream);
+/* Sample-quality metrics of the ensemble-sampling loop (scripts/sampling.py:120-194,220-239,324-333).
+ * cgvae_bond_graph: bond[i][j] = (i != j) && sqrt(((dx^2+dy^2)+dz^2)) < (radius[i] + radius[j]) * scale, in fp32 and in the
+ * reference's operation order (bit-exact adjacency); radius = covalent cutoff radius per atom (COVCUTOFFTABLE, sampling.py:12-118).
+ * cgvae_sample_quality: for every sample s of samples[n_samples][n][3] against the reference conformation:
+ *   counts[s] = { #(gen != ref), sum(ref - gen), sum(ref) } over all ordered atom pairs, then the same three over pairs of heavy
+ *   atoms (heavy[i] != 0) -- compare_graph / graph_diff_ratio of count_valid_graphs with heavy_only False / True;
+ *   rmsd[s] = { all-atom, heavy-atom } root-mean-square deviation without alignment (compute_rmsd). */
+int cgvae_bond_graph(const float* xyz, const float* radius, int64_t n, float scale, uint8_t* bond, cgvae_stream_t stream);
+int cgvae_sample_quality(const float* ref_xyz, const float* samples, const float* radius, const uint8_t* heavy, int64_t n,
+                         int64_t n_samples, float scale, int32_t* counts, float* rmsd, cgvae_stream_t stream);
 /* Programmatic dependent launch for every launch of the library from now on (default on; CGVAE_PDL=0); returns the previous
  * setting.  Launches already captured in a CUDA graph keep the edges they were captured with. */
 int cgvae_set_pdl(int on);

@@ -431,6 +431,67 @@ def pcn_dihedral():
                                "loss": _np(loss), "g_xyz_rec": _np(rec.grad)})
 
 
+def sample_quality():
+    """eval_sample_qualities and its helpers (scripts/sampling.py:120-194,220-239,324-333) lifted out of the UNMODIFIED source
+    with ast (the module imports mdshare / pyemma at the top) and run on a minimal ``Atoms`` stand-in (positions + numbers):
+    bond adjacency of the reference conformation, per-sample difference counts / ratios and RMSDs."""
+    import ast
+    src_path = os.path.join(ref_shim.REFERENCE_ROOT, "scripts", "sampling.py")
+    tree = ast.parse(open(src_path).read())
+    want = {"compute_bond_cutoff", "compute_distance_mat", "dropH", "compare_graph", "get_bond_graphs", "count_valid_graphs",
+            "compute_rmsd", "eval_sample_qualities"}
+    body = [n for n in tree.body if (isinstance(n, ast.FunctionDef) and n.name in want)
+            or (isinstance(n, ast.Assign) and getattr(n.targets[0], "id", None) == "COVCUTOFFTABLE")]
+
+    class Atoms(object):
+        def __init__(self, numbers, positions):
+            self.numbers, self.positions = np.asarray(numbers), np.asarray(positions, dtype=np.float64)
+
+        def get_positions(self):
+            return self.positions
+
+        def get_atomic_numbers(self):
+            return self.numbers
+
+        def __len__(self):
+            return len(self.numbers)
+
+    ns = {"torch": torch, "np": np, "Atoms": Atoms}
+    exec(compile(ast.Module(body=body, type_ignores=[]), src_path, "exec"), ns)
+    rng = np.random.default_rng(77)
+    # a chain molecule with hydrogens: heavy atoms 1.5 A apart, one or two hydrogens at ~1.0 A
+    n_heavy = 24
+    heavy = np.cumsum(rng.normal(size=(n_heavy, 3)) * 0.2 + np.array([1.45, 0.3, 0.1]), 0)
+    z, pos = [], []
+    for i in range(n_heavy):
+        z.append(int(rng.choice([6, 7, 8, 16])))
+        pos.append(heavy[i])
+        for _ in range(int(rng.integers(0, 3))):
+            d = rng.normal(size=3)
+            z.append(1)
+            pos.append(heavy[i] + d / np.linalg.norm(d) * 1.0)
+    z, pos = np.asarray(z), np.asarray(pos, dtype=np.float32).astype(np.float64)
+    ref = Atoms(z, pos)
+    samples = []
+    for s, noise in enumerate([0.0, 0.01, 0.03, 0.08, 0.15, 0.3, 0.02, 0.0]):
+        p = pos + rng.normal(size=pos.shape) * noise
+        if s == 7:
+            p = pos.copy()
+            p[z == 1] += rng.normal(size=(int((z == 1).sum()), 3)) * 0.6      # hydrogens scrambled, heavy graph intact
+        samples.append(np.asarray(p, dtype=np.float32).astype(np.float64))
+    atoms_list = [Atoms(z, p) for p in samples]
+    all_rmsds, heavy_rmsds, valid_ratio, valid_allatom_ratio, graph_val_ratio, graph_allatom_val_ratio = ns["eval_sample_qualities"](ref, atoms_list)
+    store = {"z": z, "ref_xyz": pos.astype(np.float32), "samples": np.stack(samples).astype(np.float32),
+             "ref_bonds": ns["get_bond_graphs"](ref).numpy(), "sample3_bonds": ns["get_bond_graphs"](atoms_list[3]).numpy(),
+             "diff_counts": np.asarray([ns["compare_graph"](ref, a, 1.3) for a in atoms_list]),
+             "all_rmsds": np.zeros((0, 2)) if all_rmsds is None else all_rmsds,
+             "heavy_rmsds": np.zeros((0, 2)) if heavy_rmsds is None else heavy_rmsds,
+             "valid_ratio": np.asarray(valid_ratio), "valid_allatom_ratio": np.asarray(valid_allatom_ratio),
+             "graph_val_ratio": np.asarray(graph_val_ratio), "graph_allatom_val_ratio": np.asarray(graph_allatom_val_ratio)}
+    print("valid heavy %.3f all-atom %.3f" % (valid_ratio, valid_allatom_ratio), store["diff_counts"])
+    _save("sample_quality.npz", store)
+
+
 def main():
     torch.set_num_threads(1)
     ref_modules, ref_conv, ref_cgvae, ref_data = ref_shim.import_reference()
@@ -443,6 +504,7 @@ def main():
     sampling(ref_cgvae, ref_data)
     dataset_lists(ref_data)
     pcn_dihedral()
+    sample_quality()
 
 
 if __name__ == "__main__":

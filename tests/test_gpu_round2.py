@@ -564,3 +564,39 @@ def test_pcn_step_graphed_matches_eager_and_reference_loss():
         lb.append(float(graphed.step(b)))
     assert la == lb, (la, lb)
     assert torch.equal(ta.flat_p, tb.flat_p)
+
+
+# ------------------------------------------------------------------------------------------ sample-quality metrics (f3)
+
+def test_sample_quality_metrics_match_reference():
+    """csrc/metrics.cu == the reference's eval_sample_qualities (tests/golden/sample_quality.npz): bond adjacency bit-exact,
+    difference counts and valid sets exact, ratios exact, RMSDs to 1e-6; plus a 3000-atom case against the oracle."""
+    from coarsegrainingvae_b200 import metrics
+    from oracle import metrics_oracle as morc
+    g = load("sample_quality.npz")
+    z = torch.from_numpy(np.asarray(g["z"])).to(DEV)
+    ref = torch.from_numpy(np.asarray(g["ref_xyz"])).to(DEV)
+    samples = torch.from_numpy(np.asarray(g["samples"])).to(DEV)
+    assert np.array_equal(metrics.get_bond_graphs(ref, z).cpu().numpy(), g["ref_bonds"])
+    assert np.array_equal(metrics.get_bond_graphs(samples[3], z).cpu().numpy(), g["sample3_bonds"])
+    counts, _ = metrics.sample_quality_counts(ref, z, samples)
+    assert np.array_equal(counts[:, 0].cpu().numpy(), g["diff_counts"])
+    all_r, heavy_r, vr, var, gvr, gavr = metrics.eval_sample_qualities(ref, z, samples)
+    assert vr == float(g["valid_ratio"]) and var == float(g["valid_allatom_ratio"])
+    assert np.allclose(gvr, g["graph_val_ratio"], rtol=0, atol=1e-12) and np.allclose(gavr, g["graph_allatom_val_ratio"], rtol=0, atol=1e-12)
+    assert np.allclose(all_r, g["all_rmsds"], rtol=1e-6) and np.allclose(heavy_r, g["heavy_rmsds"], rtol=1e-6)
+    # larger: 3000 atoms on a jittered lattice (many pairs at the cutoff boundary), 5 samples, vs the CPU oracle
+    rng = np.random.default_rng(3)
+    n = 3000
+    xyz = synthetic.lattice_points(n, 1.45, rng).astype(np.float32)
+    zz = rng.choice([1, 6, 7, 8], size=n, p=[0.4, 0.4, 0.1, 0.1])
+    radii = np.asarray(metrics.COV_CUTOFF, dtype=np.float32)[zz]
+    smp = np.stack([xyz + rng.normal(size=xyz.shape).astype(np.float32) * s for s in (0.0, 0.005, 0.02, 0.05, 0.2)]).astype(np.float32)
+    want = morc.eval_sample_qualities(xyz, list(smp), zz, radii)
+    got = metrics.eval_sample_qualities(torch.from_numpy(xyz).to(DEV), torch.from_numpy(zz).to(DEV), torch.from_numpy(smp).to(DEV))
+    assert np.array_equal(metrics.get_bond_graphs(torch.from_numpy(smp[2]).to(DEV), torch.from_numpy(zz).to(DEV)).cpu().numpy(),
+                          morc.get_bond_graphs(smp[2], radii).numpy())
+    assert got[2] == want[2] and got[3] == want[3]
+    assert np.allclose(got[4], want[4], rtol=0, atol=1e-12) and np.allclose(got[5], want[5], rtol=0, atol=1e-12)
+    for a, b in ((got[0], want[0]), (got[1], want[1])):
+        assert (a is None) == (b is None) and (a is None or np.allclose(a, b, rtol=1e-6))
