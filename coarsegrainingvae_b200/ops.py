@@ -243,12 +243,16 @@ def exclusive_scan(counts_i32, out_dtype=torch.int64):
     return out
 
 
-def radius_graph(xyz, cutoff, undirected=True, frame_ptr=None, use_cells=None):
+def radius_graph(xyz, cutoff, undirected=True, frame_ptr=None, use_cells=None, capacity=None, max_frame=None):
     """get_neighbor_list (data.py:65-82) on the GPU, optionally batched over frames.
 
     xyz [n,3] fp32 CUDA; frame_ptr int64 [n_frames+1] (defaults to one frame).  Returns int64 [E,2]
     sorted by (i, j) -- identical, bit for bit, to the reference's per-frame lists offset and
     concatenated by CG_collate (data.py:255-270).  One host read (the edge count).
+
+    capacity (with max_frame = atoms of the largest frame, known to the caller): static mode -- NO host read; returns
+    (pairs zero-padded to [capacity, 2], count int64 [1] on the device).  The capacity must cover the worst case
+    (every pair of every frame within the cutoff), which is checked on the host from the frame sizes.
     """
     _need_cuda(xyz)
     lib = _lib.load()
@@ -260,13 +264,20 @@ def radius_graph(xyz, cutoff, undirected=True, frame_ptr=None, use_cells=None):
         max_frame = n
     else:
         frame_ptr = frame_ptr.to(device=dev, dtype=torch.int64).contiguous()
-        max_frame = None
     n_frames = frame_ptr.shape[0] - 1
+    if capacity is not None:
+        if max_frame is None:
+            raise ValueError("radius_graph(capacity=...) needs max_frame (atoms of the largest frame): no host read in static mode")
+        worst = n_frames * max_frame * (max_frame - 1) // (2 if undirected else 1)
+        if capacity < worst:
+            raise ValueError("capacity %d below the worst case %d (%d frames of <= %d atoms)" % (capacity, worst, n_frames, max_frame))
     if use_cells is None:
         if max_frame is None:
             max_frame = int((frame_ptr[1:] - frame_ptr[:-1]).max().item()) if n_frames > 0 else 0
         use_cells = max_frame > 1024
     if n == 0:
+        if capacity is not None:
+            return torch.zeros((capacity, 2), dtype=torch.int64, device=dev), torch.zeros(1, dtype=torch.int64, device=dev)
         return torch.zeros((0, 2), dtype=torch.int64, device=dev)
     ws_bytes = int(lib.cgvae_radius_graph_ws_bytes(n, n_frames)) if use_cells else 0
     ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
@@ -275,6 +286,12 @@ def radius_graph(xyz, cutoff, undirected=True, frame_ptr=None, use_cells=None):
     _lib.check(lib.cgvae_radius_graph_count(_p(xyz), n, _p(frame_ptr), n_frames, float(np.float32(cutoff)), int(bool(undirected)),
                                             int(bool(use_cells)), _p(deg), _p(ws), ws_bytes, st), "radius_graph_count")
     rowptr = exclusive_scan(deg, torch.int64)
+    if capacity is not None:
+        pairs = torch.zeros((capacity, 2), dtype=torch.int64, device=dev)
+        _lib.check(lib.cgvae_radius_graph_fill(_p(xyz), n, _p(frame_ptr), n_frames, float(np.float32(cutoff)), int(bool(undirected)),
+                                               int(bool(use_cells)), _p(rowptr), _p(pairs), _p(ws), ws_bytes, st),
+                   "radius_graph_fill")
+        return pairs, rowptr[-1:].clone()
     n_edges = int(rowptr[-1].item())
     pairs = torch.empty((n_edges, 2), dtype=torch.int64, device=dev)
     if n_edges:

@@ -9,6 +9,7 @@ import pytest
 import torch
 
 import coarsegrainingvae_b200 as cg
+import coarsegrainingvae_b200 as cg_mod
 from coarsegrainingvae_b200 import ops, synthetic
 from oracle import cgvae_oracle as orc
 from oracle import graph_oracle as gorc
@@ -600,3 +601,83 @@ def test_sample_quality_metrics_match_reference():
     assert np.allclose(got[4], want[4], rtol=0, atol=1e-12) and np.allclose(got[5], want[5], rtol=0, atol=1e-12)
     for a, b in ((got[0], want[0]), (got[1], want[1])):
         assert (a is None) == (b is None) and (a is None or np.allclose(a, b, rtol=1e-6))
+
+
+# ------------------------------------------------------------------------------------------ on-GPU batch assembly (f2)
+
+def _trajectory(T, n, n_cgs, seed):
+    rng = np.random.default_rng(seed)
+    base = synthetic.lattice_points(n, 1.6, rng).astype(np.float32)
+    xyz = np.stack([base + rng.normal(size=base.shape).astype(np.float32) * 0.25 for _ in range(T)]).astype(np.float32)
+    z = rng.choice([1, 6, 7, 8], size=n).astype(np.float32)
+    mapping = (np.arange(n) * n_cgs // n).astype(np.int64)
+    bonds = np.asarray(gorc.radius_graph(base, 1.9), dtype=np.int64)
+    return xyz, z, mapping, bonds
+
+
+@pytest.mark.parametrize("cg_cutoff", [6.5, None])
+def test_device_collate_matches_host_pipeline(cg_cutoff):
+    """DeviceCGDataset.collate (trajectory resident in HBM, graphs built on the fly, bead means by the pooling kernel) ==
+    the reference pipeline: per-frame props (datasets.py:470-500) -> generate_neighbor_list (data.py:207-252) -> CG_collate
+    (data.py:255-289); index tensors bit for bit, also in the static-capacity form (== train.to_static_batch) with no host read."""
+    from coarsegrainingvae_b200 import train
+    T, n, n_cgs, atom_cutoff = 7, 60, 5, 4.0
+    xyz, z, mapping, bonds = _trajectory(T, n, n_cgs, 11)
+    props = {k: [] for k in ("nxyz", "CG_nxyz", "num_atoms", "num_CGs", "CG_mapping", "bond_edge_list")}
+    for t in range(T):
+        cg = np.stack([xyz[t][mapping == b].astype(np.float32).mean(0) for b in range(n_cgs)]).astype(np.float32)
+        props["nxyz"].append(torch.from_numpy(np.concatenate([z[:, None], xyz[t]], 1)))
+        props["CG_nxyz"].append(torch.from_numpy(np.concatenate([np.arange(n_cgs, dtype=np.float32)[:, None], cg], 1)))
+        props["num_atoms"].append(torch.LongTensor([n]))
+        props["num_CGs"].append(torch.LongTensor([n_cgs]))
+        props["CG_mapping"].append(torch.from_numpy(mapping))
+        props["bond_edge_list"].append(torch.from_numpy(bonds))
+    ds = cg_mod.CGDataset(props)
+    ds.generate_neighbor_list(atom_cutoff=atom_cutoff, cg_cutoff=cg_cutoff, device=DEV, undirected=True)
+    dds = cg_mod.DeviceCGDataset(z, xyz, mapping, bonds, atom_cutoff, cg_cutoff, device=DEV)
+    for idx in ([3, 0, 6], [5], [1, 1, 2, 4]):
+        want = cg_mod.CG_collate([ds[i] for i in idx])
+        got = dds.collate(idx)
+        assert set(got.keys()) == set(want.keys())
+        for k, w in want.items():
+            g = got[k].cpu()
+            assert g.shape == w.shape and g.dtype == w.dtype, (k, g.shape, w.shape, g.dtype, w.dtype)
+            if w.dtype.is_floating_point:
+                assert rel_err(g, w) <= 1e-6, k                       # CG_nxyz: bead means (summation order)
+            else:
+                assert torch.equal(g, w), k
+        caps = dds.capacities(len(idx))
+        swant = train.to_static_batch(want, caps)
+        sgot = dds.collate(idx, static=True)
+        for k, w in swant.items():
+            if torch.is_tensor(w):
+                g = sgot[k].cpu()
+                assert g.shape == w.shape, (k, g.shape, w.shape)
+                assert (rel_err(g, w) <= 1e-6) if w.dtype.is_floating_point else torch.equal(g, w), k
+            else:
+                assert sgot[k] == w, k
+
+
+def test_train_step_on_device_collated_batches():
+    """a graphed training step fed by DeviceCGDataset.collate(static=True) (no host data path at all) gives the losses of the
+    same step fed by host-collated static batches."""
+    from coarsegrainingvae_b200 import train
+    from coarsegrainingvae_b200.factory import build_cgvae
+    T, n, n_cgs, atom_cutoff, cg_cutoff = 6, 44, 4, 4.0, 7.0
+    xyz, z, mapping, bonds = _trajectory(T, n, n_cgs, 5)
+    dds = cg_mod.DeviceCGDataset(z, xyz, mapping, bonds, atom_cutoff, cg_cutoff, device=DEV)
+    B = 2
+    torch.manual_seed(2)
+    model = build_cgvae(64, 6, 2, 2, atom_cutoff, cg_cutoff, n_cgs).to(DEV)
+    eps = torch.randn(B * n_cgs, 64, generator=torch.Generator().manual_seed(3)).to(DEV)
+    first = dds.collate([0, 1], static=True)
+    tr = train.TrainStep(model, 0.05, 10.0, capturable=True)
+    tr.prepare(first, eps)
+    graphed = train.GraphedTrainStep(tr, first, eps)
+    ref_model = build_cgvae(64, 6, 2, 2, atom_cutoff, cg_cutoff, n_cgs).to(DEV)
+    for idx in ([2, 3], [5, 4], [0, 5]):
+        sb = dds.collate(idx, static=True)
+        ref_model.load_state_dict(model.state_dict())
+        want = train.TrainStep(ref_model, 0.05, 10.0)._loss(dds.collate(idx), eps)
+        got = graphed.step(sb)
+        assert rel_err(got, want) <= TOL
