@@ -70,6 +70,71 @@ __device__ __forceinline__ float ep_apply(const Ep& ep, float v, int64_t m, int6
   return v;
 }
 
+// One 32-row x 32-column block from a warp's transpose buffer (tr[row][33]) to C, lane = column.  The epilogue variant is
+// chosen ONCE per kernel (the per-element `ep_apply` with its pointer tests, 64-bit index arithmetic and run-time activation
+// switch was 60 % of the kernel's instructions at the 16 000 x 2048 x 512 layer): MODE 0 plain, 1 + bias, 2 + bias and swish
+// (the phi-MLP hidden layer), 3 generic.
+__device__ __forceinline__ int ep_mode(const Ep& ep) {
+  // backward forms: input gradient through a swish layer (v * swish'(z_in)), residual / accumulating add
+  if (!ep.bias && !ep.z_out && ep.act == 0) {
+    if (ep.z_in && !ep.add && ep.dact == CGVAE_ACT_SWISH) return 4;
+    if (ep.add && !ep.z_in) return 5;
+  }
+  // forward hidden layer of a phi-MLP in training: bias, pre-activation copy (saved for the backward), swish
+  if (ep.z_out && ep.bias && !ep.z_in && !ep.add && ep.act == CGVAE_ACT_SWISH) return 6;
+  if (ep.z_out || ep.z_in || ep.add) return 3;
+  if (ep.act == 0) return ep.bias ? 1 : 0;
+  return (ep.act == CGVAE_ACT_SWISH && ep.bias) ? 2 : 3;
+}
+template <int MODE>
+__device__ __forceinline__ void store_block_mode(const Ep& ep, const float* __restrict__ tr, int lane, float* __restrict__ C, int64_t ldc,
+                                                 int64_t m_base, int64_t n, int64_t M, int64_t N) {
+  if (n >= N) return;
+  const int rows = (int)min((int64_t)32, M - m_base);
+  float* dst = C + m_base * ldc + n;
+  const float b = (MODE == 1 || MODE == 2 || MODE == 6) ? __ldg(ep.bias + n) : 0.f;
+  if (MODE == 4 || MODE == 5) {
+    // the second operand of the epilogue (z_in / add) is as large as the output: all 32 row loads of this block are issued
+    // before the first is used -- read one by one inside the store loop (4 in flight per warp) this epilogue ran at ~0.3 TB/s
+    const float* aux = ((MODE == 4) ? ep.z_in : ep.add) + m_base * ldc + n;
+    float a[32];
+#pragma unroll
+    for (int rr = 0; rr < 32; ++rr) a[rr] = (rr < rows) ? __ldg(aux + (int64_t)rr * ldc) : 0.f;
+#pragma unroll
+    for (int rr = 0; rr < 32; ++rr) {
+      if (rr < rows) {
+        const float v = tr[rr * 33 + lane];
+        dst[(int64_t)rr * ldc] = (MODE == 4) ? v * dswish_f(a[rr]) : v + a[rr];
+      }
+    }
+    return;
+  }
+#pragma unroll 4
+  for (int rr = 0; rr < rows; ++rr, dst += ldc) {
+    float v = tr[rr * 33 + lane];
+    if (MODE == 3) {
+      *dst = ep_apply(ep, v, m_base + rr, n, ldc);
+    } else {
+      v += b;
+      if (MODE == 6) ep.z_out[(m_base + rr) * ldc + n] = v;
+      if (MODE == 2 || MODE == 6) v = swish_f(v);
+      *dst = v;
+    }
+  }
+}
+__device__ __forceinline__ void store_block(int mode, const Ep& ep, const float* __restrict__ tr, int lane, float* __restrict__ C,
+                                            int64_t ldc, int64_t m_base, int64_t n, int64_t M, int64_t N) {
+  switch (mode) {                       // warp-uniform
+    case 0: store_block_mode<0>(ep, tr, lane, C, ldc, m_base, n, M, N); break;
+    case 1: store_block_mode<1>(ep, tr, lane, C, ldc, m_base, n, M, N); break;
+    case 2: store_block_mode<2>(ep, tr, lane, C, ldc, m_base, n, M, N); break;
+    case 4: store_block_mode<4>(ep, tr, lane, C, ldc, m_base, n, M, N); break;
+    case 5: store_block_mode<5>(ep, tr, lane, C, ldc, m_base, n, M, N); break;
+    case 6: store_block_mode<6>(ep, tr, lane, C, ldc, m_base, n, M, N); break;
+    default: store_block_mode<3>(ep, tr, lane, C, ldc, m_base, n, M, N); break;
+  }
+}
+
 // shared-memory matrix descriptor, descriptor version 1 (sm_100); layout type in bits 61..63:
 //   K-major operand: SWIZZLE_128B (2), SBO = 1024 (8-row groups), LBO unused;  MN-major: SWIZZLE_128B_BASE32B (1)
 template <bool KC>
@@ -299,6 +364,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     if (warp < NUM_SPLIT_WARPS) {
       // 32x32 blocks through shared memory (the stages are free by now) so that a warp writes 128 contiguous bytes per row
       const int q = warp & 3, half = warp >> 2;
+      const int mode = ep_mode(ep);
       float* tr = reinterpret_cast<float*>(smem) + warp * (32 * 33);
 #pragma unroll 1
       for (int cb = 0; cb < BN / 64; ++cb) {
@@ -308,12 +374,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
 #pragma unroll
         for (int j = 0; j < 32; ++j) tr[lane * 33 + j] = r[j];   // row = lane, column = j
         __syncwarp();
-        const int64_t n = n0 + c0 + lane;
-#pragma unroll 4
-        for (int rr = 0; rr < 32; ++rr) {
-          const int64_t m = m0 + 32 * q + rr;
-          if (m < M && n < N) C[m * ldc + n] = ep_apply(ep, tr[rr * 33 + lane], m, n, ldc);
-        }
+        if (m0 + 32 * q < M) store_block(mode, ep, tr, lane, C, ldc, m0 + 32 * q, n0 + c0 + lane, M, N);
         __syncwarp();
       }
       tc_fence_before();
@@ -360,6 +421,185 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     cluster.sync();                  // nobody leaves while a peer may still read its partial tile
   }
   if (warp == NUM_SPLIT_WARPS + 1) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Persistent variant for problems with many output tiles and a short k-loop (the 16 000 .. 128 000-row layers of the protein
+// configurations: K = 512 .. 1280).  With one tile per CTA the prologue (barriers, TMEM allocation, pipeline fill) and the
+// epilogue (TMEM -> registers -> smem transpose -> global) cost more than the 16 k-steps of MMAs between them.  Here a CTA
+// walks tiles b, b + G, ...; the operand ring runs across tile boundaries; the accumulators (small + big, 256 columns) are
+// DOUBLE-BUFFERED in TMEM and four dedicated epilogue warps drain tile t while the tensor core works on tile t + 1.
+// Warp roles: 0 TMA producer, 1 MMA issuer (owns TMEM), 2..5 epilogue (TMEM lane quarter = warp % 4), 6..13 lo pass.
+// ---------------------------------------------------------------------------------------------------------------------------
+constexpr int P_EPI_WARPS = 4, P_LO_WARPS = 8;
+constexpr int P_THREADS = (2 + P_EPI_WARPS + P_LO_WARPS) * 32;
+constexpr uint32_t P_SCRATCH_BYTES = P_EPI_WARPS * 32 * 33 * 4;
+constexpr uint32_t P_SMEM_BYTES = STAGES * STAGE_BYTES + P_SCRATCH_BYTES + BAR_BYTES + 1024;
+constexpr int P_MAX_KT = 40;          // one big accumulator per tile: chain length bounded like the round-1 kernel (K <= 1280)
+
+template <bool A_KC, bool B_KC>
+__global__ void __launch_bounds__(P_THREADS, 1) gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                                          const __grid_constant__ CUtensorMap map_b, float* __restrict__ C,
+                                                                          int64_t ldc, int64_t M, int64_t N, int64_t K, Ep ep,
+                                                                          int tiles_n, int n_tiles) {
+  CGVAE_KERNEL_PROLOGUE();
+  extern __shared__ __align__(1024) char smem_raw[];
+  char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  float* scratch = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* raw_full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + P_SCRATCH_BYTES);
+  uint64_t* lo_done = raw_full + STAGES;
+  uint64_t* empty_bar = lo_done + STAGES;
+  uint64_t* acc_full = empty_bar + STAGES;     // [2]
+  uint64_t* acc_empty = acc_full + 2;          // [2]
+  uint32_t* tmem_ptr_sh = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int num_kt = (int)((K + BK - 1) / BK);
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&raw_full[s], 1);
+      mbar_init(&lo_done[s], P_LO_WARPS);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], P_EPI_WARPS);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_ptr_sh);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_sh;
+  const uint32_t smem_base = smem_u32(smem);
+
+  if (warp == 0) {
+    // ---------------- TMA producer ----------------
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+      for (int kt = 0; kt < num_kt; ++kt, ++it) {
+        const int s = it % STAGES;
+        mbar_wait(&empty_bar[s], ((uint32_t)(it / STAGES) & 1u) ^ 1u);
+        if (elect_one()) {
+          const int k0 = kt * BK;
+          const uint32_t a_dst = smem_base + (uint32_t)s * STAGE_BYTES, b_dst = a_dst + A_BYTES;
+          mbar_expect_tx(&raw_full[s], RAW_BYTES);
+          if (A_KC) {
+            tma_2d(a_dst, &map_a, k0, m0, &raw_full[s]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BM / 32; ++j) tma_2d(a_dst + (uint32_t)j * 4096u, &map_a, m0 + 32 * j, k0, &raw_full[s]);
+          }
+          if (B_KC) {
+            tma_2d(b_dst, &map_b, k0, n0, &raw_full[s]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 32; ++j) tma_2d(b_dst + (uint32_t)j * 4096u, &map_b, n0 + 32 * j, k0, &raw_full[s]);
+          }
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer ----------------
+    constexpr uint32_t idesc = idesc_tf32(BM, BN, !A_KC, !B_KC);
+    constexpr uint32_t a_step = A_KC ? 32u : 1024u, b_step = B_KC ? 32u : 1024u;
+    int it = 0, tcount = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+      const int buf = tcount & 1;
+      mbar_wait(&acc_empty[buf], ((uint32_t)(tcount >> 1) & 1u) ^ 1u);      // the epilogue has drained this accumulator set
+      tc_fence_after();
+      const uint32_t d_small = tmem_base + (uint32_t)buf * 2u * BN, d_big = d_small + BN;
+      for (int kt = 0; kt < num_kt; ++kt, ++it) {
+        const int s = it % STAGES;
+        mbar_wait(&lo_done[s], (uint32_t)(it / STAGES) & 1u);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a_hi = smem_base + (uint32_t)s * STAGE_BYTES, b_hi = a_hi + A_BYTES;
+          const uint32_t a_lo = a_hi + RAW_BYTES, b_lo = b_hi + RAW_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < BK / 8; ++ks) {
+            const uint32_t ao = (uint32_t)ks * a_step, bo = (uint32_t)ks * b_step;
+            const uint32_t acc = (kt > 0 || ks > 0) ? 1u : 0u;
+            umma_tf32_ss(d_small, make_desc_op<A_KC>(a_lo + ao), make_desc_op<B_KC>(b_hi + bo), acc, idesc);
+            umma_tf32_ss(d_small, make_desc_op<A_KC>(a_hi + ao), make_desc_op<B_KC>(b_lo + bo), 1u, idesc);
+            umma_tf32_ss(d_big, make_desc_op<A_KC>(a_hi + ao), make_desc_op<B_KC>(b_hi + bo), acc, idesc);
+          }
+          umma_commit(&empty_bar[s]);
+          if (kt == num_kt - 1) umma_commit(&acc_full[buf]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp < 2 + P_EPI_WARPS) {
+    // ---------------- epilogue: TMEM -> registers -> smem transpose -> coalesced global stores ----------------
+    const int q = warp & 3;                                   // TMEM lane quarter this warp may access
+    const int mode = ep_mode(ep);
+    float* tr = scratch + (warp - 2) * (32 * 33);
+    int tcount = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+      const int buf = tcount & 1;
+      const int64_t m0 = (int64_t)(tile / tiles_n) * BM, n0 = (int64_t)(tile % tiles_n) * BN;
+      mbar_wait(&acc_full[buf], (uint32_t)(tcount >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t t_small = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)buf * 2u * BN;
+#pragma unroll 1
+      for (int cb = 0; cb < BN / 32; ++cb) {
+        uint32_t r[32], t[32];
+        tmem_ld32(t_small + (uint32_t)cb * 32u, r);
+        tmem_ld32(t_small + BN + (uint32_t)cb * 32u, t);
+        tmem_wait_ld();
+        if (cb == BN / 32 - 1) {                              // everything of this set is in registers: hand it back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) tr[lane * 33 + j] = __uint_as_float(r[j]) + __uint_as_float(t[j]);
+        __syncwarp();
+        if (m0 + 32 * q < M) store_block(mode, ep, tr, lane, C, ldc, m0 + 32 * q, n0 + cb * 32 + lane, M, N);
+        __syncwarp();
+      }
+    }
+  } else {
+    // ---------------- lo pass ----------------
+    const int t0 = tid - (2 + P_EPI_WARPS) * 32;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int kt = 0; kt < num_kt; ++kt, ++it) {
+        const int s = it % STAGES;
+        mbar_wait(&raw_full[s], (uint32_t)(it / STAGES) & 1u);
+        const float4* raw = reinterpret_cast<const float4*>(smem + (uint32_t)s * STAGE_BYTES);
+        float4* lo = reinterpret_cast<float4*>(smem + (uint32_t)s * STAGE_BYTES + RAW_BYTES);
+        constexpr int PER = (int)(RAW_BYTES / 16) / (P_LO_WARPS * 32);
+        float4 x[PER];
+#pragma unroll
+        for (int i = 0; i < PER; ++i) x[i] = raw[t0 + i * P_LO_WARPS * 32];
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+          float4 l;
+          l.x = lo_of(x[i].x);
+          l.y = lo_of(x[i].y);
+          l.z = lo_of(x[i].z);
+          l.w = lo_of(x[i].w);
+          lo[t0 + i * P_LO_WARPS * 32] = l;
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&lo_done[s]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<TMEM_COLS>(tmem_base);
   }
@@ -440,6 +680,32 @@ int launch_gemm_tcgen05(int form, const float* A, int64_t lda, const float* B, i
   const int b_const = (form != CGVAE_GEMM_TN &&
                        weights_are_constant(B, sizeof(float) * (size_t)(((b_kc ? N : K) - 1) * ldb + (b_kc ? K : N)))) ? 1 : 0;
   tc::Ep ep{bias, act, z_out, z_in, dact, add};
+  static const bool persistent_on = [] { const char* e = getenv("CGVAE_TC_PERSISTENT"); return !(e && e[0] == '0'); }();
+  if (persistent_on && S == 1 && groups == 1 && tiles >= 2 * kNumSM && num_kt <= tc::P_MAX_KT) {
+    cudaLaunchConfig_t pc = {};
+    pc.gridDim = dim3((unsigned)std::min<int64_t>(tiles, kNumSM));
+    pc.blockDim = dim3(tc::P_THREADS);
+    pc.dynamicSmemBytes = tc::P_SMEM_BYTES;
+    pc.stream = st;
+    cudaLaunchAttribute pattr[1];
+    pattr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    pattr[0].val.programmaticStreamSerializationAllowed = 1;
+    pc.attrs = pattr;
+    pc.numAttrs = pdl_enabled() ? 1 : 0;
+    const int tiles_n = (int)ceil_div(N, tc::BN), n_tiles = (int)tiles;
+    static bool p_attr_done[3] = {false, false, false};
+    auto pgo = [&](auto kernel, int idx) {
+      if (!p_attr_done[idx]) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::P_SMEM_BYTES);
+        p_attr_done[idx] = true;
+      }
+      (void)cudaLaunchKernelEx(&pc, kernel, map_a, map_b, C, ldc, M, N, K, ep, tiles_n, n_tiles);
+    };
+    if (a_kc && b_kc) pgo(tc::gemm_tc_persistent_kernel<true, true>, 0);
+    else if (a_kc) pgo(tc::gemm_tc_persistent_kernel<true, false>, 1);
+    else pgo(tc::gemm_tc_persistent_kernel<false, false>, 2);
+    return 1;
+  }
   if (groups > 1) ep = tc::Ep{nullptr, 0, nullptr, nullptr, 0, nullptr};
   float* partial = groups > 1 ? ws : nullptr;
   cudaLaunchConfig_t cfg = {};
