@@ -727,7 +727,7 @@ int cgvae_message_tc_fwd(int n_split, const float* phi, const float* v_send, con
                          float* out_v, float* q, void* ws, size_t ws_bytes, cgvae_stream_t stream) {
   CGVAE_REQUIRE(n_split == 3 || n_split == 4, "message_tc_fwd: n_split must be 3 or 4 (got %d)", n_split);
   CGVAE_REQUIRE(RC == 4 || RC == 8 || RC == 16, "message_tc_fwd: RC must be 4, 8 or 16 (got %d)", RC);
-  CGVAE_REQUIRE(n_split == 3 || RC == 4, "message_tc_fwd: the cross block runs with RC = 4 (register budget)");
+  CGVAE_REQUIRE(n_split == 3 || RC <= 8, "message_tc_fwd: the cross block runs with RC = 4 or 8 (register budget)");
   CGVAE_REQUIRE(R >= 1 && R + 1 <= mtc::KT && F >= 1, "message_tc_fwd: need 1 <= R <= 15");
   if (n_recv == 0) return 0;
   CGVAE_REQUIRE(phi && bptr && ngroups && rec && Wf && bf && out_s && out_v, "message_tc_fwd: null pointer");
@@ -759,9 +759,15 @@ int cgvae_message_tc_fwd(int n_split, const float* phi, const float* v_send, con
                   part_ws);                                                                                                      \
   } while (0)
   if (n_split == 3) {
-    if (RC == 4) LAUNCH_TC_FWD(3, 4, 4); else if (RC == 8) LAUNCH_TC_FWD(3, 8, 4); else LAUNCH_TC_FWD(3, 16, 2);
+    // RC = 8 with 8 consumer warps (NSUB = 2: 320 threads, no spills) beats 16 consumer warps at 96 registers (48-byte spill in
+    // the column loop): 76.8 vs 80.7 us at the chignolin atom graph, 15.7 vs 16.2 ms at c5 / 12 A.  CGVAE_MSG_TC_NSUB2=0: old form
+    static const bool nsub2 = [] { const char* e = getenv("CGVAE_MSG_TC_NSUB2"); return !(e && e[0] == '0'); }();
+    if (RC == 4) LAUNCH_TC_FWD(3, 4, 4);
+    else if (RC == 8) { if (nsub2) LAUNCH_TC_FWD(3, 8, 2); else LAUNCH_TC_FWD(3, 8, 4); }
+    else LAUNCH_TC_FWD(3, 16, 2);
   } else {
-    LAUNCH_TC_FWD(4, 4, 4);
+    // RC = 8: 56 accumulators per thread only fit with 8 consumer warps (NSUB = 2: 320 threads, 204 registers each)
+    if (RC == 4) LAUNCH_TC_FWD(4, 4, 4); else LAUNCH_TC_FWD(4, 8, 2);
   }
 #undef LAUNCH_TC_FWD
   return launched("message_tc_fwd");

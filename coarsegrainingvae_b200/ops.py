@@ -649,9 +649,10 @@ class MessageTiles(object):
 import os as _os
 MSG_TC = _os.environ.get("CGVAE_MSG_TC", "auto")
 MSG_TC_RC = int(_os.environ.get("CGVAE_MSG_TC_RC", "8"))
+MSG_TC_CROSS_RC = int(_os.environ.get("CGVAE_MSG_TC_CROSS_RC", "8"))
 MSG_TC_MIN_EDGES = 4096
 MSG_TC_MIN_DEGREE = 12.0
-MSG_TC_MIN_FILL = float(_os.environ.get("CGVAE_MSG_TC_MIN_FILL", "0.45"))
+MSG_TC_MIN_FILL = float(_os.environ.get("CGVAE_MSG_TC_MIN_FILL", "0.40"))
 _TC_DECISIONS = {}
 
 
@@ -694,7 +695,7 @@ def _tc_applies(geom, n_split):
         return False
     if MSG_TC == "1":
         return True
-    if n_split != 3:
+    if n_split not in (3, 4):
         return False
     if g.n_edges < MSG_TC_MIN_EDGES or g.n_edges < MSG_TC_MIN_DEGREE * g.n_recv:
         return False
@@ -719,7 +720,7 @@ def message_tc_fwd(n_split, phi, v_send, v_recv, geom, Wf, bf, res_s, res_v, wan
     g = geom.graph
     F = phi.shape[-1]
     dev = phi.device
-    rc = MSG_TC_RC if n_split == 3 else 4       # the cross block's extra accumulators only fit the register budget at RC = 4
+    rc = MSG_TC_RC if n_split == 3 else min(MSG_TC_RC, MSG_TC_CROSS_RC)   # cross block: 7 accumulators per receiver
     tiles = message_tiles(geom, False, rc)
     out_s = torch.empty((g.n_recv, F), dtype=torch.float32, device=dev)
     out_v = torch.empty((g.n_recv, 3, F), dtype=torch.float32, device=dev)
