@@ -199,12 +199,12 @@ class TrainStep(object):
         # kernel holds its SMs for the whole transfer and the encoder's backward slows down by more than the transfer
         # takes: 270 MB move in 0.37 ms at 730 GB/s), factor exchange 3.46 ms -> overlap is opt-in (CGVAE_DP_OVERLAP=1).
         self.dp_overlap = os.environ.get("CGVAE_DP_OVERLAP", "0") == "1"
-        # sharded optimiser (opt-in, CGVAE_SHARD_OPT=1): reduce-scatter of the flat gradient buffer, clip + Adam on this
-        # rank's 1/world slice (global norm and loss from a 1025-float all-reduce), all-gather of the parameters: the 0.35 ms
-        # HBM-bound optimiser pass (28 B per parameter) shrinks world-fold.  Measured on 2 x B200 (tools/nccl_micro.py, 270
-        # MB): all-reduce 543 us, reduce-scatter 347 + all-gather 321 us -- NCCL's all-reduce beats the pair by more than
-        # the optimiser saves (3.58 vs 3.30 ms per step), so the plain all-reduce stays the default.
-        self.shard_opt = os.environ.get("CGVAE_SHARD_OPT", "0") == "1"
+        # sharded optimiser: reduce-scatter of the flat gradient buffer, clip + Adam on this rank's 1/world slice (global norm
+        # and loss from a 1025-float all-reduce), all-gather of the parameters: the 0.35 ms HBM-bound optimiser pass (28 B per
+        # parameter) shrinks world-fold.  Measured (tools/nccl_micro.py, 270 MB): 2 x B200 all-reduce 543 us vs reduce-scatter
+        # 347 + all-gather 321 us -> the pair loses more than half an Adam pass saves (3.58 vs 3.30 ms per step); 8 x B200
+        # all-reduce 723 us vs 407 + 406 us -> 3.58 vs 3.72 ms per step.  "auto" = from 4 ranks; CGVAE_SHARD_OPT=0 / 1 forces.
+        self.shard_opt = os.environ.get("CGVAE_SHARD_OPT", "auto")
         self._adam_ws = None
         self.n_overlap = 0
         self._comm_stream = None
@@ -258,7 +258,8 @@ class TrainStep(object):
             params = dec + [p for k, p in used if not k.startswith("equivaraintconv.")]
             self.n_overlap = sum(p.numel() for p in dec)
         world = self._world()
-        self.shard_opt = bool(self.shard_opt and on_cuda and self.optimizer == "fused" and world > 1
+        want_shard = (world >= 4) if self.shard_opt == "auto" else (self.shard_opt not in ("0", False, None))
+        self.shard_opt = bool(want_shard and on_cuda and self.optimizer == "fused" and world > 1
                               and not self.gather_factors and not self.n_overlap)
         align = 4 * world if self.shard_opt else 4
         if on_cuda and self.optimizer == "fused":
