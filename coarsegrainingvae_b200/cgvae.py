@@ -123,6 +123,9 @@ class EquivariantDecoder(nn.Module):
         for i, message_block in enumerate(self.message_blocks):
             H, V = message_block.fused(H, V, geom)
             H, V = self.update_blocks[i].fused(H, V)
+        if V is None:                               # num_conv = 0: the reference returns its zero-initialised vectors
+            n, f = H.shape
+            V = ops.fill((n, 3, f), 0.0, H)
         return H, (V if planar else _Unplanar.apply(V))
 
 

@@ -161,6 +161,13 @@ class Fork(object):
 GRAD_SINK = {}
 
 
+def _has_sink(param):
+    """the parameter's gradient region of a flat buffer will be ADOPTED by autograd (registered sink, no gradient yet): the
+    only situation in which a deferred (still unwritten) gradient tensor may be returned from a backward node -- with
+    gradient accumulation or a parameter used twice autograd would add the uninitialised tensor before the flush."""
+    return (param is not None and bool(GRAD_SINK) and param.grad is None and GRAD_SINK.get(param.data_ptr()) is not None)
+
+
 def _grad_out(param, shape):
     hit = GRAD_SINK.get(param.data_ptr()) if GRAD_SINK else None
     if hit is None or param.grad is not None:
@@ -419,6 +426,9 @@ def _tickets(dev, stream):
 def gemm(form, A, B, M, N, K, bias=None, act=0, z_out=False, z_in=None, dact=0, add=None, out=None):
     """C[M,N] = epilogue(op(A) op(B)); see cgvae_gemm in the header.  A, B 2-D contiguous views."""
     _need_cuda(A, B)
+    if A.dtype != torch.float32 or B.dtype != torch.float32 or A.stride(-1) != 1 or B.stride(-1) != 1:
+        raise RuntimeError("gemm: operands must be float32 with unit inner stride (got %s %s, %s %s)"
+                           % (A.dtype, tuple(A.stride()), B.dtype, tuple(B.stride())))
     lib = _lib.load()
     dev = A.device
     C = out if out is not None else torch.empty((M, N), dtype=torch.float32, device=dev)
@@ -601,9 +611,7 @@ def linear_bwd_weight(gy, x, param=None):
     rows, n_out = gy.shape
     n_in = x.shape[1]
     out = _grad_out(param, (n_out, n_in)) if param is not None else None
-    if deferring(rows) and gy.is_cuda and gy.stride(1) == 1 and x.stride(1) == 1:
-        if out is None:
-            out = torch.empty((n_out, n_in), dtype=torch.float32, device=gy.device)
+    if deferring(rows) and _has_sink(param) and gy.is_cuda and gy.stride(1) == 1 and x.stride(1) == 1:
         # record an ALIAS of the output: autograd only adopts a returned gradient without copying when nothing else
         # references the tensor object (AccumulateGrad's use_count test); gy / x are recorded as they are so that
         # nobody accumulates into them in place before the flush
@@ -617,7 +625,7 @@ def colsum(X, param=None):
     lib = _lib.load()
     M, N = X.shape
     out = _grad_out(param, (N,)) if param is not None else torch.empty(N, dtype=torch.float32, device=X.device)
-    if deferring(M) and X.stride(1) == 1:
+    if deferring(M) and _has_sink(param) and X.stride(1) == 1:
         _DEFERRED.append((X, None, None, out.detach()))
         return out
     _lib.check(lib.cgvae_colsum(_p(X), X.stride(0), M, N, _p(out), _stream()), "colsum")
