@@ -59,6 +59,8 @@ SIGNATURES = {
     "cgvae_update_combine_fwd": (_INT, [_P, _P, _P, _P, _P, _I64, _INT, _INT, _P, _P, _P]),
     "cgvae_update_combine_bwd": (_INT, [_P, _P, _P, _P, _P, _I64, _INT, _P, _P, _P, _P]),
     "cgvae_update_norm_bwd": (_INT, [_P, _P, _P, _P, _I64, _INT, _INT, _P, _P, _P]),
+    "cgvae_update_combine_bwd_ld": (_INT, [_P, _P, _P, _P, _P, _I64, _INT, _P, _P, _P, _I64, _P]),
+    "cgvae_update_norm_bwd_ld": (_INT, [_P, _P, _P, _P, _I64, _INT, _INT, _P, _P, _I64, _P]),
     "cgvae_segment_reduce_fwd": (_INT, [_P, _P, _P, _I64, _I64, _INT, _P, _P]),
     "cgvae_segment_reduce_bwd": (_INT, [_P, _P, _P, _I64, _I64, _INT, _P, _P]),
     "cgvae_gather_rows": (_INT, [_P, _P, _I64, _I64, _I64, _P, _P]),

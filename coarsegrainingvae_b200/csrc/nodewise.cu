@@ -46,13 +46,16 @@ __global__ void __launch_bounds__(256) update_combine_bwd_kernel(const float* __
                                                                  const float* __restrict__ q, const float* __restrict__ g_s,
                                                                  const float* __restrict__ g_v, int64_t N, int F,
                                                                  float* __restrict__ gq, float* __restrict__ gUv,
-                                                                 float* __restrict__ gVv) {
+                                                                 float* __restrict__ gVv, int64_t ldg) {
+  // ldg: row pitch (floats) of gUv / gVv viewed as [3N][.]: F for two separate tensors, 2F when they are the two column
+  // halves of ONE [3N][2F] matrix (the input gradient through u_mat and v_mat is then a single contraction over 2F)
   CGVAE_KERNEL_PROLOGUE();
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= N * F) return;
   const int64_t n = idx / F;
   const int f = (int)(idx % F);
   const int64_t o = n * 3 * F + f;
+  const int64_t og = n * 3 * ldg + f;
   const float a_vv = q[o], a_sv = q[o + F];
   const float gs = g_s[idx];
   float inner = 0.f, g_avv = 0.f;
@@ -62,8 +65,8 @@ __global__ void __launch_bounds__(256) update_combine_bwd_kernel(const float* __
     const float u = Uv[o + (int64_t)c * F], w = Vv[o + (int64_t)c * F], g = g_v[o + (int64_t)c * F];
     inner = fmaf(u, w, inner);
     g_avv = fmaf(g, u, g_avv);
-    gUv[o + (int64_t)c * F] = g * a_vv + t * w;
-    gVv[o + (int64_t)c * F] = t * u;
+    gUv[og + (int64_t)c * ldg] = g * a_vv + t * w;
+    gVv[og + (int64_t)c * ldg] = t * u;
   }
   gq[o] = g_avv;
   gq[o + F] = gs * inner;
@@ -73,7 +76,7 @@ __global__ void __launch_bounds__(256) update_combine_bwd_kernel(const float* __
 __global__ void __launch_bounds__(256) update_norm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ Vv,
                                                               const float* __restrict__ gx, const float* __restrict__ g_s,
                                                               int64_t N, int F, int residual, float* __restrict__ gs_in,
-                                                              float* __restrict__ gVv) {
+                                                              float* __restrict__ gVv, int64_t ldg) {
   CGVAE_KERNEL_PROLOGUE();
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= N * F) return;
@@ -81,9 +84,9 @@ __global__ void __launch_bounds__(256) update_norm_bwd_kernel(const float* __res
   const int f = (int)(idx % F);
   gs_in[idx] = (residual ? g_s[idx] : 0.f) + gx[n * 2 * F + f];
   const float scale = gx[n * 2 * F + F + f] / x[n * 2 * F + F + f];
-  const int64_t o = n * 3 * F + f;
+  const int64_t o = n * 3 * F + f, og = n * 3 * ldg + f;
 #pragma unroll
-  for (int c = 0; c < 3; ++c) gVv[o + (int64_t)c * F] = fmaf(scale, Vv[o + (int64_t)c * F], gVv[o + (int64_t)c * F]);
+  for (int c = 0; c < 3; ++c) gVv[og + (int64_t)c * ldg] = fmaf(scale, Vv[o + (int64_t)c * F], gVv[og + (int64_t)c * ldg]);
 }
 
 // out[b][w] = sum over the bead's atoms (ascending) of X[a][w], optionally / max(count, 1)
@@ -254,14 +257,31 @@ int cgvae_update_combine_bwd(const float* Uv, const float* Vv, const float* q, c
                              float* gq, float* gUv, float* gVv, cgvae_stream_t stream) {
   if (N == 0) return 0;
   CGVAE_REQUIRE(Uv && Vv && q && g_s && g_v && gq && gUv && gVv, "update_combine_bwd: null pointer");
-  launch_kernel(update_combine_bwd_kernel, dim3((unsigned)ceil_div(N * F, 256)), dim3(256), 0, (cudaStream_t)stream, Uv, Vv, q, g_s, g_v, N, F, gq, gUv, gVv);
+  launch_kernel(update_combine_bwd_kernel, dim3((unsigned)ceil_div(N * F, 256)), dim3(256), 0, (cudaStream_t)stream, Uv, Vv, q, g_s, g_v, N, F, gq, gUv, gVv, (int64_t)F);
   return launched("update_combine_bwd");
 }
 int cgvae_update_norm_bwd(const float* x, const float* Vv, const float* gx, const float* g_s, int64_t N, int F, int residual,
                           float* gs_in, float* gVv, cgvae_stream_t stream) {
   if (N == 0) return 0;
   CGVAE_REQUIRE(x && Vv && gx && gs_in && gVv && (!residual || g_s), "update_norm_bwd: null pointer");
-  launch_kernel(update_norm_bwd_kernel, dim3((unsigned)ceil_div(N * F, 256)), dim3(256), 0, (cudaStream_t)stream, x, Vv, gx, g_s, N, F, residual, gs_in, gVv);
+  launch_kernel(update_norm_bwd_kernel, dim3((unsigned)ceil_div(N * F, 256)), dim3(256), 0, (cudaStream_t)stream, x, Vv, gx, g_s, N, F, residual, gs_in, gVv, (int64_t)F);
+  return launched("update_norm_bwd");
+}
+
+int cgvae_update_combine_bwd_ld(const float* Uv, const float* Vv, const float* q, const float* g_s, const float* g_v, int64_t N, int F,
+                                float* gq, float* gUv, float* gVv, int64_t ldg, cgvae_stream_t stream) {
+  if (N == 0) return 0;
+  CGVAE_REQUIRE(Uv && Vv && q && g_s && g_v && gq && gUv && gVv && ldg >= F, "update_combine_bwd_ld: bad arguments");
+  launch_kernel(update_combine_bwd_kernel, dim3((unsigned)ceil_div(N * F, 256)), dim3(256), 0, (cudaStream_t)stream, Uv, Vv, q, g_s, g_v, N, F, gq,
+                gUv, gVv, ldg);
+  return launched("update_combine_bwd");
+}
+int cgvae_update_norm_bwd_ld(const float* x, const float* Vv, const float* gx, const float* g_s, int64_t N, int F, int residual,
+                             float* gs_in, float* gVv, int64_t ldg, cgvae_stream_t stream) {
+  if (N == 0) return 0;
+  CGVAE_REQUIRE(x && Vv && gx && gs_in && gVv && (!residual || g_s) && ldg >= F, "update_norm_bwd_ld: bad arguments");
+  launch_kernel(update_norm_bwd_kernel, dim3((unsigned)ceil_div(N * F, 256)), dim3(256), 0, (cudaStream_t)stream, x, Vv, gx, g_s, N, F, residual,
+                gs_in, gVv, ldg);
   return launched("update_norm_bwd");
 }
 

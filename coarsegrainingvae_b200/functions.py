@@ -177,10 +177,20 @@ class UpdateBlockFn(Function):
         v, Uv, Vv, x, h, z, q, U, V, A0, c0, A1, c1 = ctx.saved_tensors
         g_s, g_v = g_s.contiguous(), g_v.contiguous()
         N, _, F = v.shape
-        gq, gUv, gVv = ops.update_combine_bwd(Uv, Vv, q, g_s, g_v)
+        # u_mat and v_mat adjacent in memory (the flat parameter buffer of a training step): their two input-gradient mixes
+        # share the output, so gUv / gVv are produced as the column halves of one [3N, 2F] matrix and contracted once with
+        # [U; V] ([2F, F]) -- one launch and one pass over the [3N, F] output instead of two
+        pair = (U.is_cuda and U.is_contiguous() and V.is_contiguous() and U.shape == V.shape
+                and V.data_ptr() == U.data_ptr() + 4 * U.numel()
+                and U.untyped_storage().data_ptr() == V.untyped_storage().data_ptr())     # views of ONE buffer ([U; V] view below)
+        gq, gUv, gVv = ops.update_combine_bwd(Uv, Vv, q, g_s, g_v, cat=pair)
         gq2 = gq.view(N, 3 * F)
         v2 = v.view(3 * N, F)
-        gUv2, gVv2 = gUv.view(3 * N, F), gVv.view(3 * N, F)
+        if pair:
+            gUV2 = gUv.as_strided((3 * N, 2 * F), (2 * F, 1))
+            gUv2, gVv2 = gUV2[:, :F], gUV2[:, F:]
+        else:
+            gUv2, gVv2 = gUv.view(3 * N, F), gVv.view(3 * N, F)
         fork = ops.Fork(g_s.device, enabled=not ops.deferring(3 * N))
         gz = ops.linear_bwd_input(gq2, A1, z_in=z, dact=ctx.act)
         with fork.branch():                                                 # parameter gradients: off the critical path
@@ -194,8 +204,12 @@ class UpdateBlockFn(Function):
             gc0 = ops.colsum(gz, c0)
         gs_in = ops.update_norm_bwd(x, Vv, gx, g_s, gVv, ctx.residual)      # adds the norm path into gVv in place
         fork.sync()
-        gv_in = ops.linear_bwd_input(gUv2, U, add=g_v.view(3 * N, F) if ctx.residual else None)
-        gv_in = ops.linear_bwd_input(gVv2, V, add=gv_in).view(N, 3, F)
+        if pair:
+            UV = U.as_strided((2 * F, U.shape[1]), (U.shape[1], 1))
+            gv_in = ops.linear_bwd_input(gUV2, UV, add=g_v.view(3 * N, F) if ctx.residual else None).view(N, 3, F)
+        else:
+            gv_in = ops.linear_bwd_input(gUv2, U, add=g_v.view(3 * N, F) if ctx.residual else None)
+            gv_in = ops.linear_bwd_input(gVv2, V, add=gv_in).view(N, 3, F)
         with fork.branch():
             gV = ops.linear_bwd_weight(gVv2, v2, V)
         fork.join()

@@ -863,11 +863,18 @@ def update_combine_fwd(s, v, Uv, Vv, q, residual):
     return s_out, v_out
 
 
-def update_combine_bwd(Uv, Vv, q, g_s, g_v):
+def update_combine_bwd(Uv, Vv, q, g_s, g_v, cat=False):
+    """cat: gUv and gVv are returned as the two column halves (views) of ONE [N, 3, 2F] tensor."""
     _need_cuda(Uv)
     lib = _lib.load()
     N, _, F = Uv.shape
     gq = torch.empty_like(q)
+    if cat:
+        gUV = torch.empty((N, 3, 2 * F), dtype=torch.float32, device=Uv.device)
+        gUv, gVv = gUV[:, :, :F], gUV[:, :, F:]
+        _lib.check(lib.cgvae_update_combine_bwd_ld(_p(Uv), _p(Vv), _p(q), _p(g_s), _p(g_v), N, F, _p(gq), _p(gUV), gUV.data_ptr() + 4 * F,
+                                                   2 * F, _stream()), "update_combine_bwd_ld")
+        return gq, gUv, gVv
     gUv = torch.empty_like(Uv)
     gVv = torch.empty_like(Vv)
     _lib.check(lib.cgvae_update_combine_bwd(_p(Uv), _p(Vv), _p(q), _p(g_s), _p(g_v), N, F, _p(gq), _p(gUv), _p(gVv), _stream()),
@@ -881,6 +888,10 @@ def update_norm_bwd(x, Vv, gx, g_s, gVv, residual):
     lib = _lib.load()
     N, _, F = Vv.shape
     gs_in = torch.empty((N, F), dtype=torch.float32, device=x.device)
+    if not gVv.is_contiguous():                      # column half of a [N, 3, 2F] tensor (update_combine_bwd(cat=True))
+        _lib.check(lib.cgvae_update_norm_bwd_ld(_p(x), _p(Vv), _p(gx), _p(g_s), N, F, int(bool(residual)), _p(gs_in), _p(gVv),
+                                                gVv.stride(1), _stream()), "update_norm_bwd_ld")
+        return gs_in
     _lib.check(lib.cgvae_update_norm_bwd(_p(x), _p(Vv), _p(gx), _p(g_s), N, F, int(bool(residual)), _p(gs_in), _p(gVv), _stream()),
                "update_norm_bwd")
     return gs_in

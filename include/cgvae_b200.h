@@ -255,6 +255,12 @@ int cgvae_update_combine_bwd(const float* Uv, const float* Vv, const float* q, c
 /* gs_in = g_s + gx[:, :F] ; gVv += gx[:, F:] * Vv / nrm  (nrm = x[:, F:]) */
 int cgvae_update_norm_bwd(const float* x, const float* Vv, const float* gx, const float* g_s,
                           int64_t N, int F, int residual, float* gs_in, float* gVv, cgvae_stream_t stream);
+/* The same two kernels with gUv / gVv as column halves of ONE matrix [3N][ldg] (ldg = 2F, gVv = gUv + F): the input gradient
+ * through u_mat and v_mat (conv.py:592-598; weights adjacent in memory) is then a single contraction over 2F. */
+int cgvae_update_combine_bwd_ld(const float* Uv, const float* Vv, const float* q, const float* g_s, const float* g_v, int64_t N, int F,
+                                float* gq, float* gUv, float* gVv, int64_t ldg, cgvae_stream_t stream);
+int cgvae_update_norm_bwd_ld(const float* x, const float* Vv, const float* gx, const float* g_s, int64_t N, int F, int residual,
+                             float* gs_in, float* gVv, int64_t ldg, cgvae_stream_t stream);
 
 /* ------------------------------------------------------------------ pooling and lifting */
 

@@ -309,7 +309,7 @@ def update_combine_fwd(s, v, Uv, Vv, q, residual):
     return (s + ds, v + dv) if residual else (ds, dv)
 
 
-def update_combine_bwd(Uv, Vv, q, g_s, g_v):
+def update_combine_bwd(Uv, Vv, q, g_s, g_v, cat=False):
     inner = (Uv * Vv).sum(1)
     gq = torch.stack([(g_v * Uv).sum(1), g_s * inner, g_s], 1)
     t = (g_s * q[:, 1])[:, None, :]

@@ -335,7 +335,9 @@ def test_message_layer_full_size_equivariance():
 
 def test_train_step_gradient_sink_matches_plain_autograd():
     """train.TrainStep makes the weight-gradient kernels write straight into one flat buffer (ops.GRAD_SINK); the
-    gradients must be bit-identical to the plain autograd path and alias the buffer."""
+    gradients must alias the buffer and equal the plain autograd path.  (Equal to rounding, not bitwise: with the parameters
+    laid out in one buffer u_mat and v_mat are adjacent and the update-block backward contracts [gUv | gVv] with [U; V] in ONE
+    launch over 2F instead of two launches over F -- a different summation order for everything upstream.)"""
     from coarsegrainingvae_b200.factory import build_cgvae
     from coarsegrainingvae_b200.train import TrainStep, training_loss
     cfg = dict(synthetic.CONFIGS["c1_dipeptide"])
@@ -356,7 +358,7 @@ def test_train_step_gradient_sink_matches_plain_autograd():
     assert step.flat.check_adopted()
     for k, p in model.named_parameters():
         if k in plain:
-            assert torch.equal(p.grad, plain[k]), k
+            assert rel_err(p.grad, plain[k]) < 2e-6, (k, rel_err(p.grad, plain[k]))
     # deferred mode: the small-graph weight / bias gradients come from ONE grouped launch after the backward pass
     # (different summation order than the per-layer contraction: compare to rounding)
     step.defer_grads = True
