@@ -195,14 +195,15 @@ class TrainStep(object):
         # data parallel, overlap: the decoder's parameters (83 % of the gradient bytes at chignolin) are laid out FIRST in the
         # flat buffers; a hook on the latent's gradient fires when the backward pass leaves the decoder, and their
         # all-reduce runs on a side stream while the encoder's backward (message + atom-level GEMM kernels) proceeds.
-        # Measured on 2 x B200 (chignolin, graph replay): plain all-reduce 3.30 ms per step, overlapped 3.64 ms (the NCCL
-        # kernel holds its SMs for the whole transfer and the encoder's backward slows down by more than the transfer
-        # takes: 270 MB move in 0.37 ms at 730 GB/s), factor exchange 3.46 ms -> overlap is opt-in (CGVAE_DP_OVERLAP=1).
+        # Measured on 2 x B200 (chignolin, graph replay, final build): plain all-reduce 3.39 ms per step, factor exchange
+        # 3.24-3.32 ms (default for 2 ranks), sharded optimiser 3.40 ms; overlapped exchange 3.64 ms on an earlier build (the
+        # NCCL kernel holds its SMs for the whole transfer and the encoder's backward slows down by more than the transfer
+        # takes) -> overlap is opt-in (CGVAE_DP_OVERLAP=1).
         self.dp_overlap = os.environ.get("CGVAE_DP_OVERLAP", "0") == "1"
         # sharded optimiser: reduce-scatter of the flat gradient buffer, clip + Adam on this rank's 1/world slice (global norm
         # and loss from a 1025-float all-reduce), all-gather of the parameters: the 0.35 ms HBM-bound optimiser pass (28 B per
         # parameter) shrinks world-fold.  Measured (tools/nccl_micro.py, 270 MB): 2 x B200 all-reduce 543 us vs reduce-scatter
-        # 347 + all-gather 321 us -> the pair loses more than half an Adam pass saves (3.58 vs 3.30 ms per step); 8 x B200
+        # 347 + all-gather 321 us -> the pair costs what half an Adam pass saves (3.40 vs 3.39 ms per step); 8 x B200
         # all-reduce 723 us vs 407 + 406 us -> 3.58 vs 3.72 ms per step.  "auto" = from 4 ranks; CGVAE_SHARD_OPT=0 / 1 forces.
         self.shard_opt = os.environ.get("CGVAE_SHARD_OPT", "auto")
         self._adam_ws = None
@@ -249,7 +250,7 @@ class TrainStep(object):
         overlap_ok = (self.dp_overlap and on_cuda and self.optimizer == "fused" and self._world() > 1
                       and any(k.startswith("equivaraintconv.") for k, _ in used)
                       and any(not k.startswith("equivaraintconv.") for k, _ in used))
-        want = False if want == "auto" else (want not in ("0", False, None))
+        want = (self._world() == 2 and not overlap_ok) if want == "auto" else (want not in ("0", False, None))
         self.gather_factors = bool(want and on_cuda and self.optimizer == "fused" and self.defer_grads and self._world() > 1)
         if self.gather_factors:
             params = self._deferred_last(params, batch, eps)
