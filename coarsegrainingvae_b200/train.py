@@ -839,3 +839,37 @@ class GraphedSampler(object):
         self.graph.replay()
         return self.out
 
+
+
+class ShardedGraphedSampler(object):
+    """``GraphedSampler`` with the ensemble members sharded over the ranks of a process group (BASELINE
+    config 3): member m runs on rank m % world, every rank replays ONE CUDA graph (the prior + its ceil(n_ensemble / world)
+    members) per conformation, and the geometries are exchanged with one ``all_gather``.  ``eps [n_ensemble, n_beads, F]`` must be
+    the same on every rank; the result equals ``GraphedSampler`` / ``sample_single`` on one device member by member."""
+
+    def __init__(self, model, example_batch, n_ensemble, group=None):
+        import torch.distributed as dist
+        self.group = group
+        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
+        self.n_ensemble = int(n_ensemble)
+        self.per = (self.n_ensemble + self.world - 1) // self.world
+        self.mine = [m for m in range(self.n_ensemble) if m % self.world == self.rank]
+        self.local = GraphedSampler(model, example_batch, self.per)
+        dev = self.local.eps.device
+        self._eps_local = torch.zeros_like(self.local.eps)
+        self._mine_idx = torch.tensor(self.mine, dtype=torch.int64, device=dev)
+        n_atoms = int(self.local.out.shape[1])
+        self._gathered = torch.empty((self.world, self.per, n_atoms, 3), dtype=torch.float32, device=dev)
+        members = torch.arange(self.n_ensemble, device=dev)
+        self._idx_rank, self._idx_slot = members % self.world, members // self.world
+
+    def sample(self, batch, eps):
+        import torch.distributed as dist
+        if self.mine:
+            self._eps_local[:len(self.mine)].copy_(eps.index_select(0, self._mine_idx))
+        out = self.local.sample(batch, self._eps_local)
+        if self.world == 1:
+            return out[:self.n_ensemble]
+        dist.all_gather_into_tensor(self._gathered, out.contiguous(), group=self.group)
+        return self._gathered[self._idx_rank, self._idx_slot]          # member m = slot m // world of rank m % world

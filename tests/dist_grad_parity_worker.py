@@ -153,6 +153,15 @@ eps_m = torch.randn(n_ens, ncg, F, generator=torch.Generator().manual_seed(11)).
 want = sample_single(model, one, n_ens, eps_m, reconstruct=False)[0]
 got = sample_ensemble_sharded(model, one, n_ens, eps_m)
 assert got.shape == want.shape and torch.equal(got, want), float((got - want).abs().max())
+# ... and as one CUDA graph per rank (ShardedGraphedSampler) over a static-capacity batch
+from coarsegrainingvae_b200.train import ShardedGraphedSampler
+cpu_one = cg.CG_collate(samples[:1])
+caps1 = {"nbr_list": 22 * 21 // 2, "CG_nbr_list": ncg * (ncg - 1) // 2 + 1, "bond_edge_list": cpu_one["bond_edge_list"].shape[0] + 4}
+static_one = to_dev(to_static_batch(cpu_one, caps1))
+ss = ShardedGraphedSampler(model, static_one, n_ens)
+got_g = ss.sample(static_one, eps_m)
+assert got_g.shape == want.shape and float((got_g - want).abs().max() / want.abs().max()) < 1e-6
+ss = None
 dist.barrier()
 if rank == 0:
     print("DIST_GRAD_PARITY_OK world=%d worst_rel_err=%.2e modes=%s" % (world, worst_all, ",".join(modes)), flush=True)
