@@ -122,6 +122,46 @@ __device__ __forceinline__ void store_block_mode(const Ep& ep, const float* __re
     }
   }
 }
+// one element through the epilogue variant MODE (see ep_mode)
+template <int MODE>
+__device__ __forceinline__ float ep_apply_mode(const Ep& ep, float v, int64_t m, int64_t n, int64_t ldc) {
+  if (MODE == 0) return v;
+  if (MODE == 1) return v + __ldg(ep.bias + n);
+  if (MODE == 2) return swish_f(v + __ldg(ep.bias + n));
+  if (MODE == 4) return v * dswish_f(__ldg(ep.z_in + m * ldc + n));
+  if (MODE == 5) return v + __ldg(ep.add + m * ldc + n);
+  if (MODE == 6) {
+    const float zz = v + __ldg(ep.bias + n);
+    ep.z_out[m * ldc + n] = zz;
+    return swish_f(zz);
+  }
+  return ep_apply(ep, v, m, n, ldc);
+}
+// rows [r_lo, r_hi) of the output tile = sum of the S parked partial tiles of the cluster in rank order, through the epilogue
+template <int MODE>
+__device__ __forceinline__ void cluster_reduce_rows(const Ep& ep, cg::cluster_group& cluster, float* P, int S, int r_lo, int r_hi, int tid,
+                                                    float* __restrict__ C, int64_t ldc, int64_t m0, int64_t n0, int64_t M, int64_t N) {
+  for (int idx = tid; idx < (r_hi - r_lo) * (BN / 4); idx += NUM_THREADS) {
+    const int row = r_lo + idx / (BN / 4), c4 = (idx % (BN / 4)) * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int rk = 0; rk < S; ++rk) {
+      const float4 v = *reinterpret_cast<const float4*>(cluster.map_shared_rank(P, rk) + row * PS + c4);
+      acc.x += v.x;
+      acc.y += v.y;
+      acc.z += v.z;
+      acc.w += v.w;
+    }
+    const int64_t m = m0 + row, n = n0 + c4;
+    if (m < M) {
+      float* dst = C + m * ldc + n;
+      if (n + 0 < N) dst[0] = ep_apply_mode<MODE>(ep, acc.x, m, n + 0, ldc);
+      if (n + 1 < N) dst[1] = ep_apply_mode<MODE>(ep, acc.y, m, n + 1, ldc);
+      if (n + 2 < N) dst[2] = ep_apply_mode<MODE>(ep, acc.z, m, n + 2, ldc);
+      if (n + 3 < N) dst[3] = ep_apply_mode<MODE>(ep, acc.w, m, n + 3, ldc);
+    }
+  }
+}
+
 __device__ __forceinline__ void store_block(int mode, const Ep& ep, const float* __restrict__ tr, int lane, float* __restrict__ C,
                                             int64_t ldc, int64_t m_base, int64_t n, int64_t M, int64_t N) {
   switch (mode) {                       // warp-uniform
@@ -400,23 +440,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     cluster.sync();
     const int rows_per = (BM + S - 1) / S;
     const int r_lo = z * rows_per, r_hi = min(BM, r_lo + rows_per);
-    for (int idx = tid; idx < (r_hi - r_lo) * (BN / 4); idx += NUM_THREADS) {
-      const int row = r_lo + idx / (BN / 4), c4 = (idx % (BN / 4)) * 4;
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int rk = 0; rk < S; ++rk) {
-        const float4 v = *reinterpret_cast<const float4*>(cluster.map_shared_rank(P, rk) + row * PS + c4);
-        acc.x += v.x;
-        acc.y += v.y;
-        acc.z += v.z;
-        acc.w += v.w;
-      }
-      const int64_t m = m0 + row, n = n0 + c4;
-      if (m < M) {
-        if (n + 0 < N) C[m * ldc + n + 0] = ep_apply(ep, acc.x, m, n + 0, ldc);
-        if (n + 1 < N) C[m * ldc + n + 1] = ep_apply(ep, acc.y, m, n + 1, ldc);
-        if (n + 2 < N) C[m * ldc + n + 2] = ep_apply(ep, acc.z, m, n + 2, ldc);
-        if (n + 3 < N) C[m * ldc + n + 3] = ep_apply(ep, acc.w, m, n + 3, ldc);
-      }
+    switch (ep_mode(ep)) {           // CTA-uniform
+      case 0: cluster_reduce_rows<0>(ep, cluster, P, S, r_lo, r_hi, tid, C, ldc, m0, n0, M, N); break;
+      case 1: cluster_reduce_rows<1>(ep, cluster, P, S, r_lo, r_hi, tid, C, ldc, m0, n0, M, N); break;
+      case 2: cluster_reduce_rows<2>(ep, cluster, P, S, r_lo, r_hi, tid, C, ldc, m0, n0, M, N); break;
+      case 4: cluster_reduce_rows<4>(ep, cluster, P, S, r_lo, r_hi, tid, C, ldc, m0, n0, M, N); break;
+      case 5: cluster_reduce_rows<5>(ep, cluster, P, S, r_lo, r_hi, tid, C, ldc, m0, n0, M, N); break;
+      case 6: cluster_reduce_rows<6>(ep, cluster, P, S, r_lo, r_hi, tid, C, ldc, m0, n0, M, N); break;
+      default: cluster_reduce_rows<3>(ep, cluster, P, S, r_lo, r_hi, tid, C, ldc, m0, n0, M, N); break;
     }
     cluster.sync();                  // nobody leaves while a peer may still read its partial tile
   }

@@ -18,6 +18,7 @@ constexpr int WG_MAXP = 48;   // problems per launch (72-byte entries: the table
 constexpr int WG_ROWS = 32;   // rows staged per pass
 constexpr int WG_T = 64;      // output tile edge
 constexpr int WG_STRIP = 4;   // output tiles along n_in per CTA
+constexpr int WG_FAST_ROWS = 16;   // up to this many rows the whole strip of x is staged at once
 
 struct WgradBatch {
   cgvae_wgrad_problem p[WG_MAXP];
@@ -104,6 +105,67 @@ __global__ void __launch_bounds__(256) wgrad_grouped_kernel(const __grid_constan
     if (tid < WG_T && n0 + tid < n_out) db[n0 + tid] = bsum;
   }
   if (!has_w) return;
+  if (rows <= WG_FAST_ROWS) {
+    // few rows (12-bead layers): the x columns of ALL WG_STRIP tiles of the strip are staged at once -- one global-load latency
+    // per CTA instead of one per tile (each tile was a load -> sync -> 12 FMA -> store chain)
+    __shared__ __align__(16) float xw[WG_FAST_ROWS][WG_STRIP * WG_T];
+    const int ncol4 = WG_STRIP * WG_T / 4;
+    for (int idx = tid; idx < rows * ncol4; idx += 256) {
+      const int r = idx / ncol4, c = 4 * (idx % ncol4);
+      float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float* q;
+      if (seg_rows > 0) {
+        const int sgm = r / seg_rows;
+        q = x + (int64_t)sgm * sx + (int64_t)(r - sgm * seg_rows) * ldx + kstrip + c;
+      } else {
+        q = x + (int64_t)r * ldx + kstrip + c;
+      }
+      if (x_vec && kstrip + c + 3 < n_in) {
+        val = __ldg(reinterpret_cast<const float4*>(q));
+      } else {
+        if (kstrip + c + 0 < n_in) val.x = __ldg(q + 0);
+        if (kstrip + c + 1 < n_in) val.y = __ldg(q + 1);
+        if (kstrip + c + 2 < n_in) val.z = __ldg(q + 2);
+        if (kstrip + c + 3 < n_in) val.w = __ldg(q + 3);
+      }
+      *reinterpret_cast<float4*>(&xw[r][c]) = val;
+    }
+    __syncthreads();                                 // gs (staged above: one_chunk) and xw complete
+#pragma unroll
+    for (int kk = 0; kk < WG_STRIP; ++kk) {
+      const int k0 = kstrip + kk * WG_T;
+      if (k0 >= n_in) break;
+      float acc[4][4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+      for (int r = 0; r < rows; ++r) {               // rows in order: the same sums as the general path
+        const float4 g4 = *reinterpret_cast<const float4*>(&gs[r][4 * ty]);
+        const float4 x4 = *reinterpret_cast<const float4*>(&xw[r][kk * WG_T + 4 * tx]);
+        const float g[4] = {g4.x, g4.y, g4.z, g4.w}, xv[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(g[a], xv[b], acc[a][b]);
+      }
+      const int k = k0 + 4 * tx;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int n = n0 + 4 * ty + a;
+        if (n >= n_out) continue;
+        float* dst = dW + (int64_t)n * n_in + k;
+        if (w_vec && k + 3 < n_in) {
+          *reinterpret_cast<float4*>(dst) = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
+        } else {
+#pragma unroll
+          for (int b = 0; b < 4; ++b)
+            if (k + b < n_in) dst[b] = acc[a][b];
+        }
+      }
+    }
+    return;
+  }
   for (int kk = 0; kk < WG_STRIP; ++kk) {
     const int k0 = kstrip + kk * WG_T;
     if (k0 >= n_in) break;
