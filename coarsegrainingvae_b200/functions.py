@@ -196,7 +196,8 @@ class UpdateBlockFn(Function):
         with fork.branch():                                                 # parameter gradients: off the critical path
             gA1 = ops.linear_bwd_weight(gq2, h, A1)
             gc1 = ops.colsum(gq2, c1)
-            gU = ops.linear_bwd_weight(gUv2, v2, U)
+            if not pair:
+                gU = ops.linear_bwd_weight(gUv2, v2, U)
         fork.sync()
         gx = ops.linear_bwd_input(gz, A0)
         with fork.branch():
@@ -211,7 +212,12 @@ class UpdateBlockFn(Function):
             gv_in = ops.linear_bwd_input(gUv2, U, add=g_v.view(3 * N, F) if ctx.residual else None)
             gv_in = ops.linear_bwd_input(gVv2, V, add=gv_in).view(N, 3, F)
         with fork.branch():
-            gV = ops.linear_bwd_weight(gVv2, v2, V)
+            if pair:
+                # [gU; gV] = [gUv | gVv]^T v: one contraction into the adjacent gradient regions of u_mat and v_mat
+                gUVw = ops.linear_bwd_weight(gUV2, v2, U, shape=(2 * F, U.shape[1]))
+                gU, gV = gUVw[:F], gUVw[F:]
+            else:
+                gV = ops.linear_bwd_weight(gVv2, v2, V)
         fork.join()
         return None, None, gs_in, gv_in, gU, gV, gA0, gc0, gA1, gc1
 

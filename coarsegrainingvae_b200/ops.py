@@ -606,10 +606,13 @@ def flush_deferred(pending):
     wgrad_grouped(merge_deferred(pending))
 
 
-def linear_bwd_weight(gy, x, param=None):
-    """gW[out,in] = gy^T x (written into the parameter's gradient sink when one is registered)"""
+def linear_bwd_weight(gy, x, param=None, shape=None):
+    """gW[out,in] = gy^T x (written into the parameter's gradient sink when one is registered).  shape: the output covers
+    SEVERAL parameters adjacent in the flat buffers, starting at ``param`` (u_mat / v_mat of an UpdateBlock: [2F, F])."""
     rows, n_out = gy.shape
     n_in = x.shape[1]
+    if shape is not None and tuple(shape) != (n_out, n_in):
+        raise ValueError("linear_bwd_weight: shape %s does not match gy^T x = (%d, %d)" % (tuple(shape), n_out, n_in))
     out = _grad_out(param, (n_out, n_in)) if param is not None else None
     if deferring(rows) and _has_sink(param) and gy.is_cuda and gy.stride(1) == 1 and x.stride(1) == 1:
         # record an ALIAS of the output: autograd only adopts a returned gradient without copying when nothing else
