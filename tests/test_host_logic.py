@@ -191,3 +191,56 @@ def test_torch_library_ops_are_registered_and_cuda_only():
         assert tuple(y.shape) == (12, 1800) and tuple(a1.shape) == (12, 600) == tuple(z1.shape)
     with pytest.raises((NotImplementedError, RuntimeError)):
         torch.ops.cgvae_b200.dense(torch.zeros(2, 4), torch.zeros(3, 4), None)
+
+
+def test_pcn_train_step_and_static_batch_cpu():
+    """PCNTrainStep on the torch-optimiser path (emulated kernels): its loss is the oracle's restatement of the PCN loop
+    (scripts/pcn_utils.py:160-183: MSE + gamma * bond term + kappa * dihedral term), the guard sits at gamma * 300, and
+    to_static_pcn_batch pads every index list with its live count (the padded batch gives the same loss)."""
+    from coarsegrainingvae_b200 import synthetic, train
+    from coarsegrainingvae_b200.factory import build_pcn
+    from oracle import cgvae_oracle as orc
+    from oracle import graph_oracle as gorc
+    from tests.golden_util import rel_err
+    cfg = dict(synthetic.CONFIGS["c4_protein"])
+    cfg.update(n_res=12, n_basis=32)
+    rad = lambda xyz, c: gorc.radius_graph(np.asarray(xyz, dtype=np.float32), c)
+    raw = synthetic.pcn_batch(cfg, 0, rad, n_proteins=2)
+    torch.manual_seed(0)
+    model = build_pcn(cfg["n_basis"], cfg["n_rbf"], cfg["cg_cutoff"], 2)
+    gamma, kappa = 2.0, 0.5
+    tr = train.PCNTrainStep(model, gamma, kappa, optimizer="torch")
+    assert tr.loss_limit == gamma * 300.0 and tr.beta == 0.0
+    out = model(raw)
+    want = orc.pcn_loss(out[5].detach().double(), raw["xyz"].double(), raw["bond_edge_list"], raw["dihe_idxs"], gamma, kappa)[0]
+    got = tr._loss(raw, None)
+    assert rel_err(got, want) < 1e-5
+    caps = {"CG_nbr_list": raw["CG_nbr_list"].shape[0] + 7, "bond_edge_list": raw["bond_edge_list"].shape[0] + 5,
+            "dihe_idxs": raw["dihe_idxs"].shape[0] + 3, "ca_idx": raw["ca_idx"].shape[0] + 2}
+    sb = train.to_static_pcn_batch(raw, caps)
+    for key, cnt in (("CG_nbr_list", "CG_nbr_count"), ("bond_edge_list", "bond_count"), ("dihe_idxs", "dihe_count"), ("ca_idx", "ca_count")):
+        n = int(sb[cnt])
+        assert sb[key].shape[0] == caps[key] and n == raw[key].shape[0]
+        assert torch.equal(sb[key][:n], raw[key]) and int(sb[key][n:].abs().sum()) == 0
+    assert "seq" not in sb and sb["CG_nbr_symmetrize"] is True
+    assert rel_err(tr._loss(sb, None), want) < 1e-5
+    # one optimiser step moves the parameters; a loss past the guard does not
+    tr.prepare(sb, None)
+    before = [p.detach().clone() for p in tr.flat.params]
+    tr.step(sb, None)
+    assert any(not torch.equal(a, p) for a, p in zip(before, tr.flat.params))
+    after = [p.detach().clone() for p in tr.flat.params]
+    tr.loss_limit = 0.0
+    tr.step(sb, None)
+    assert all(torch.equal(a, p) for a, p in zip(after, tr.flat.params)) and tr.skipped_steps() == 1
+
+
+def test_device_dataset_and_metrics_refuse_cpu():
+    """the round-2 device-side helpers have no CPU path either."""
+    from coarsegrainingvae_b200 import metrics
+    from coarsegrainingvae_b200.data import DeviceCGDataset
+    xyz = np.zeros((2, 4, 3), dtype=np.float32)
+    with pytest.raises(RuntimeError):
+        DeviceCGDataset(np.ones(4), xyz, np.array([0, 0, 1, 1]), np.array([[0, 1]]), 3.0, 5.0, device="cpu")
+    with pytest.raises(RuntimeError):
+        metrics.get_bond_graphs(torch.zeros(4, 3), torch.ones(4, dtype=torch.int64))
