@@ -93,7 +93,7 @@ __device__ __forceinline__ void store_block_mode(const Ep& ep, const float* __re
   const int rows = (int)min((int64_t)32, M - m_base);
   float* dst = C + m_base * ldc + n;
   const float b = (MODE == 1 || MODE == 2 || MODE == 6) ? __ldg(ep.bias + n) : 0.f;
-  if (MODE == 4 || MODE == 5) {
+  if constexpr (MODE == 4 || MODE == 5) {
     // the second operand of the epilogue (z_in / add) is as large as the output: all 32 row loads of this block are issued
     // before the first is used -- read one by one inside the store loop (4 in flight per warp) this epilogue ran at ~0.3 TB/s
     const float* aux = ((MODE == 4) ? ep.z_in : ep.add) + m_base * ldc + n;
@@ -107,18 +107,18 @@ __device__ __forceinline__ void store_block_mode(const Ep& ep, const float* __re
         dst[(int64_t)rr * ldc] = (MODE == 4) ? v * dswish_f(a[rr]) : v + a[rr];
       }
     }
-    return;
-  }
+  } else {
 #pragma unroll 4
-  for (int rr = 0; rr < rows; ++rr, dst += ldc) {
-    float v = tr[rr * 33 + lane];
-    if (MODE == 3) {
-      *dst = ep_apply(ep, v, m_base + rr, n, ldc);
-    } else {
-      v += b;
-      if (MODE == 6) ep.z_out[(m_base + rr) * ldc + n] = v;
-      if (MODE == 2 || MODE == 6) v = swish_f(v);
-      *dst = v;
+    for (int rr = 0; rr < rows; ++rr, dst += ldc) {
+      float v = tr[rr * 33 + lane];
+      if (MODE == 3) {
+        *dst = ep_apply(ep, v, m_base + rr, n, ldc);
+      } else {
+        v += b;
+        if (MODE == 6) ep.z_out[(m_base + rr) * ldc + n] = v;
+        if (MODE == 2 || MODE == 6) v = swish_f(v);
+        *dst = v;
+      }
     }
   }
 }
