@@ -11,11 +11,15 @@ training loop (scripts/utils.py:112-157): make_directed + CSR build + edge geome
 
 Prints ONE JSON line (rank 0).  `value` = conformations/s with the batch resident in HBM; `e2e` = the same through
 the public API from pinned HOST buffers with the H2D copy and the D2H loss read inside the timed region;
-`roofline` = the dominant kernel (fused message layer on the atom graph) timed live with CUDA events;
-`cpu_baseline` = the CPU oracle port of the reference on this box's host cores, bounded sample.
+`kernel_family_shares` = CUPTI timeline of graph replays grouped into kernel families; `roofline` = the modelled family
+with the largest share of the step (algorithmic bytes or flops of one step / its kernel time, against MEASURED_PEAKS.json),
+all modelled families in `roofline_kernels`; `hbm_floor` = the step's compulsory HBM traffic / measured bandwidth;
+`other_workloads` = BASELINE configs 3 / 4 / 5 (ensemble sampling, PCN protein step, one layer at 20 000 atoms);
+`cpu_baseline` = the UNMODIFIED reference (baseline/_ref, tools/install_reference.sh) on this box's host cores, bounded
+sample (the oracle port only if the reference install is missing).
 
---impl reference: times the reference algorithm's CPU implementation (the oracle port: the reference is pure
-Python/PyTorch, so there is no oracle/_ref binary) on the host cores for the same metric / config.
+--impl reference: times the unmodified reference's own training step (its CPU PyTorch path, all host threads) for the
+same metric / config; under torchrun only rank 0 runs and prints.
 """
 import argparse
 import json
@@ -30,10 +34,15 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-# DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) at the chignolin shapes, from the committed
-# ncu --set full capture profiles/r1b_ncu_full_hot_kernels_raw.csv (tools/profile_kernels.py)
-NCU_DRAM_BYTES = {"message_atom_fwd": 15.0e6, "message_atom_bwd": 12.5e6}
-NCU_SOURCE = ("profiles/r2_ncu_message_tc_fwd_raw.csv (forward, tensor-core kernel) / profiles/r1b_ncu_full_hot_kernels_raw.csv "
+# DRAM traffic of ONE launch (dram__bytes_read.sum + dram__bytes_write.sum) at the chignolin shapes, from the committed
+# ncu --set full captures of tools/profile_kernels.py: profiles/r2_ncu_message_tc_fwd_raw.csv (message forward on the atom
+# graph) and profiles/r2_ncu_full_hot_kernels_raw.csv (message backward; the 5400 x 600 weight matrix streamed by the NT
+# kernel: 12.96 MB algorithmic; the 350 x 1800 x 600 NT problem of the tcgen05 GEMM: 5.6 MB of operands + output)
+NCU_DRAM_BYTES = {"message_atom_fwd": 17.5e6, "message_atom_bwd": 12.5e6, "gemm_stream": 13.06e6, "gemm_tcgen05": 5.24e6}
+NCU_TRAFFIC_NOTE = {"gemm_stream": "one NT launch streaming the 5400 x 600 matrix (12.96 MB algorithmic; the NN launch reads 13.25 MB): "
+                                   "the matrix is read exactly once",
+                    "gemm_tcgen05": "one NT launch 350 x 1800 x 600 (reads only: the 2.5 MB output had not been written back yet)"}
+NCU_SOURCE = ("profiles/r2_ncu_message_tc_fwd_raw.csv (forward, tensor-core kernel) / profiles/r2_ncu_full_hot_kernels_raw.csv "
               "(backward): same shapes")
 
 METRIC = "conformations/s (fwd+bwd train step)"
@@ -646,8 +655,8 @@ def run_cuda(args, cfg):
         "message_atom_fwd": ("tensor", "message_tc_fwd_kernel (filter on tcgen05, 3xTF32)" if tc_fwd else "message_fwd_kernel<3,%d>" % (ops.rb_for(R) // 4),
                              "filter flops 2(R+1)*3F per directed edge"),
         "message_atom_bwd": ("tensor", "message_bwd_kernel<3,%d> (fp32 SIMT)" % (ops.rb_for(R) // 4), "2x the forward filter flops"),
-        "gemm_simt": ("tensor", "gemm_kernel<64,64,16,4,4> family (fp32 SIMT tiles: atom-level Dense layers and their gradients)", "2MNK per call"),
-        "gemm_tcgen05": ("tensor", "tc::gemm_tc_kernel (tcgen05, 3xTF32)", "2MNK per call"),
+        "gemm_simt": ("tensor", "gemm_kernel<48,32,32,3,2> family (fp32 SIMT tiles with cluster split-K: the 36-row update-block mixes of the 12-bead decoder)", "2MNK per call"),
+        "gemm_tcgen05": ("tensor", "tc::gemm_tc_kernel (tcgen05, 3xTF32: every contraction with >= 64 rows -- atom-level Dense layers, input and weight gradients)", "2MNK per call"),
         "gemm_stream": ("hbm", "gemm_nt_stream / gemm_nn_stream (12-bead Dense layers, TMA weight streaming)", "the weight matrix once per launch"),
         "wgrad_grouped": ("hbm", "wgrad_grouped_kernel (small-graph weight / bias gradients)", "gradients written once"),
         "adam_clip": ("hbm", "sumsq_partial + adam_clip_kernel", "4 (norm pass) + 28 (p, g, m, v read; p, m, v written) bytes per parameter"),
@@ -668,6 +677,9 @@ def run_cuda(args, cfg):
                       "traffic": NCU_DRAM_BYTES.get(fam), "algorithmic_work_per_step": work[fam], "work_model": per_unit,
                       "time_per_step_us": t_us, "launches_per_step": fam_launches.get(fam), "share_of_step": t_us / tot_us,
                       "peak_source": src}
+        if fam in NCU_TRAFFIC_NOTE:
+            other[fam]["traffic_source"] = ("dram__bytes_read.sum + dram__bytes_write.sum in profiles/r2_ncu_full_hot_kernels_raw.csv: "
+                                            + NCU_TRAFFIC_NOTE[fam])
         if fam.startswith("message_atom"):
             n_l = max(fam_launches.get(fam) or 1, 1)
             other[fam].update(avg_launch_us=t_us / n_l, edges_per_launch=E, edges_per_s=E / (t_us / n_l * 1e-6),
